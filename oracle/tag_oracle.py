@@ -1,0 +1,456 @@
+"""CPU oracle for the cnn8rnn-w2vmean hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, in plain fp32 PyTorch-on-CPU ops, the arithmetic the reference
+(wsntxxn/TextToAudioGrounding) performs on its strong-supervision hot path.  It is the
+checker the CUDA path is compared against; it is *never* imported by the product
+package.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import it.
+
+Parity pin: the reference holds no tests or golden vectors, so this
+oracle is pinned against outputs of the reference itself, imported read-only in the
+build container by ``oracle/make_golden.py`` and committed as ``tests/golden/*.npz``
+(see ``tests/test_oracle_golden.py``).
+
+Reference sites restated here (all relative to /root/reference):
+  * log-mel frontend ............ models/audio_encoder.py:113-124,183-184 (torchaudio
+                                  MelSpectrogram + AmplitudeToDB; algorithm lives in
+                                  torchaudio 2.11.0 `functional.spectrogram`,
+                                  `functional.melscale_fbanks`, `amplitude_to_DB`)
+  * bn0 over mel bins ........... models/audio_encoder.py:188-190
+  * ConvBlock x4 + dropout ...... models/panns.py:47-62, models/audio_encoder.py:202-211
+  * freq mean, fc1, BiGRU ....... models/audio_encoder.py:212-217
+  * length arithmetic ........... models/audio_encoder.py:219-227
+  * EmbeddingAgg (mean) ......... models/text_encoder.py:39-43,79-88; models/utils.py:33-58
+  * BiEncoder orchestration ..... models/audio_text_model.py:58-98
+  * DotProduct match ............ models/match.py:43-60
+  * Runner.forward post-step .... python_scripts/training/run_strong.py:92-120
+  * FrameBceLoss ................ losses.py:12-24; models/utils.py:22-30
+  * train step .................. python_scripts/training/run_strong.py:139-147
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+N_FFT = 1024
+HOP = 320
+N_MELS = 64
+SAMPLE_RATE = 32000
+F_MIN = 50.0
+F_MAX = 14000.0
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+VOCAB = 5221
+EMBED = 512
+HIDDEN = 256
+
+CONV_CHANNELS = [(1, 64), (64, 128), (128, 256), (256, 512)]
+POOLS = [(2, 2), (2, 2), (1, 2), (1, 2)]
+
+
+# --------------------------------------------------------------------------- frontend
+def _hz_to_mel_slaney(f: float) -> float:
+    f_sp = 200.0 / 3
+    mel = f / f_sp
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = math.log(6.4) / 27.0
+    if f >= min_log_hz:
+        mel = min_log_mel + math.log(f / min_log_hz) / logstep
+    return mel
+
+
+def _mel_to_hz_slaney(mels: torch.Tensor) -> torch.Tensor:
+    f_sp = 200.0 / 3
+    freqs = f_sp * mels
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = math.log(6.4) / 27.0
+    log_t = mels >= min_log_mel
+    freqs[log_t] = min_log_hz * torch.exp(logstep * (mels[log_t] - min_log_mel))
+    return freqs
+
+
+def melscale_fbanks(n_freqs: int = N_FFT // 2 + 1, f_min: float = F_MIN,
+                    f_max: float = F_MAX, n_mels: int = N_MELS,
+                    sample_rate: int = SAMPLE_RATE) -> torch.Tensor:
+    """Slaney-scale, slaney-normalised triangular filterbank [n_freqs, n_mels]
+    (torchaudio.functional.melscale_fbanks(norm="slaney", mel_scale="slaney"))."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = _hz_to_mel_slaney(f_min)
+    m_max = _hz_to_mel_slaney(f_max)
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = _mel_to_hz_slaney(m_pts)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    fb = torch.clamp(torch.min(down, up), min=0.0)
+    enorm = 2.0 / (f_pts[2:n_mels + 2] - f_pts[:n_mels])
+    return fb * enorm.unsqueeze(0)
+
+
+def hann_window(n: int = N_FFT) -> torch.Tensor:
+    """Periodic Hann (torch.hann_window default)."""
+    k = torch.arange(n, dtype=torch.float64)
+    return (0.5 - 0.5 * torch.cos(2 * math.pi * k / n)).float()
+
+
+def power_spectrogram(waveform: torch.Tensor, window: torch.Tensor) -> torch.Tensor:
+    """[B, L] -> [B, 513, T0]; center=True, reflect pad, |rfft|^2 (power=2)."""
+    pad = N_FFT // 2
+    x = F.pad(waveform.unsqueeze(1), (pad, pad), mode="reflect").squeeze(1)
+    frames = x.unfold(-1, N_FFT, HOP)                      # [B, T0, 1024]
+    spec = torch.fft.rfft(frames * window, dim=-1)         # [B, T0, 513]
+    return (spec.real ** 2 + spec.imag ** 2).transpose(1, 2)
+
+
+def logmel_db(waveform: torch.Tensor, window: torch.Tensor, fb: torch.Tensor) -> torch.Tensor:
+    """[B, L] -> dB log-mel [B, 64, T0]  (MelScale matmul + AmplitudeToDB(power))."""
+    power = power_spectrogram(waveform, window)            # [B, 513, T0]
+    mel = torch.matmul(power.transpose(-1, -2), fb).transpose(-1, -2)
+    return 10.0 * torch.log10(torch.clamp(mel, min=1e-10))
+
+
+# --------------------------------------------------------------------------- weights
+def state_dict_spec(vocab: int = VOCAB):
+    """(key, shape, kind) for every entry of the reference BiEncoder state dict on the
+    cnn8rnn-w2vmean config (SURVEY.md §8b 'State-dict keys')."""
+    spec = []
+    ae = "audio_encoder."
+    spec.append((ae + "melspec_extractor.spectrogram.window", (N_FFT,), "window"))
+    spec.append((ae + "melspec_extractor.mel_scale.fb", (N_FFT // 2 + 1, N_MELS), "fb"))
+    def bn(prefix, c):
+        spec.append((prefix + ".weight", (c,), "bn_w"))
+        spec.append((prefix + ".bias", (c,), "bn_b"))
+        spec.append((prefix + ".running_mean", (c,), "bn_rm"))
+        spec.append((prefix + ".running_var", (c,), "bn_rv"))
+        spec.append((prefix + ".num_batches_tracked", (), "bn_n"))
+    bn(ae + "bn0", N_MELS)
+    for i, (ci, co) in enumerate(CONV_CHANNELS, 1):
+        p = f"{ae}conv_block{i}."
+        spec.append((p + "conv1.weight", (co, ci, 3, 3), "xavier"))
+        spec.append((p + "conv2.weight", (co, co, 3, 3), "xavier"))
+        bn(p + "bn1", co)
+        bn(p + "bn2", co)
+    spec.append((ae + "fc1.weight", (EMBED, EMBED), "xavier"))
+    spec.append((ae + "fc1.bias", (EMBED,), "bias"))
+    for sfx in ("", "_reverse"):
+        spec.append((f"{ae}rnn.weight_ih_l0{sfx}", (3 * HIDDEN, EMBED), "gru"))
+        spec.append((f"{ae}rnn.weight_hh_l0{sfx}", (3 * HIDDEN, HIDDEN), "gru"))
+        spec.append((f"{ae}rnn.bias_ih_l0{sfx}", (3 * HIDDEN,), "gru"))
+        spec.append((f"{ae}rnn.bias_hh_l0{sfx}", (3 * HIDDEN,), "gru"))
+    spec.append(("text_encoder.embedding.core.weight", (vocab, EMBED), "emb"))
+    return spec
+
+
+def synth_state_dict(seed: int = 1, vocab: int = VOCAB, sharpen: float = 1.0,
+                     perturb_bn: bool = False) -> Dict[str, torch.Tensor]:
+    """Implementation-independent deterministic weights: every tensor is drawn from its
+    own generator keyed by (seed, position in spec), with the reference's init
+    distributions (models/panns.py:5-17 Xavier-uniform; nn.GRU U(+-1/sqrt(H));
+    models/utils.py:18-19 Kaiming-uniform embedding).  ``sharpen`` scales the embedding
+    so logits leave the +-0.01 band of the raw init; ``perturb_bn``
+    gives BN affine/running stats non-trivial values so eval-mode parity is not vacuous."""
+    sd = {}
+    for idx, (key, shape, kind) in enumerate(state_dict_spec(vocab)):
+        g = torch.Generator().manual_seed(seed * 100003 + idx)
+        if kind == "window":
+            t = hann_window()
+        elif kind == "fb":
+            t = melscale_fbanks()
+        elif kind == "xavier":
+            if len(shape) == 4:
+                fan_out, fan_in = shape[0] * 9, shape[1] * 9
+            else:
+                fan_out, fan_in = shape
+            a = math.sqrt(6.0 / (fan_in + fan_out))
+            t = (torch.rand(shape, generator=g) * 2 - 1) * a
+        elif kind == "bias":
+            t = torch.zeros(shape)
+            if perturb_bn:
+                t = (torch.rand(shape, generator=g) * 2 - 1) * 0.1
+        elif kind == "gru":
+            a = 1.0 / math.sqrt(HIDDEN)
+            t = (torch.rand(shape, generator=g) * 2 - 1) * a
+        elif kind == "emb":
+            a = math.sqrt(6.0 / EMBED)
+            t = (torch.rand(shape, generator=g) * 2 - 1) * a * sharpen
+        elif kind == "bn_w":
+            t = torch.ones(shape)
+            if perturb_bn:
+                t = 0.75 + 0.5 * torch.rand(shape, generator=g)
+        elif kind == "bn_b":
+            t = torch.zeros(shape)
+            if perturb_bn:
+                t = (torch.rand(shape, generator=g) * 2 - 1) * 0.2
+        elif kind == "bn_rm":
+            t = torch.zeros(shape)
+            if perturb_bn:
+                if key.endswith("bn0.running_mean"):
+                    t = -10.0 + torch.rand(shape, generator=g) * 2
+                else:
+                    t = (torch.rand(shape, generator=g) * 2 - 1) * 0.3
+        elif kind == "bn_rv":
+            t = torch.ones(shape)
+            if perturb_bn:
+                if key.endswith("bn0.running_var"):
+                    t = 5.0 + 4.0 * torch.rand(shape, generator=g)
+                else:
+                    t = 0.5 + torch.rand(shape, generator=g)
+        elif kind == "bn_n":
+            t = torch.zeros((), dtype=torch.long)
+        else:
+            raise ValueError(kind)
+        sd[key] = t
+    return sd
+
+
+def synth_batch(batch: int, n_samples: int, n_tokens: int = 8, seed: int = 0,
+                vocab: int = VOCAB, ragged: bool = False, tonal: bool = True):
+    """Seeded synthetic batch in the collate schema of datasets/collate_function.py:43-84
+    (SURVEY.md §8d 'Synthetic inputs')."""
+    g = torch.Generator().manual_seed(seed)
+    wav = 0.1 * torch.randn(batch, n_samples, generator=g)
+    if tonal:
+        t = torch.arange(n_samples, dtype=torch.float32) / SAMPLE_RATE
+        for b in range(batch):
+            for k in range(3):
+                f = 110.0 * (b + 1) * (2 ** k) + 37.0 * k
+                wav[b] += 0.05 * torch.sin(2 * math.pi * f * t)
+    wav_len = [n_samples] * batch
+    text_len = [n_tokens] * batch
+    if ragged:
+        fr = [1.0, 0.9, 0.75, 0.5]
+        wav_len = [int(n_samples * fr[b % 4]) for b in range(batch)]
+        for b in range(batch):
+            wav[b, wav_len[b]:] = 0.0
+        text_len = [3 + (b * 5) % (n_tokens - 2) for b in range(batch)]
+        text_len[0] = n_tokens
+    text = torch.randint(2, vocab, (batch, n_tokens), generator=g)
+    for b in range(batch):
+        text[b, text_len[b]:] = 0
+    t_out = (n_samples // HOP + 1) // 4
+    label = (torch.rand(batch, t_out + 1, generator=g) > 0.5).float()
+    import numpy as np
+    return {
+        "waveform": wav,
+        "waveform_len": np.asarray(wav_len, dtype=np.int64),
+        "text": text,
+        "text_len": torch.as_tensor(text_len, dtype=torch.long),
+        "label": label,
+    }
+
+
+# --------------------------------------------------------------------------- model
+def _bn(x, sd, prefix, training, stages=None):
+    """BatchNorm2d forward; in training mode also updates running stats in ``sd``
+    (momentum 0.1, unbiased var) exactly as nn.BatchNorm2d does."""
+    rm, rv = sd[prefix + ".running_mean"], sd[prefix + ".running_var"]
+    if training:
+        with torch.no_grad():
+            sd[prefix + ".num_batches_tracked"] += 1
+    return F.batch_norm(x, rm if not training else rm, rv, sd[prefix + ".weight"],
+                        sd[prefix + ".bias"], training, BN_MOMENTUM, BN_EPS)
+
+
+def gru_direction(x, w_ih, w_hh, b_ih, b_hh, reverse: bool):
+    """One direction of nn.GRU, h0 = 0, gate order [r; z; n]."""
+    B, T, _ = x.shape
+    H = w_hh.shape[1]
+    gi_all = F.linear(x, w_ih, b_ih)                       # [B, T, 3H]
+    h = x.new_zeros(B, H)
+    outs = [None] * T
+    steps = range(T - 1, -1, -1) if reverse else range(T)
+    for t in steps:
+        gi = gi_all[:, t]
+        gh = F.linear(h, w_hh, b_hh)
+        r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+        z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+        h = (1.0 - z) * n + z * h
+        outs[t] = h
+    return torch.stack(outs, dim=1)
+
+
+def bigru(x, sd, prefix="audio_encoder.rnn.", fast: bool = False):
+    if fast:  # torch's fused CPU GRU (what nn.GRU calls); used for baseline timing
+        flat = [sd[prefix + n] for n in (
+            "weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0",
+            "weight_ih_l0_reverse", "weight_hh_l0_reverse", "bias_ih_l0_reverse",
+            "bias_hh_l0_reverse")]
+        h0 = x.new_zeros(2, x.shape[0], HIDDEN)
+        out, _ = torch._VF.gru(x, h0, flat, True, 1, 0.0, False, True, True)
+        return out
+    fw = gru_direction(x, sd[prefix + "weight_ih_l0"], sd[prefix + "weight_hh_l0"],
+                       sd[prefix + "bias_ih_l0"], sd[prefix + "bias_hh_l0"], False)
+    bw = gru_direction(x, sd[prefix + "weight_ih_l0_reverse"],
+                       sd[prefix + "weight_hh_l0_reverse"],
+                       sd[prefix + "bias_ih_l0_reverse"],
+                       sd[prefix + "bias_hh_l0_reverse"], True)
+    return torch.cat([fw, bw], dim=-1)
+
+
+def _dropout(x, p, training, masks, name):
+    if not training or p == 0.0:
+        return x
+    if masks is not None:
+        m = masks.get(name)
+        if m is None:
+            return x
+        return x * m            # mask already carries the 1/(1-p) scale
+    return F.dropout(x, p=p, training=True)
+
+
+def cnn8rnn_forward(sd, waveform, waveform_len, training: bool = False,
+                    dropout_masks: Optional[dict] = None, dropout: bool = True,
+                    stages: Optional[dict] = None, fast_gru: bool = False):
+    """models/audio_encoder.py:178-232 with specaug=False and no mixup.
+
+    ``dropout_masks`` (name -> multiplicative mask in NCHW / [B,T,C] layout) injects
+    explicit masks; ``dropout=False`` disables dropout in training mode (parity runs)."""
+    ae = "audio_encoder."
+    x = logmel_db(waveform, sd[ae + "melspec_extractor.spectrogram.window"],
+                  sd[ae + "melspec_extractor.mel_scale.fb"])          # [B, 64, T0]
+    if stages is not None:
+        stages["logmel_db"] = x
+    x = x.transpose(1, 2).unsqueeze(1)                                  # [B,1,T0,64]
+    x = x.transpose(1, 3)
+    x = _bn(x, sd, ae + "bn0", training)
+    if stages is not None:
+        stages["bn0"] = x            # [B, 64, T0, 1], the layout nn.BatchNorm2d sees
+    x = x.transpose(1, 3)
+    use_do = training and dropout
+    for i in range(4):
+        p = f"{ae}conv_block{i + 1}."
+        x = F.relu(_bn(F.conv2d(x, sd[p + "conv1.weight"], padding=1), sd, p + "bn1", training))
+        x = F.relu(_bn(F.conv2d(x, sd[p + "conv2.weight"], padding=1), sd, p + "bn2", training))
+        x = F.avg_pool2d(x, kernel_size=POOLS[i]) + F.max_pool2d(x, kernel_size=POOLS[i])
+        x = _dropout(x, 0.2, use_do, dropout_masks, f"block{i + 1}")
+        if stages is not None:
+            stages[f"conv_block{i + 1}"] = x
+    x = torch.mean(x, dim=3).transpose(1, 2)                            # [B, T', 512]
+    x = _dropout(x, 0.5, use_do, dropout_masks, "fc_in")
+    x = F.relu(F.linear(x, sd[ae + "fc1.weight"], sd[ae + "fc1.bias"]))
+    if stages is not None:
+        stages["fc1"] = x
+    x = bigru(x, sd, ae + "rnn.", fast=fast_gru)
+    if stages is not None:
+        stages["rnn"] = x
+    length = torch.div(torch.as_tensor(waveform_len), HOP, rounding_mode="floor") + 1
+    length = torch.div(length, 4, rounding_mode="floor")
+    return {"embedding": x, "length": length}
+
+
+def generate_length_mask(lens, max_length=None):
+    lens = torch.as_tensor(lens)
+    if max_length is None:
+        max_length = int(lens.max().item())
+    idx = torch.arange(max_length).unsqueeze(0)
+    return idx < lens.view(-1, 1)
+
+
+def embedding_mean(sd, text, text_len):
+    """models/text_encoder.py:39-43,79-88 + models/utils.py:33-58 (aggregation='mean')."""
+    emb = F.embedding(text.long(), sd["text_encoder.embedding.core.weight"])   # [B,N,D]
+    lens = torch.as_tensor(text_len)
+    mask = generate_length_mask(lens, emb.size(1)).unsqueeze(-1)
+    seq = (emb * mask).sum(1) / lens.view(-1, 1).to(emb.dtype)
+    return {"token_emb": emb, "seq_emb": seq}
+
+
+def dot_product_match(audio_emb, seq_emb, scale: bool = True):
+    """models/match.py:43-60 (l2norm=False, text_level='seq'). Returns (frame_sim, logits)."""
+    score = (audio_emb * seq_emb.unsqueeze(1)).sum(-1)
+    if scale:
+        score = score / math.sqrt(audio_emb.size(-1))
+    return torch.sigmoid(score).clamp(1e-7, 1.0), score
+
+
+def biencoder_forward(sd, input_dict, training=False, dropout_masks=None, dropout=True,
+                      stages=None, fast_gru=False):
+    """models/audio_text_model.py:58-98 (no cross encoder / projections / upsample)."""
+    a = cnn8rnn_forward(sd, input_dict["waveform"], input_dict["waveform_len"], training,
+                        dropout_masks, dropout, stages, fast_gru)
+    t = embedding_mean(sd, input_dict["text"], input_dict["text_len"])
+    frame_sim, logits = dot_product_match(a["embedding"], t["seq_emb"])
+    if stages is not None:
+        stages["seq_emb"] = t["seq_emb"]
+        stages["logits"] = logits
+    return {"frame_sim": frame_sim, "length": a["length"]}
+
+
+def runner_forward(sd, batch, training=True, **kw):
+    """python_scripts/training/run_strong.py:92-120."""
+    out = biencoder_forward(sd, batch, training=training, **kw)
+    if training:
+        label = batch["label"].float()
+        frame_sim = out["frame_sim"]
+        trunc = min(frame_sim.size(1), label.size(1))
+        out.update({
+            "frame_sim": frame_sim[..., :trunc],
+            "label": label[..., :trunc],
+            "length": torch.clamp(out["length"], 1, trunc),
+        })
+    return out
+
+
+def frame_bce_loss(output):
+    """losses.py:12-24."""
+    loss = F.binary_cross_entropy(output["frame_sim"], output["label"], reduction="none")
+    mask = generate_length_mask(output["length"]).to(loss.dtype)
+    if mask.size(1) < loss.size(1):      # generate_length_mask uses max(length) columns
+        loss = loss[:, :mask.size(1)]
+    return (loss * mask).sum() / mask.sum()
+
+
+TRAINABLE_KINDS = ("xavier", "bias", "gru", "emb", "bn_w", "bn_b")
+
+
+def trainable_keys(vocab: int = VOCAB):
+    return [k for k, _, kind in state_dict_spec(vocab) if kind in TRAINABLE_KINDS]
+
+
+class AdamState:
+    """torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8, weight_decay=0) restated."""
+    def __init__(self, keys):
+        self.step = 0
+        self.m = {k: None for k in keys}
+        self.v = {k: None for k in keys}
+
+
+def train_step(sd, batch, opt: AdamState, lr: float = 1e-3, max_grad_norm: float = 1.0,
+               dropout: bool = False, dropout_masks=None, fast_gru: bool = False):
+    """One iteration of run_strong.py:139-147: zero_grad, forward, loss, backward,
+    clip_grad_norm_(max_grad_norm) (global L2, coef = max/(norm+1e-6) clamped to 1),
+    Adam step.  Mutates ``sd`` in place.  Returns (loss, grads-before-clip, total_norm)."""
+    keys = list(opt.m.keys())
+    params = []
+    for k in keys:
+        sd[k] = sd[k].detach().requires_grad_(True)
+        params.append(sd[k])
+    out = runner_forward(sd, batch, training=True, dropout=dropout,
+                         dropout_masks=dropout_masks, fast_gru=fast_gru)
+    loss = frame_bce_loss(out)
+    grads = torch.autograd.grad(loss, params, allow_unused=True)
+    grads = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads, params)]
+    total_norm = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()
+    coef = torch.clamp(max_grad_norm / (total_norm + 1e-6), max=1.0)
+    opt.step += 1
+    b1, b2, eps = 0.9, 0.999, 1e-8
+    bc1 = 1 - b1 ** opt.step
+    bc2 = 1 - b2 ** opt.step
+    with torch.no_grad():
+        for k, p, g in zip(keys, params, grads):
+            gc = g * coef
+            if opt.m[k] is None:
+                opt.m[k] = torch.zeros_like(p)
+                opt.v[k] = torch.zeros_like(p)
+            opt.m[k].mul_(b1).add_(gc, alpha=1 - b1)
+            opt.v[k].mul_(b2).addcmul_(gc, gc, value=1 - b2)
+            denom = (opt.v[k].sqrt() / math.sqrt(bc2)).add_(eps)
+            sd[k] = (p - (lr / bc1) * opt.m[k] / denom).detach()
+    return loss.detach(), dict(zip(keys, grads)), total_norm
