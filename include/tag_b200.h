@@ -1,0 +1,128 @@
+/* tag_b200.h — C ABI of libtag_b200.so: the B200 (sm_100a) kernels of the cnn8rnn-w2vmean hot path.
+ *
+ * The reference (wsntxxn/TextToAudioGrounding) has no FFI: its "operator API" for this path is
+ * the set of torch / torchaudio library calls listed below.  Every entry point replaces one of
+ * those call sites (file:line relative to the reference root) and is bound from Python with
+ * ctypes by texttoaudiogrounding_b200/_lib.py (see INTEGRATION.md for the stub a reference
+ * maintainer would add).
+ *
+ * Conventions: every pointer is a DEVICE pointer unless stated; the caller owns all buffers
+ * (no allocation inside); calls are stream-ordered on `stream` with no internal
+ * synchronisation and are re-entrant; the return value is 0 on success, a cudaError_t value
+ * for a failed launch, or TAG_ERR_* (>= 10001) for a rejected argument.  Activations are NHWC;
+ * dtype codes: 0 = float32, 1 = bfloat16.  Conv weights are [Cout][tap][Cin] fp32, i.e. the
+ * memory of a channels_last [Cout,Cin,3,3] tensor (tap = kh*3+kw).
+ */
+#ifndef TAG_B200_H
+#define TAG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define TAG_DTYPE_F32 0
+#define TAG_DTYPE_BF16 1
+#define TAG_ERR_BAD_ARG 10001
+#define TAG_ERR_UNSUPPORTED 10002
+
+int tag_version(void);
+
+/* ---- log-mel frontend -------------------------------------------------------------------
+ * torchaudio MelSpectrogram(n_fft=win=1024, hop=320, hann, center, reflect, power=2, slaney
+ * fb) + AmplitudeToDB — models/audio_encoder.py:113-124 (construction), :183-184 (call).
+ * wav [batch, n_samples] (row stride wav_stride) -> db_out [batch, T0 = n_samples/320+1, 64].
+ * fb is the [513,64] filterbank buffer, window the 1024 Hann buffer, mel_range (optional,
+ * int[64][2]) the [lo,hi) bin support of each mel.  stats (optional, double[128], pre-zeroed)
+ * receives per-mel sum and sum of squares for bn0 (models/audio_encoder.py:188-190). */
+int tag_logmel_fwd(const float* wav, int batch, int n_samples, long wav_stride, const float* window,
+                   const float* fb, const int* mel_range, float* db_out, double* stats,
+                   cudaStream_t stream);
+
+/* ---- BatchNorm2d pieces — models/audio_encoder.py:133,188-190; models/panns.py:35-36,49-50 */
+int tag_channel_stats_f32(const float* x, long rows, int C, double* stats, cudaStream_t stream);
+int tag_bn_finalize(const double* stats, double count, int C, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps, int training,
+                    int update_running, float* scale, float* shift, float* save_mean,
+                    float* save_invstd, cudaStream_t stream);
+int tag_scale_shift_act(const void* x, int x_dtype, void* y, int y_dtype, const float* scale,
+                        const float* shift, long n, int C, int relu, cudaStream_t stream);
+
+/* ---- convolutions / dense contractions --------------------------------------------------
+ * F.conv2d(3x3, pad 1, no bias) — models/panns.py:25-33,49-50; with taps=1 the x @ W^T (+bias,
+ * relu) of fc1 and the GRU input projection — models/audio_encoder.py:140-141,216-217.
+ * tag_conv_fwd also computes dgrad when given dy and tag_weight_flip_transpose'd weights.
+ * stats (optional, double[2*Cout], pre-zeroed): per-channel sum / sum of squares of y. */
+int tag_conv_c1_fwd(const void* x, const float* w, void* y, int dtype, double* stats, int B, int H,
+                    int W, cudaStream_t stream);
+int tag_conv_c1_bwd(const void* dy, const void* x, const float* w, int dtype, float* dw, float* dx,
+                    int B, int H, int W, cudaStream_t stream);
+int tag_conv_fwd(const void* x, int x_dtype, const float* w, void* y, int y_dtype, const float* bias,
+                 int relu, double* stats, int B, int H, int W, int Cin, int Cout, int taps,
+                 cudaStream_t stream);
+int tag_conv_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype, float* dw, int B, int H,
+                   int W, int Cin, int Cout, int taps, int splits, cudaStream_t stream);
+int tag_weight_flip_transpose(const float* w, float* wt, int Co, int Ci, int taps, cudaStream_t stream);
+
+/* ---- BN + ReLU + avg+max pool + dropout — models/panns.py:50-58, audio_encoder.py:202-211 */
+int tag_bn_relu_pool_fwd(const void* y, void* out, int dtype, const float* scale, const float* shift,
+                         int B, int H, int W, int C, int ph, int pw, float dropout_p, uint64_t seed,
+                         const uint64_t* seed_dev, cudaStream_t stream);
+int tag_bn_relu_pool_bwd(int mode, const void* y, const void* dout, void* dy, int dtype,
+                         const float* scale, const float* shift, const float* mean,
+                         const float* invstd, double* red, int bn_training, int B, int H, int W, int C,
+                         int ph, int pw, float dropout_p, uint64_t seed, const uint64_t* seed_dev,
+                         cudaStream_t stream);
+/* torch.mean(x, dim=3) + transpose + dropout(0.5) — models/audio_encoder.py:212-215 */
+int tag_freq_mean_fwd(const void* x, void* out, int dtype, long rows, int Wf, int C, float dropout_p,
+                      uint64_t seed, const uint64_t* seed_dev, cudaStream_t stream);
+int tag_freq_mean_bwd(const void* dm, int dm_dtype, void* dx, int dx_dtype, long rows, int Wf, int C,
+                      float dropout_p, uint64_t seed, const uint64_t* seed_dev,
+                         cudaStream_t stream);
+int tag_dropout_mask(float* mask, long n, float dropout_p, uint64_t seed, const uint64_t* seed_dev,
+                         cudaStream_t stream);
+int tag_colsum(const void* x, int dtype, long rows, int C, float* out, cudaStream_t stream);
+int tag_bn_bwd_reduce_f32(const float* dx, const float* x, const float* mean, const float* invstd,
+                          long rows, int C, double* red, cudaStream_t stream);
+int tag_bn_param_grads(const double* red, int C, float* dgamma, float* dbeta, cudaStream_t stream);
+int tag_relu_bwd(const void* dy, int dy_dtype, const void* act, int act_dtype, void* out, int out_dtype,
+                 long n, cudaStream_t stream);
+
+/* ---- BiGRU recurrence — nn.GRU(512,256,bidirectional) models/audio_encoder.py:141,217 ---- */
+int tag_gru_fwd(const float* gi, const float* w_hh, const float* b_hh, float* out, float* gates, int B,
+                int T, cudaStream_t stream);
+int tag_gru_bwd(const float* d_out, const float* out, const float* gates, const float* w_hh, float* dgi,
+                float* dgh, float* hprev, int B, int T, cudaStream_t stream);
+
+/* ---- text encoder + match + loss — models/text_encoder.py:39-43,79-88; models/utils.py:33-58;
+ * models/match.py:43-60; losses.py:12-24 (host pointers: none) */
+int tag_embed_mean_fwd(const long long* text, const long long* text_len, const float* emb,
+                       float* token_emb, float* seq_emb, int B, int N, int D, int vocab,
+                       cudaStream_t stream);
+int tag_embed_mean_bwd(const long long* text, const long long* text_len, const float* d_seq,
+                       float* d_emb, int B, int N, int D, int vocab, cudaStream_t stream);
+int tag_dot_sigmoid_fwd(const float* audio, const float* seq, float* sim, float* logits, int B, int T,
+                        int D, float scale, cudaStream_t stream);
+int tag_dot_sigmoid_bwd(const float* d_sim, const float* sim, const float* audio, const float* seq,
+                        float* d_audio, float* d_seq, float* d_logit_ws, int B, int T, int D,
+                        float scale, cudaStream_t stream);
+int tag_frame_bce(const float* sim, long sim_stride, const float* label, long label_stride,
+                  const long long* length, int B, int Tt, float* loss_out, float* d_sim,
+                  long dsim_stride, float grad_scale, cudaStream_t stream);
+
+/* ---- optimizer step — clip_grad_norm_ + Adam, python_scripts/training/run_strong.py:143-145 */
+int tag_sumsq(const float* g, long n, double* out, cudaStream_t stream);
+int tag_clip_adam(float* p, const float* g, float* m, float* v, long n, const double* sumsq,
+                  long long* step_ptr, float grad_mult, float max_norm, float lr, float beta1,
+                  float beta2, float eps, float* norm_out, cudaStream_t stream);
+int tag_cast_f32_to_bf16(const float* x, void* y, long n, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAG_B200_H */

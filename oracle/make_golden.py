@@ -132,9 +132,25 @@ def run_case(ns, name, cfg):
           "logits range", out["eval_logits"].min(), out["eval_logits"].max())
 
 
+def init_fixture(ns):
+    """Per-tensor checksums of the reference's own initialisation under torch.manual_seed(1):
+    pins that the B200 modules draw the same initial weights for the same seed."""
+    torch.manual_seed(1)
+    model = ns.BiEncoder(ns.Cnn8Rnn(32000), ns.EmbeddingAgg(O.VOCAB, 512), ns.DotProduct(), 512)
+    out = {}
+    for k, v in model.state_dict().items():
+        if v.dtype.is_floating_point:
+            out["sum/" + k] = np.array(v.double().sum().item())
+            out["abs/" + k] = np.array(v.double().abs().sum().item())
+    np.savez_compressed(os.path.join(OUT, "init_seed1.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_shim.import_reference()
+    init_fixture(ns)
+    if os.environ.get("TAG_GOLDEN_INIT_ONLY"):
+        return
     torch.set_num_threads(os.cpu_count())
     for name, cfg in CASES.items():
         run_case(ns, name, cfg)

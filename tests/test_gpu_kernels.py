@@ -1,0 +1,270 @@
+"""Per-kernel parity through the C ABI against fp32 PyTorch / oracle restatements of the same op,
+on odd and ragged shapes (tile edges, floor-mode pooling leftovers, batch not a multiple of 8)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import tag_oracle as O
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from texttoaudiogrounding_b200 import ops
+    return ops
+
+
+def g(seed=0):
+    return torch.Generator().manual_seed(seed)
+
+
+def test_logmel_matches_oracle_incl_short_and_tonal():
+    ops = _ops()
+    from texttoaudiogrounding_b200 import engine
+    for L, B in [(64000, 3), (32000, 2), (6401, 1), (320000, 1)]:
+        batch = O.synth_batch(B, L, seed=L % 7)
+        wav = batch["waveform"]
+        window, fb = O.hann_window(), O.melscale_fbanks()
+        ref = O.logmel_db(wav, window, fb).transpose(1, 2)          # [B,T0,64]
+        T0 = L // 320 + 1
+        out = torch.empty(B, T0, 64, device="cuda")
+        stats = torch.zeros(128, device="cuda", dtype=torch.float64)
+        fbc = fb.cuda()
+        ops.call("tag_logmel_fwd", wav.cuda(), B, L, L, window.cuda(), fbc, engine.compute_mel_range(fbc),
+                 out, stats)
+        err = (out.cpu() - ref).abs().max().item()
+        assert err < 5e-3, (L, err)
+        np.testing.assert_allclose(stats[:64].cpu().numpy(), ref.double().sum((0, 1)).numpy(), rtol=1e-4)
+        # dense filterbank path (mel_range = NULL) gives the same answer
+        out2 = torch.empty_like(out)
+        ops.call("tag_logmel_fwd", wav.cuda(), B, L, L, window.cuda(), fbc, None, out2, None)
+        assert (out2 - out).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 13, 8, 64, 64), (1, 7, 16, 64, 128), (3, 5, 4, 128, 256)])
+def test_conv3x3_fwd_dgrad_wgrad_fp32(B, H, W, Cin, Cout):
+    ops = _ops()
+    x = torch.randn(B, Cin, H, W, generator=g(1))
+    w = torch.randn(Cout, Cin, 3, 3, generator=g(2)) * 0.05
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    y = F.conv2d(x, w, padding=1)
+    dy = torch.randn(y.shape, generator=g(3))
+    y.backward(dy)
+    xn = x.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    wp = w.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    yn = torch.empty(B, H, W, Cout, device="cuda")
+    stats = torch.zeros(2 * Cout, device="cuda", dtype=torch.float64)
+    ops.conv_fwd(xn, wp, yn, None, False, stats, B, H, W, Cin, Cout, 9)
+    assert rel_err(yn.permute(0, 3, 1, 2).cpu(), y.detach()) < 1e-5
+    np.testing.assert_allclose(stats[:Cout].cpu().numpy(), y.detach().double().sum((0, 2, 3)).numpy(),
+                               rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(stats[Cout:].cpu().numpy(), y.detach().double().pow(2).sum((0, 2, 3)).numpy(),
+                               rtol=1e-4)
+    dyn = dy.permute(0, 2, 3, 1).contiguous().cuda()
+    wt = torch.empty(Cin, 3, 3, Cout, device="cuda")
+    ops.call("tag_weight_flip_transpose", wp, wt, Cout, Cin, 9)
+    dxn = torch.empty(B, H, W, Cin, device="cuda")
+    ops.conv_fwd(dyn, wt, dxn, None, False, None, B, H, W, Cout, Cin, 9)
+    assert rel_err(dxn.permute(0, 3, 1, 2).cpu(), x.grad) < 1e-5
+    dw = torch.zeros(Cout, 3, 3, Cin, device="cuda")
+    ops.conv_wgrad(dyn, xn, dw, B, H, W, Cin, Cout, 9, 3)
+    assert rel_err(dw.permute(0, 3, 1, 2).cpu(), w.grad) < 1e-5
+
+
+def test_linear_as_one_tap_conv_with_bias_relu_and_bf16_io():
+    ops = _ops()
+    M, K, N = 300, 512, 1536
+    x = torch.randn(M, K, generator=g(4))
+    w = torch.randn(N, K, generator=g(5)) * 0.03
+    b = torch.randn(N, generator=g(6))
+    ref = F.relu(F.linear(x, w, b))
+    y = torch.empty(M, N, device="cuda")
+    ops.conv_fwd(x.cuda(), w.cuda(), y, b.cuda(), True, None, 1, M, 1, K, N, 1)
+    assert rel_err(y.cpu(), ref) < 1e-5
+    xb = x.cuda().bfloat16()
+    yb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.conv_fwd(xb, w.cuda(), yb, b.cuda(), True, None, 1, M, 1, K, N, 1)
+    ref_b = F.relu(F.linear(xb.float().cpu(), w, b))
+    assert rel_err(yb.float().cpu(), ref_b) < 5e-3
+
+
+def test_conv_c1_fwd_bwd():
+    ops = _ops()
+    B, H, W = 2, 11, 64
+    x = torch.randn(B, 1, H, W, generator=g(7), requires_grad=True)
+    w = (torch.randn(64, 1, 3, 3, generator=g(8)) * 0.2).requires_grad_(True)
+    y = F.conv2d(x, w, padding=1)
+    dy = torch.randn(y.shape, generator=g(9))
+    y.backward(dy)
+    xn = x.detach().reshape(B, H, W).cuda()
+    yn = torch.empty(B, H, W, 64, device="cuda")
+    stats = torch.zeros(128, device="cuda", dtype=torch.float64)
+    ops.call("tag_conv_c1_fwd", xn, w.detach().reshape(64, 9).cuda(), yn, 0, stats, B, H, W)
+    assert rel_err(yn.permute(0, 3, 1, 2).cpu(), y.detach()) < 1e-5
+    np.testing.assert_allclose(stats[:64].cpu().numpy(), y.detach().double().sum((0, 2, 3)).numpy(), rtol=1e-4, atol=1e-3)
+    dw = torch.zeros(64, 9, device="cuda")
+    dx = torch.empty(B, H, W, device="cuda")
+    ops.call("tag_conv_c1_bwd", dy.permute(0, 2, 3, 1).contiguous().cuda(), xn, w.detach().reshape(64, 9).cuda(), 0,
+             dw, dx, B, H, W)
+    assert rel_err(dw.cpu().reshape(64, 1, 3, 3), w.grad) < 1e-5
+    assert rel_err(dx.cpu().reshape(B, 1, H, W), x.grad) < 1e-5
+
+
+@pytest.mark.parametrize("ph,pw,H", [(2, 2, 9), (1, 2, 6), (2, 2, 8)])
+def test_bn_relu_pool_fwd_bwd_matches_torch_autograd(ph, pw, H):
+    ops = _ops()
+    B, W, C = 3, 8, 64
+    y = torch.randn(B, C, H, W, generator=g(10), requires_grad=True)
+    gamma = (torch.rand(C, generator=g(11)) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, generator=g(12)) * 0.2).requires_grad_(True)
+    a = F.relu(F.batch_norm(y, None, None, gamma, beta, True, 0.1, 1e-5))
+    p = F.avg_pool2d(a, (ph, pw)) + F.max_pool2d(a, (ph, pw))
+    dp = torch.randn(p.shape, generator=g(13))
+    p.backward(dp)
+    yn = y.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    stats = torch.stack([yn.double().sum((0, 1, 2)), yn.double().pow(2).sum((0, 1, 2))]).reshape(-1).contiguous()
+    aux = [torch.empty(C, device="cuda") for _ in range(4)]
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    ops.bn_finalize(stats, B * H * W, C, gamma.detach().cuda(), beta.detach().cuda(), rm, rv, 0.1, 1e-5, True,
+                    True, *aux)
+    ref_rv = 0.9 + 0.1 * y.detach().transpose(0, 1).reshape(C, -1).var(1, unbiased=True)
+    np.testing.assert_allclose(rv.cpu().numpy(), ref_rv.numpy(), rtol=1e-4)
+    Ho, Wo = H // ph, W // pw
+    pn = torch.empty(B, Ho, Wo, C, device="cuda")
+    ops.call("tag_bn_relu_pool_fwd", yn, pn, 0, aux[0], aux[1], B, H, W, C, ph, pw, 0.0, 0, None)
+    assert rel_err(pn.permute(0, 3, 1, 2).cpu(), p.detach()) < 1e-5
+    dpn = dp.permute(0, 2, 3, 1).contiguous().cuda()
+    red = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    ops.call("tag_bn_relu_pool_bwd", 0, yn, dpn, None, 0, *aux, red, 1, B, H, W, C, ph, pw, 0.0, 0, None)
+    np.testing.assert_allclose(red[:C].cpu().numpy(), beta.grad.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(red[C:].cpu().numpy(), gamma.grad.numpy(), rtol=1e-4, atol=1e-5)
+    dyn = torch.empty_like(yn)
+    ops.call("tag_bn_relu_pool_bwd", 1, yn, dpn, dyn, 0, *aux, red, 1, B, H, W, C, ph, pw, 0.0, 0, None)
+    assert rel_err(dyn.permute(0, 3, 1, 2).cpu(), y.grad) < 1e-4
+
+
+def test_bn_relu_nopool_bwd_matches_torch_autograd():
+    ops = _ops()
+    B, H, W, C = 2, 5, 4, 128
+    y = torch.randn(B, C, H, W, generator=g(14), requires_grad=True)
+    gamma = (torch.rand(C, generator=g(15)) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, generator=g(16)) * 0.2).requires_grad_(True)
+    a = F.relu(F.batch_norm(y, None, None, gamma, beta, True, 0.1, 1e-5))
+    da = torch.randn(a.shape, generator=g(17))
+    a.backward(da)
+    yn = y.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    stats = torch.stack([yn.double().sum((0, 1, 2)), yn.double().pow(2).sum((0, 1, 2))]).reshape(-1).contiguous()
+    aux = [torch.empty(C, device="cuda") for _ in range(4)]
+    ops.bn_finalize(stats, B * H * W, C, gamma.detach().cuda(), beta.detach().cuda(), None, None, 0.1, 1e-5, True,
+                    False, *aux)
+    dan = da.permute(0, 2, 3, 1).contiguous().cuda()
+    red = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    ops.call("tag_bn_relu_pool_bwd", 0, yn, dan, None, 0, *aux, red, 1, B, H, W, C, 0, 0, 0.0, 0, None)
+    np.testing.assert_allclose(red[C:].cpu().numpy(), gamma.grad.numpy(), rtol=1e-4, atol=1e-5)
+    dyn = torch.empty_like(yn)
+    ops.call("tag_bn_relu_pool_bwd", 1, yn, dan, dyn, 0, *aux, red, 1, B, H, W, C, 0, 0, 0.0, 0, None)
+    assert rel_err(dyn.permute(0, 3, 1, 2).cpu(), y.grad) < 1e-4
+
+
+@pytest.mark.parametrize("B,T", [(3, 7), (8, 25), (11, 50)])
+def test_bigru_fwd_bwd_matches_oracle(B, T):
+    ops = _ops()
+    sd = O.synth_state_dict(seed=5)
+    pre = "audio_encoder.rnn."
+    x = torch.randn(B, T, 512, generator=g(18)) * 0.5
+    ws = {k: sd[pre + k].clone().requires_grad_(True) for k in
+          ["weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0",
+           "weight_ih_l0_reverse", "weight_hh_l0_reverse", "bias_ih_l0_reverse", "bias_hh_l0_reverse"]}
+    x.requires_grad_(True)
+    ref = O.bigru(x, {pre + k: v for k, v in ws.items()}, pre)
+    d_out = torch.randn(ref.shape, generator=g(19))
+    ref.backward(d_out)
+
+    w_ih = torch.cat([ws["weight_ih_l0"], ws["weight_ih_l0_reverse"]]).detach().cuda()
+    b_ih = torch.cat([ws["bias_ih_l0"], ws["bias_ih_l0_reverse"]]).detach().cuda()
+    w_hh = torch.stack([ws["weight_hh_l0"], ws["weight_hh_l0_reverse"]]).detach().cuda().contiguous()
+    b_hh = torch.cat([ws["bias_hh_l0"], ws["bias_hh_l0_reverse"]]).detach().cuda()
+    rows = B * T
+    xc = x.detach().cuda().reshape(rows, 512)
+    gi = torch.empty(rows, 1536, device="cuda")
+    ops.conv_fwd(xc, w_ih, gi, b_ih, False, None, 1, rows, 1, 512, 1536, 1)
+    out = torch.empty(B, T, 512, device="cuda")
+    gates = torch.empty(B, T, 2, 4, 256, device="cuda")
+    ops.call("tag_gru_fwd", gi, w_hh, b_hh, out, gates, B, T)
+    assert (out.cpu() - ref.detach()).abs().max().item() < 2e-5
+    dgi = torch.empty(rows, 1536, device="cuda")
+    dgh = torch.empty(2, rows, 768, device="cuda")
+    hprev = torch.empty(2, rows, 256, device="cuda")
+    ops.call("tag_gru_bwd", d_out.cuda(), out, gates, w_hh, dgi, dgh, hprev, B, T)
+    # input gradient and parameter gradients from dgi / dgh
+    dx = dgi @ w_ih
+    assert rel_err(dx.cpu().reshape(B, T, 512), x.grad) < 1e-4
+    dw_ih = torch.zeros(1536, 512, device="cuda")
+    ops.conv_wgrad(dgi, xc, dw_ih, 1, rows, 1, 512, 1536, 1, 2)
+    ref_dw_ih = torch.cat([ws["weight_ih_l0"].grad, ws["weight_ih_l0_reverse"].grad])
+    assert rel_err(dw_ih.cpu(), ref_dw_ih) < 1e-4
+    for d, k in enumerate(["weight_hh_l0", "weight_hh_l0_reverse"]):
+        dw = torch.zeros(768, 256, device="cuda")
+        ops.conv_wgrad(dgh[d], hprev[d], dw, 1, rows, 1, 256, 768, 1, 2)
+        assert rel_err(dw.cpu(), ws[k].grad) < 1e-4, k
+    db = torch.zeros(768, device="cuda")
+    ops.call("tag_colsum", dgh[1], 0, rows, 768, db)
+    assert rel_err(db.cpu(), ws["bias_hh_l0_reverse"].grad) < 1e-4
+
+
+def test_head_embed_dot_bce_fwd_bwd():
+    ops = _ops()
+    from texttoaudiogrounding_b200.models.text_encoder import _EmbedMeanFunction
+    from texttoaudiogrounding_b200.models.match import _DotSigmoidFunction
+    from texttoaudiogrounding_b200.losses import frame_bce
+    B, T, N, V, D = 5, 37, 8, 101, 512
+    emb = (torch.randn(V, D, generator=g(20)) * 2).requires_grad_(True)
+    audio = torch.randn(B, T, D, generator=g(21)).requires_grad_(True)
+    text = torch.randint(0, V, (B, N), generator=g(22))
+    tl = torch.tensor([8, 3, 5, 1, 8])
+    label = (torch.rand(B, T + 1, generator=g(23)) > 0.5).float()
+    length = torch.tensor([37, 20, 1, 37, 30])
+    # oracle
+    t = O.embedding_mean({"text_encoder.embedding.core.weight": emb}, text, tl)
+    sim, _ = O.dot_product_match(audio, t["seq_emb"])
+    ref_loss = O.frame_bce_loss({"frame_sim": sim[:, :T], "label": label[:, :T], "length": length})
+    ref_loss.backward()
+    # CUDA
+    e2 = emb.detach().cuda().requires_grad_(True)
+    a2 = audio.detach().cuda().requires_grad_(True)
+    tok, seq = _EmbedMeanFunction.apply(e2, text.cuda(), tl.cuda())
+    s2 = _DotSigmoidFunction.apply(a2, seq, 1.0 / math.sqrt(D))
+    loss = frame_bce(s2[:, :T], label[:, :T].cuda(), length)
+    loss.backward()
+    assert (s2.detach().cpu() - sim.detach()).abs().max().item() < 1e-5
+    np.testing.assert_allclose(loss.item(), ref_loss.item(), rtol=1e-5)
+    assert rel_err(a2.grad.cpu(), audio.grad) < 1e-4
+    assert rel_err(e2.grad.cpu(), emb.grad) < 1e-4
+    assert torch.equal(tok.cpu(), F.embedding(text, emb.detach()))
+
+
+def test_clip_adam_matches_torch():
+    ops = _ops()
+    n = 10007
+    p = torch.randn(n, generator=g(24))
+    ref_p = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=1e-3)
+    pc, m, v = p.cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    step = torch.zeros(1, device="cuda", dtype=torch.int64)
+    norm = torch.zeros(1, device="cuda")
+    for it in range(3):
+        gr = torch.randn(n, generator=g(25 + it)) * (3.0 if it == 0 else 0.001)
+        ref_p.grad = gr.clone()
+        tn = torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        ss = torch.zeros(1, device="cuda", dtype=torch.float64)
+        gc = gr.cuda()
+        ops.call("tag_sumsq", gc, n, ss)
+        ops.call("tag_clip_adam", pc, gc, m, v, n, ss, step, 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, norm)
+        np.testing.assert_allclose(norm.item(), float(tn), rtol=1e-5)
+        assert (pc.cpu() - ref_p.detach()).abs().max().item() < 2e-6

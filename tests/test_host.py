@@ -1,0 +1,114 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, the module
+classes mirror the reference's surface (state-dict keys/shapes, config instantiation, error
+behaviour) — no kernel is launched here."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from oracle import tag_oracle as O
+
+
+def test_library_builds_and_exports_every_header_symbol():
+    from texttoaudiogrounding_b200 import _lib
+    _lib.build()
+    protos = _lib.parse_header()
+    assert len(protos) >= 29
+    cdll = ctypes.CDLL(_lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(cdll, name), name
+    assert _lib.lib().tag_version() == 100
+
+
+def test_no_cpu_fallback():
+    from helpers import build_model
+    from texttoaudiogrounding_b200.losses import FrameBceLoss
+    model = build_model(None, "fp32", device="cpu")
+    batch = O.synth_batch(1, 32000)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model({"specaug": False, **batch})
+    with pytest.raises(KeyError):
+        model({k: v for k, v in batch.items()})          # 'specaug' is a required key (reference quirk)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FrameBceLoss()({"frame_sim": torch.rand(2, 5), "label": torch.rand(2, 5), "length": [5, 5]})
+
+
+def test_state_dict_keys_and_shapes_match_reference():
+    from helpers import build_model
+    model = build_model(None, "fp32", device="cpu")
+    sd = model.state_dict()
+    spec = {k: tuple(shape) for k, shape, _ in O.state_dict_spec()}
+    assert set(sd) == set(spec)
+    for k, v in sd.items():
+        assert tuple(v.shape) == spec[k], k
+    assert sum(p.numel() for p in model.parameters()) == 8804800
+    # frontend buffers equal torchaudio's (restated in the oracle, pinned in test_oracle_golden)
+    np.testing.assert_allclose(sd["audio_encoder.melspec_extractor.mel_scale.fb"].numpy(),
+                               O.melscale_fbanks().numpy(), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(sd["audio_encoder.melspec_extractor.spectrogram.window"].numpy(),
+                               O.hann_window().numpy(), atol=1e-7)
+    # load a reference-layout (NCHW-contiguous) state dict, read it back unchanged
+    ref_sd = O.synth_state_dict(seed=7)
+    model.load_state_dict(ref_sd, strict=True)
+    w = model.audio_encoder.conv_block2.conv1.weight
+    assert torch.equal(w.detach(), ref_sd["audio_encoder.conv_block2.conv1.weight"])
+    assert w.permute(0, 2, 3, 1).is_contiguous()       # kernels see [Cout][kh][kw][Cin]
+
+
+def test_initialisation_matches_reference_for_same_seed():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "init_seed1.npz"))
+    from helpers import build_model
+    torch.manual_seed(1)
+    model = build_model(None, "fp32", device="cpu")
+    for k, v in model.state_dict().items():
+        if v.dtype.is_floating_point:
+            np.testing.assert_allclose(v.double().sum().item(), g["sum/" + k].item(), rtol=1e-6, atol=1e-6, err_msg=k)
+            np.testing.assert_allclose(v.double().abs().sum().item(), g["abs/" + k].item(), rtol=1e-6, err_msg=k)
+
+
+def test_run_strong_dialect_config_instantiates_b200_classes(tmp_path):
+    from texttoaudiogrounding_b200.utils import train_util
+    train_util.install_as_reference_modules()
+    cfg = {
+        "model": {
+            "audio_encoder": {"type": "models.audio_encoder.Cnn8Rnn", "args": {"sample_rate": 32000}},
+            "text_encoder": {"type": "models.text_encoder.EmbeddingAgg",
+                             "args": {"vocab_size": 50, "embed_dim": 512, "aggregation": "mean"}},
+            "match_fn": {"type": "models.match.DotProduct", "args": {}},
+            "type": "models.audio_text_model.BiEncoder", "args": {"shared_dim": 512},
+        },
+        "loss": {"type": "losses.FrameBceLoss", "args": {}},
+        "optimizer": {"type": "torch.optim.Adam", "args": {"lr": 0.001}},
+        "trainer": {"max_grad_norm": 1.0},
+    }
+    base = tmp_path / "base.yaml"
+    base.write_text(yaml.dump(cfg))
+    child = tmp_path / "child.yaml"
+    child.write_text(yaml.dump({"inherit_from": "base.yaml", "trainer": {"max_grad_norm": 2.0}}))
+    config = train_util.parse_config_or_kwargs(str(child), **{"optimizer.args.lr": 0.01})
+    assert config["trainer"]["max_grad_norm"] == 2.0 and config["optimizer"]["args"]["lr"] == 0.01
+    model = train_util.get_model(config)
+    import texttoaudiogrounding_b200.models.audio_encoder as ae
+    assert isinstance(model.audio_encoder, ae.Cnn8Rnn)
+    assert model.audio_encoder.embed_dim == 512 and model.audio_encoder.downsample_ratio == 4
+    loss = train_util.init_obj_from_str(config["loss"])
+    opt = train_util.init_obj_from_str(config["optimizer"], params=model.parameters())
+    assert type(loss).__name__ == "FrameBceLoss" and opt.defaults["lr"] == 0.01
+    with pytest.raises(NotImplementedError):
+        train_util.init_obj_from_str({"type": "models.match.DotProduct", "args": {"text_level": "token"}})(
+            {"audio_emb": torch.zeros(1, 2, 4), "text_emb": {"token_emb": torch.zeros(1, 2, 4)}})
+
+
+def test_freeze_and_train_mode_semantics():
+    from texttoaudiogrounding_b200.models.audio_encoder import Cnn8Rnn
+    enc = Cnn8Rnn(32000, freeze_cnn=True, freeze_bn=True)
+    assert all(p.requires_grad for p in enc.rnn.parameters())
+    assert not enc.conv_block1.conv1.weight.requires_grad and not enc.fc1.weight.requires_grad
+    enc.train()
+    assert enc.training and not enc.bn0.training and not enc.conv_block3.bn2.training
+    length = torch.div(torch.div(torch.as_tensor([64000, 32000]), 320, rounding_mode="floor") + 1, 4,
+                       rounding_mode="floor")
+    assert length.tolist() == [50, 25]

@@ -1,0 +1,150 @@
+// Fused log-mel frontend: reflect-pad framing -> Hann -> 1024-pt FFT in shared memory ->
+// |X|^2 -> slaney mel filterbank -> 10*log10(clamp) (+ per-mel sum / sum-of-squares for bn0).
+//
+// Replaces the reference's torchaudio MelSpectrogram + AmplitudeToDB call chain
+// (reference models/audio_encoder.py:113-124,183-184), which materialises the complex
+// spectrum, the magnitude and the power tensors in HBM (SURVEY.md §8a rows a1,a2).
+// Here one CTA stages 8 frames worth of contiguous samples (3264 floats, coalesced),
+// runs four 1024-point complex FFTs (two real frames packed per FFT) entirely in shared
+// memory and writes only the [B, T0, 64] dB tensor.
+#include "common.cuh"
+
+namespace {
+
+constexpr int N_FFT = 1024;
+constexpr int HOP = 320;
+constexpr int N_BINS = 513;
+constexpr int N_MELS = 64;
+constexpr int FRAMES_PER_CTA = 8;
+constexpr int PAIRS = FRAMES_PER_CTA / 2;
+constexpr int SPAN = N_FFT + (FRAMES_PER_CTA - 1) * HOP;  // 3264 samples
+constexpr int P_STRIDE = 516;
+constexpr int THREADS = 256;
+
+struct FrontendSmem {
+    float samples[SPAN];
+    float2 z[PAIRS][N_FFT];
+    float2 tw[N_FFT / 2];
+    float win[N_FFT];
+    float power[FRAMES_PER_CTA][P_STRIDE];
+    float db[FRAMES_PER_CTA][N_MELS];
+};
+
+__device__ __forceinline__ int bitrev10(int x) { return (int)(__brev((unsigned)x) >> 22); }
+
+__global__ void __launch_bounds__(THREADS)
+logmel_kernel(const float* __restrict__ wav, int L, long wav_stride, int T0,
+              const float* __restrict__ window, const float* __restrict__ fb,
+              const int* __restrict__ mel_range, float* __restrict__ db_out,
+              double* __restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FrontendSmem& s = *reinterpret_cast<FrontendSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * FRAMES_PER_CTA;
+    const float* w = wav + (long)b * wav_stride;
+
+    // ---- stage samples (reflect padding of 512 on both sides, torch.stft center=True)
+    const int start = t0 * HOP - N_FFT / 2;
+    for (int i = tid; i < SPAN; i += THREADS) {
+        int src = start + i;
+        if (src < 0) src = -src;
+        if (src >= L) src = 2 * (L - 1) - src;
+        float v = 0.f;
+        if (src >= 0 && src < L) v = __ldg(w + src);
+        s.samples[i] = v;
+    }
+    for (int i = tid; i < N_FFT / 2; i += THREADS) {
+        float sn, cs;
+        sincospif(2.0f * (float)i / (float)N_FFT, &sn, &cs);
+        s.tw[i] = make_float2(cs, -sn);
+    }
+    for (int i = tid; i < N_FFT; i += THREADS) s.win[i] = __ldg(window + i);
+    __syncthreads();
+
+    // ---- windowed load in bit-reversed order; frame 2p -> real part, 2p+1 -> imaginary
+    for (int i = tid; i < PAIRS * N_FFT; i += THREADS) {
+        int p = i >> 10, n = i & (N_FFT - 1);
+        float wn = s.win[n];
+        float xa = s.samples[(2 * p) * HOP + n] * wn;
+        float xb = s.samples[(2 * p + 1) * HOP + n] * wn;
+        s.z[p][bitrev10(n)] = make_float2(xa, xb);
+    }
+    __syncthreads();
+
+    // ---- radix-2 decimation-in-time, 10 stages, 4 x 512 butterflies per stage
+#pragma unroll 1
+    for (int stage = 0; stage < 10; ++stage) {
+        const int half = 1 << stage;
+        const int tw_step = (N_FFT / 2) >> stage;
+        for (int i = tid; i < PAIRS * (N_FFT / 2); i += THREADS) {
+            int p = i >> 9, j = i & 511;
+            int pos = j & (half - 1);
+            int i0 = ((j >> stage) << (stage + 1)) + pos;
+            int i1 = i0 + half;
+            float2 wv = s.tw[pos * tw_step];
+            float2 a = s.z[p][i0], c = s.z[p][i1];
+            float2 t = make_float2(c.x * wv.x - c.y * wv.y, c.x * wv.y + c.y * wv.x);
+            s.z[p][i0] = make_float2(a.x + t.x, a.y + t.y);
+            s.z[p][i1] = make_float2(a.x - t.x, a.y - t.y);
+        }
+        __syncthreads();
+    }
+
+    // ---- separate the two real spectra and take |.|^2
+    for (int i = tid; i < PAIRS * N_BINS; i += THREADS) {
+        int p = i / N_BINS, k = i - p * N_BINS;
+        float2 zk = s.z[p][k];
+        float2 zn = s.z[p][(N_FFT - k) & (N_FFT - 1)];
+        float ar = zk.x + zn.x, ai = zk.y - zn.y;   // 2 * X_a[k]
+        float br = zk.x - zn.x, bi = zk.y + zn.y;   // 2i * X_b[k]
+        s.power[2 * p][k] = 0.25f * (ar * ar + ai * ai);
+        s.power[2 * p + 1][k] = 0.25f * (br * br + bi * bi);
+    }
+    __syncthreads();
+
+    // ---- mel filterbank (each mel touches only bins [lo, hi)) + dB
+    for (int i = tid; i < FRAMES_PER_CTA * N_MELS; i += THREADS) {
+        int f = i >> 6, m = i & 63;
+        int lo = 0, hi = N_BINS;
+        if (mel_range != nullptr) { lo = mel_range[2 * m]; hi = mel_range[2 * m + 1]; }
+        float acc = 0.f;
+        for (int k = lo; k < hi; ++k) acc = fmaf(s.power[f][k], __ldg(fb + k * N_MELS + m), acc);
+        float v = 10.0f * log10f(fmaxf(acc, 1e-10f));
+        s.db[f][m] = v;
+        int t = t0 + f;
+        if (t < T0) db_out[((long)b * T0 + t) * N_MELS + m] = v;
+    }
+    if (stats != nullptr) {
+        __syncthreads();
+        if (tid < N_MELS) {
+            float sm = 0.f, sq = 0.f;
+            for (int f = 0; f < FRAMES_PER_CTA; ++f) {
+                if (t0 + f < T0) { float v = s.db[f][tid]; sm += v; sq += v * v; }
+            }
+            atomicAdd(stats + tid, (double)sm);
+            atomicAdd(stats + N_MELS + tid, (double)sq);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int tag_logmel_fwd(const float* wav, int batch, int n_samples, long wav_stride,
+                              const float* window, const float* fb, const int* mel_range,
+                              float* db_out, double* stats, cudaStream_t stream) {
+    if (batch <= 0 || n_samples <= N_FFT / 2) return TAG_ERR_BAD_ARG;
+    const int T0 = n_samples / HOP + 1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(FrontendSmem));
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    dim3 grid((T0 + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA, batch);
+    logmel_kernel<<<grid, THREADS, sizeof(FrontendSmem), stream>>>(
+        wav, n_samples, wav_stride, T0, window, fb, mel_range, db_out, stats);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}

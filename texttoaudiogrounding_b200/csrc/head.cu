@@ -1,0 +1,207 @@
+// Text side and matching head: embedding gather + masked mean, frame-wise scaled dot product ->
+// sigmoid -> clamp, masked frame BCE; forward and analytic backward.  Warp-shuffle reductions.
+//
+// Reference: models/text_encoder.py:39-43,79-88 + models/utils.py:33-58 (EmbeddingAgg 'mean'),
+// models/match.py:43-60 (DotProduct, l2norm=False), losses.py:12-24 (FrameBceLoss).
+#include "common.cuh"
+
+namespace {
+
+// one CTA per sequence; seq[b,:] = sum_{n < len} E[text[b,n], :] / len
+__global__ void embed_mean_fwd_kernel(const long long* __restrict__ text, const long long* __restrict__ text_len,
+                                      const float* __restrict__ emb, float* __restrict__ token_emb,
+                                      float* __restrict__ seq_emb, int N, int D, int vocab) {
+    const int b = blockIdx.x;
+    const long long len = text_len[b];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+        for (int n = 0; n < N; ++n) {
+            long long id = text[(long)b * N + n];
+            if (id < 0) id = 0;
+            if (id >= vocab) id = vocab - 1;
+            const float v = emb[id * D + d];
+            if (token_emb != nullptr) token_emb[((long)b * N + n) * D + d] = v;
+            if (n < len) acc += v;
+        }
+        seq_emb[(long)b * D + d] = acc / (float)len;
+    }
+}
+
+__global__ void embed_mean_bwd_kernel(const long long* __restrict__ text, const long long* __restrict__ text_len,
+                                      const float* __restrict__ d_seq, float* __restrict__ d_emb,
+                                      int N, int D, int vocab) {
+    const int b = blockIdx.x;
+    const long long len = text_len[b];
+    const float inv = 1.0f / (float)len;
+    for (int n = 0; n < N && n < len; ++n) {
+        long long id = text[(long)b * N + n];
+        if (id < 0) id = 0;
+        if (id >= vocab) id = vocab - 1;
+        for (int d = threadIdx.x; d < D; d += blockDim.x)
+            atomicAdd(d_emb + id * D + d, d_seq[(long)b * D + d] * inv);
+    }
+}
+
+// one warp per (b, t): sim = clamp(sigmoid(scale * <a[b,t,:], s[b,:]>), 1e-7, 1)
+__global__ void dot_sigmoid_fwd_kernel(const float* __restrict__ audio, const float* __restrict__ seq,
+                                       float* __restrict__ sim, float* __restrict__ logits,
+                                       long BT, int T, int D, float scale) {
+    const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= BT) return;
+    const long b = wid / T;
+    const float* a = audio + wid * D;
+    const float* s = seq + b * D;
+    float acc = 0.f;
+    for (int d = lane * 4; d < D; d += 128) {
+        const float4 av = *reinterpret_cast<const float4*>(a + d);
+        const float4 sv = *reinterpret_cast<const float4*>(s + d);
+        acc += av.x * sv.x + av.y * sv.y + av.z * sv.z + av.w * sv.w;
+    }
+    acc = warp_sum(acc) * scale;
+    if (lane == 0) {
+        const float p = 1.0f / (1.0f + expf(-acc));
+        sim[wid] = fminf(fmaxf(p, 1e-7f), 1.0f);
+        if (logits != nullptr) logits[wid] = acc;
+    }
+}
+
+// d_audio[b,t,:] = dlogit * seq[b,:] * scale ; dlogit = d_sim * p (1-p), zero where clamped
+__global__ void dot_sigmoid_bwd_audio_kernel(const float* __restrict__ d_sim, const float* __restrict__ sim,
+                                             const float* __restrict__ seq, float* __restrict__ d_audio,
+                                             float* __restrict__ d_logit, long BT, int T, int D, float scale) {
+    const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= BT) return;
+    const long b = wid / T;
+    const float p = sim[wid];
+    float g = (p > 1e-7f) ? d_sim[wid] * p * (1.0f - p) : 0.f;
+    if (lane == 0) d_logit[wid] = g;
+    g *= scale;
+    const float* s = seq + b * D;
+    float* o = d_audio + wid * D;
+    for (int d = lane * 4; d < D; d += 128) {
+        const float4 sv = *reinterpret_cast<const float4*>(s + d);
+        *reinterpret_cast<float4*>(o + d) = make_float4(g * sv.x, g * sv.y, g * sv.z, g * sv.w);
+    }
+}
+
+// d_seq[b,:] = scale * sum_t dlogit[b,t] * audio[b,t,:]   (one CTA per b, thread per 2 features)
+__global__ void dot_sigmoid_bwd_seq_kernel(const float* __restrict__ d_logit, const float* __restrict__ audio,
+                                           float* __restrict__ d_seq, int T, int D, float scale) {
+    const int b = blockIdx.x;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) acc = fmaf(d_logit[(long)b * T + t], audio[((long)b * T + t) * D + d], acc);
+        d_seq[(long)b * D + d] = acc * scale;
+    }
+}
+
+// loss = sum_{b, t < min(len_b, Tt)} bce(sim[b,t], label[b,t]) / sum_b min(len_b, Tt)
+// (single CTA; B*T is at most a few 10^4).  Also writes d_sim (d loss / d sim) when asked.
+__global__ void frame_bce_kernel(const float* __restrict__ sim, long sim_stride,
+                                 const float* __restrict__ label, long label_stride,
+                                 const long long* __restrict__ length, int B, int Tt,
+                                 float* __restrict__ loss_out, float* __restrict__ d_sim, long dsim_stride,
+                                 float grad_scale) {
+    __shared__ float red[32];
+    __shared__ float s_cnt;
+    float cnt = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        long long l = length[b];
+        if (l > Tt) l = Tt;
+        if (l < 0) l = 0;
+        cnt += (float)l;
+    }
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float c = 0.f;
+        for (int i = 0; i < (blockDim.x >> 5); ++i) c += red[i];
+        s_cnt = c;
+    }
+    __syncthreads();
+    const float total = s_cnt;
+    float acc = 0.f;
+    for (long i = threadIdx.x; i < (long)B * Tt; i += blockDim.x) {
+        const int b = (int)(i / Tt), t = (int)(i % Tt);
+        const bool on = t < length[b];
+        const float p = sim[b * sim_stride + t];
+        const float y = label[b * label_stride + t];
+        if (on) {
+            const float lp = fmaxf(logf(p), -100.f);
+            const float lq = fmaxf(log1pf(-p), -100.f);
+            acc -= y * lp + (1.f - y) * lq;
+        }
+        if (d_sim != nullptr) {
+            float g = 0.f;
+            if (on) {
+                // torch's binary_cross_entropy_backward: (p - y) / max((1 - p) * p, 1e-12)
+                g = (p - y) / fmaxf((1.f - p) * p, 1e-12f) * grad_scale / total;
+            }
+            d_sim[b * dsim_stride + t] = g;
+        }
+    }
+    __syncthreads();
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0 && loss_out != nullptr) {
+        float c = 0.f;
+        for (int i = 0; i < (blockDim.x >> 5); ++i) c += red[i];
+        *loss_out = c / total;
+    }
+}
+
+}  // namespace
+
+extern "C" int tag_embed_mean_fwd(const long long* text, const long long* text_len, const float* emb,
+                                  float* token_emb, float* seq_emb, int B, int N, int D, int vocab,
+                                  cudaStream_t stream) {
+    if (B <= 0) return TAG_ERR_BAD_ARG;
+    embed_mean_fwd_kernel<<<B, 128, 0, stream>>>(text, text_len, emb, token_emb, seq_emb, N, D, vocab);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_embed_mean_bwd(const long long* text, const long long* text_len, const float* d_seq,
+                                  float* d_emb, int B, int N, int D, int vocab, cudaStream_t stream) {
+    if (B <= 0) return TAG_ERR_BAD_ARG;
+    embed_mean_bwd_kernel<<<B, 128, 0, stream>>>(text, text_len, d_seq, d_emb, N, D, vocab);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_dot_sigmoid_fwd(const float* audio, const float* seq, float* sim, float* logits,
+                                   int B, int T, int D, float scale, cudaStream_t stream) {
+    if (D % 4 != 0) return TAG_ERR_BAD_ARG;
+    const long BT = (long)B * T;
+    const int blocks = (int)((BT * 32 + 255) / 256);
+    dot_sigmoid_fwd_kernel<<<blocks, 256, 0, stream>>>(audio, seq, sim, logits, BT, T, D, scale);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_dot_sigmoid_bwd(const float* d_sim, const float* sim, const float* audio,
+                                   const float* seq, float* d_audio, float* d_seq, float* d_logit_ws,
+                                   int B, int T, int D, float scale, cudaStream_t stream) {
+    if (D % 4 != 0) return TAG_ERR_BAD_ARG;
+    const long BT = (long)B * T;
+    const int blocks = (int)((BT * 32 + 255) / 256);
+    dot_sigmoid_bwd_audio_kernel<<<blocks, 256, 0, stream>>>(d_sim, sim, seq, d_audio, d_logit_ws, BT, T, D, scale);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    dot_sigmoid_bwd_seq_kernel<<<B, 256, 0, stream>>>(d_logit_ws, audio, d_seq, T, D, scale);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_frame_bce(const float* sim, long sim_stride, const float* label, long label_stride,
+                             const long long* length, int B, int Tt, float* loss_out, float* d_sim,
+                             long dsim_stride, float grad_scale, cudaStream_t stream) {
+    if (B <= 0 || Tt <= 0) return TAG_ERR_BAD_ARG;
+    frame_bce_kernel<<<1, 1024, 0, stream>>>(sim, sim_stride, label, label_stride, length, B, Tt, loss_out,
+                                             d_sim, dsim_stride, grad_scale);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}

@@ -1,0 +1,296 @@
+"""Host-side orchestration of the Cnn8Rnn forward / backward over the C-ABI kernels.
+
+This is the kernel schedule behind ``models.audio_encoder.Cnn8Rnn`` (the mirror of reference
+models/audio_encoder.py:178-232).  It only allocates device buffers and sequences kernel
+launches; all arithmetic is in ``csrc/``.
+
+Weights arrive as an ``EncoderWeights`` bundle of kernel-ready tensors:
+  bn[i]   = (gamma, beta, running_mean, running_var)   i = 0 (bn0), 1..8 (block b: bn1, bn2)
+  conv[i] = fp32 weights with memory layout [Cout][tap][Cin]   i = 0..7
+  fc_w [512,512], fc_b [512], w_ih [1536,512], b_ih [1536], w_hh [2,768,256], b_hh [1536]
+Gradients are accumulated (+=) into an identically shaped ``EncoderGrads`` bundle.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .ops import call
+
+HOP = 320
+N_MELS = 64
+CHANNELS = [(1, 64), (64, 128), (128, 256), (256, 512)]
+POOLS = [(2, 2), (2, 2), (1, 2), (1, 2)]
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+P_BLOCK = 0.2
+P_FC = 0.5
+
+
+@dataclass
+class EncoderWeights:
+    window: torch.Tensor
+    fb: torch.Tensor
+    mel_range: Optional[torch.Tensor]
+    bn: List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]]
+    conv: List[torch.Tensor]
+    fc_w: torch.Tensor
+    fc_b: torch.Tensor
+    w_ih: torch.Tensor
+    b_ih: torch.Tensor
+    w_hh: torch.Tensor
+    b_hh: torch.Tensor
+
+
+@dataclass
+class EncoderGrads:
+    bn: List[Tuple[torch.Tensor, torch.Tensor]]          # (dgamma, dbeta) x 9
+    conv: List[torch.Tensor]
+    fc_w: torch.Tensor
+    fc_b: torch.Tensor
+    w_ih: torch.Tensor
+    b_ih: torch.Tensor
+    w_hh: torch.Tensor
+    b_hh: torch.Tensor
+
+
+@dataclass
+class EncoderCtx:
+    B: int = 0
+    T0: int = 0
+    dtype: torch.dtype = torch.float32
+    bn_training: bool = True
+    seed: int = 0
+    seed_dev: Optional[torch.Tensor] = None
+    dropout: bool = False
+    db: torch.Tensor = None
+    x0: torch.Tensor = None
+    bn_aux: list = field(default_factory=list)      # per BN: (scale, shift, mean, invstd)
+    y: list = field(default_factory=list)           # raw conv outputs, 8 tensors
+    a: list = field(default_factory=list)           # relu(bn1(y1)) per block, 4 tensors
+    p: list = field(default_factory=list)           # pooled block outputs, 4 tensors
+    dims: list = field(default_factory=list)        # (H, W) at each block's conv resolution
+    m: torch.Tensor = None
+    f: torch.Tensor = None
+    out: torch.Tensor = None
+    gates: torch.Tensor = None
+
+
+def _seed_for(seed: int, layer: int) -> int:
+    return (seed * 1000003 + layer * 7919 + 12345) & 0xFFFFFFFFFFFFFFFF
+
+
+def compute_mel_range(fb: torch.Tensor) -> torch.Tensor:
+    """[64,2] int32 (lo, hi) support of each mel filter, derived from the fb buffer."""
+    nz = fb != 0
+    any_nz = nz.any(dim=0)
+    idx = torch.arange(fb.shape[0], device=fb.device).unsqueeze(1)
+    big = fb.shape[0]
+    lo = torch.where(nz, idx, torch.full_like(idx, big)).min(dim=0).values
+    hi = torch.where(nz, idx + 1, torch.zeros_like(idx)).max(dim=0).values
+    lo = torch.where(any_nz, lo, torch.zeros_like(lo))
+    return torch.stack([lo, hi], dim=1).to(torch.int32).contiguous()
+
+
+def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn_training: bool,
+                    dropout: bool, seed: int, dtype: torch.dtype, save: bool,
+                    seed_dev: Optional[torch.Tensor] = None,
+                    stages: Optional[dict] = None) -> Tuple[torch.Tensor, Optional[EncoderCtx]]:
+    """wav [B, L] fp32 (cuda) -> embedding [B, T', 512] fp32.  ``save`` keeps what backward needs."""
+    assert wav.is_cuda and wav.dtype == torch.float32 and wav.dim() == 2
+    if wav.stride(1) != 1:
+        wav = wav.contiguous()
+    dev = wav.device
+    B, L = wav.shape
+    T0 = L // HOP + 1
+    f32 = dict(device=dev, dtype=torch.float32)
+    act = dict(device=dev, dtype=dtype)
+    ctx = EncoderCtx(B=B, T0=T0, dtype=dtype, bn_training=bn_training, seed=seed, seed_dev=seed_dev,
+                     dropout=dropout and training) if save else None
+    use_dropout = dropout and training
+
+    def bn_aux(C):
+        return tuple(torch.empty(C, **f32) for _ in range(4))
+
+    def finalize(stats, count, C, bn_idx, aux):
+        g, b, rm, rv = Wt.bn[bn_idx]
+        ops.bn_finalize(stats, count, C, g, b, rm, rv, BN_MOMENTUM, BN_EPS, bn_training,
+                        bn_training and training, aux[0], aux[1], aux[2], aux[3])
+
+    # ---- log-mel + bn0
+    db = torch.empty(B, T0, N_MELS, **f32)
+    st = torch.zeros(2 * N_MELS, device=dev, dtype=torch.float64) if bn_training else None
+    call("tag_logmel_fwd", wav, B, L, wav.stride(0), Wt.window, Wt.fb, Wt.mel_range, db, st)
+    aux0 = bn_aux(N_MELS)
+    finalize(st, B * T0, N_MELS, 0, aux0)
+    x0 = torch.empty(B, T0, N_MELS, **act)
+    ops.scale_shift_act(db, x0, aux0[0], aux0[1], N_MELS, relu=False)
+    if stages is not None:
+        stages["logmel_db"] = db
+        stages["bn0"] = x0
+    if save:
+        ctx.db, ctx.x0 = db, x0
+        ctx.bn_aux.append(aux0)
+
+    # ---- conv blocks
+    x = x0
+    H, W = T0, N_MELS
+    for blk, ((cin, cout), (ph, pw)) in enumerate(zip(CHANNELS, POOLS)):
+        count = B * H * W
+        # conv1
+        y1 = torch.empty(B, H, W, cout, **act)
+        st1 = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if bn_training else None
+        if cin == 1:
+            call("tag_conv_c1_fwd", x, Wt.conv[0], y1, ops.dt(y1), st1, B, H, W)
+        else:
+            ops.conv_fwd(x, Wt.conv[2 * blk], y1, None, False, st1, B, H, W, cin, cout, 9)
+        aux1 = bn_aux(cout)
+        finalize(st1, count, cout, 1 + 2 * blk, aux1)
+        a1 = torch.empty(B, H, W, cout, **act)
+        ops.scale_shift_act(y1, a1, aux1[0], aux1[1], cout, relu=True)
+        # conv2
+        y2 = torch.empty(B, H, W, cout, **act)
+        st2 = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if bn_training else None
+        ops.conv_fwd(a1, Wt.conv[2 * blk + 1], y2, None, False, st2, B, H, W, cout, cout, 9)
+        aux2 = bn_aux(cout)
+        finalize(st2, count, cout, 2 + 2 * blk, aux2)
+        # bn2 + relu + pool + dropout
+        Ho, Wo = H // ph, W // pw
+        p = torch.empty(B, Ho, Wo, cout, **act)
+        call("tag_bn_relu_pool_fwd", y2, p, ops.dt(p), aux2[0], aux2[1], B, H, W, cout, ph, pw,
+             P_BLOCK if use_dropout else 0.0, _seed_for(seed, blk), seed_dev)
+        if stages is not None:
+            stages[f"conv_block{blk + 1}"] = p
+        if save:
+            ctx.y += [y1, y2]
+            ctx.a.append(a1)
+            ctx.p.append(p)
+            ctx.bn_aux += [aux1, aux2]
+            ctx.dims.append((H, W))
+        x = p
+        H, W = Ho, Wo
+
+    # ---- mean over frequency (+dropout 0.5), fc1 + relu, GRU
+    Tp, Wf, C = H, W, CHANNELS[-1][1]
+    rows = B * Tp
+    m = torch.empty(rows, C, **act)
+    call("tag_freq_mean_fwd", x, m, ops.dt(m), rows, Wf, C, P_FC if use_dropout else 0.0,
+         _seed_for(seed, 4), seed_dev)
+    f = torch.empty(rows, 512, **act)
+    ops.conv_fwd(m, Wt.fc_w, f, Wt.fc_b, True, None, 1, rows, 1, C, 512, 1)
+    gi = torch.empty(rows, 1536, **f32)
+    ops.conv_fwd(f, Wt.w_ih, gi, Wt.b_ih, False, None, 1, rows, 1, 512, 1536, 1)
+    out = torch.empty(B, Tp, 512, **f32)
+    gates = torch.empty(B, Tp, 2, 4, 256, **f32) if save else None
+    call("tag_gru_fwd", gi, Wt.w_hh, Wt.b_hh, out, gates, B, Tp)
+    if stages is not None:
+        stages["fc1"] = f.view(B, Tp, 512)
+        stages["rnn"] = out
+    if save:
+        ctx.m, ctx.f, ctx.out, ctx.gates = m, f, out, gates
+    return out, ctx
+
+
+def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G: EncoderGrads) -> None:
+    """Backward of encoder_forward: accumulates parameter gradients into ``G``."""
+    dev = d_emb.device
+    B, dtype = ctx.B, ctx.dtype
+    f32 = dict(device=dev, dtype=torch.float32)
+    act = dict(device=dev, dtype=dtype)
+    Tp = ctx.out.shape[1]
+    rows = B * Tp
+    d_emb = d_emb.contiguous()
+    p_blk = P_BLOCK if ctx.dropout else 0.0
+    p_fc = P_FC if ctx.dropout else 0.0
+
+    # ---- GRU
+    dgi = torch.empty(rows, 1536, **f32)
+    dgh = torch.empty(2, rows, 768, **f32)
+    hprev = torch.empty(2, rows, 256, **f32)
+    call("tag_gru_bwd", d_emb, ctx.out, ctx.gates, Wt.w_hh, dgi, dgh, hprev, B, Tp)
+    call("tag_colsum", dgi, ops.F32, rows, 1536, G.b_ih)
+    for d in range(2):
+        call("tag_colsum", dgh[d], ops.F32, rows, 768, G.b_hh[d * 768:(d + 1) * 768])
+        ops.conv_wgrad(dgh[d], hprev[d], G.w_hh[d], 1, rows, 1, 256, 768, 1,
+                       ops.wgrad_splits(rows, 256, 768, 1))
+    ops.conv_wgrad(dgi, ctx.f, G.w_ih, 1, rows, 1, 512, 1536, 1, ops.wgrad_splits(rows, 512, 1536, 1))
+    w_ih_t = torch.empty(512, 1536, **f32)
+    call("tag_weight_flip_transpose", Wt.w_ih, w_ih_t, 1536, 512, 1)
+    df = torch.empty(rows, 512, **f32)
+    ops.conv_fwd(dgi, w_ih_t, df, None, False, None, 1, rows, 1, 1536, 512, 1)
+
+    # ---- fc1
+    dpre = torch.empty(rows, 512, **act)
+    call("tag_relu_bwd", df, ops.F32, ctx.f, ops.dt(ctx.f), dpre, ops.dt(dpre), df.numel())
+    call("tag_colsum", dpre, ops.dt(dpre), rows, 512, G.fc_b)
+    ops.conv_wgrad(dpre, ctx.m, G.fc_w, 1, rows, 1, 512, 512, 1, ops.wgrad_splits(rows, 512, 512, 1))
+    fc_t = torch.empty(512, 512, **f32)
+    call("tag_weight_flip_transpose", Wt.fc_w, fc_t, 512, 512, 1)
+    dm = torch.empty(rows, 512, **act)
+    ops.conv_fwd(dpre, fc_t, dm, None, False, None, 1, rows, 1, 512, 512, 1)
+
+    # ---- frequency mean (+dropout)
+    Wf = ctx.p[3].shape[2]
+    dp = torch.empty_like(ctx.p[3])
+    call("tag_freq_mean_bwd", dm, ops.dt(dm), dp, ops.dt(dp), rows, Wf, 512, p_fc,
+         _seed_for(ctx.seed, 4), ctx.seed_dev)
+
+    # ---- conv blocks, last to first
+    bn_tr = int(ctx.bn_training)
+    for blk in range(3, -1, -1):
+        cin, cout = CHANNELS[blk]
+        ph, pw = POOLS[blk]
+        H, W = ctx.dims[blk]
+        y1, y2 = ctx.y[2 * blk], ctx.y[2 * blk + 1]
+        a1 = ctx.a[blk]
+        aux1, aux2 = ctx.bn_aux[1 + 2 * blk], ctx.bn_aux[2 + 2 * blk]
+        P = B * H * W
+        # bn2 + relu + pool + dropout
+        red = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
+        seed = _seed_for(ctx.seed, blk)
+        call("tag_bn_relu_pool_bwd", 0, y2, dp, None, ops.dt(y2), aux2[0], aux2[1], aux2[2], aux2[3], red,
+             bn_tr, B, H, W, cout, ph, pw, p_blk, seed, ctx.seed_dev)
+        dg, dbt = G.bn[2 + 2 * blk]
+        call("tag_bn_param_grads", red, cout, dg, dbt)
+        dy2 = torch.empty_like(y2)
+        call("tag_bn_relu_pool_bwd", 1, y2, dp, dy2, ops.dt(y2), aux2[0], aux2[1], aux2[2], aux2[3], red,
+             bn_tr, B, H, W, cout, ph, pw, p_blk, seed, ctx.seed_dev)
+        # conv2
+        ops.conv_wgrad(dy2, a1, G.conv[2 * blk + 1], B, H, W, cout, cout, 9,
+                       ops.wgrad_splits(P, cout, cout, 9))
+        w2t = torch.empty(cout * 9 * cout, **f32)
+        call("tag_weight_flip_transpose", Wt.conv[2 * blk + 1], w2t, cout, cout, 9)
+        da1 = torch.empty_like(a1)
+        ops.conv_fwd(dy2, w2t, da1, None, False, None, B, H, W, cout, cout, 9)
+        del dy2
+        # bn1 + relu
+        red1 = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
+        call("tag_bn_relu_pool_bwd", 0, y1, da1, None, ops.dt(y1), aux1[0], aux1[1], aux1[2], aux1[3], red1,
+             bn_tr, B, H, W, cout, 0, 0, 0.0, 0, None)
+        dg, dbt = G.bn[1 + 2 * blk]
+        call("tag_bn_param_grads", red1, cout, dg, dbt)
+        dy1 = torch.empty_like(y1)
+        call("tag_bn_relu_pool_bwd", 1, y1, da1, dy1, ops.dt(y1), aux1[0], aux1[1], aux1[2], aux1[3], red1,
+             bn_tr, B, H, W, cout, 0, 0, 0.0, 0, None)
+        del da1
+        # conv1
+        if cin == 1:
+            dx0 = torch.empty(B, H, W, **f32)
+            call("tag_conv_c1_bwd", dy1, ctx.x0, Wt.conv[0], ops.dt(dy1), G.conv[0], dx0, B, H, W)
+            red0 = torch.zeros(2 * N_MELS, device=dev, dtype=torch.float64)
+            aux0 = ctx.bn_aux[0]
+            call("tag_bn_bwd_reduce_f32", dx0, ctx.db, aux0[2], aux0[3], B * H, N_MELS, red0)
+            dg, dbt = G.bn[0]
+            call("tag_bn_param_grads", red0, N_MELS, dg, dbt)
+        else:
+            x_in = ctx.p[blk - 1]
+            ops.conv_wgrad(dy1, x_in, G.conv[2 * blk], B, H, W, cin, cout, 9,
+                           ops.wgrad_splits(P, cin, cout, 9))
+            w1t = torch.empty(cin * 9 * cout, **f32)
+            call("tag_weight_flip_transpose", Wt.conv[2 * blk], w1t, cout, cin, 9)
+            dp = torch.empty_like(x_in)
+            ops.conv_fwd(dy1, w1t, dp, None, False, None, B, H, W, cout, cin, 9)
+        del dy1

@@ -1,0 +1,235 @@
+"""Training-step plumbing of the strong-supervision runner.
+
+* ``runner_forward`` / ``train_step`` mirror Runner.forward and the body of Runner.train_epoch
+  (reference python_scripts/training/run_strong.py:92-120 and :139-147) on top of the mirrored
+  nn.Modules (autograd path; any torch optimizer works).
+* ``FusedTrainStep`` is the production path: all parameters, gradients and Adam moments live
+  in flat fp32 buffers, the whole step (forward, backward, clip_grad_norm_, Adam) is a fixed
+  sequence of libtag_b200 kernels captured in CUDA graphs, and data parallelism is one NCCL
+  all-reduce of the flat gradient bucket per step (batches shard by clip; BN statistics stay
+  per rank, as in the reference's single-process semantics).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import engine, ops
+from .losses import FrameBceLoss
+from .ops import call
+
+
+def runner_forward(model: nn.Module, batch: Dict, device, training: bool = True) -> Dict:
+    """Runner.forward (run_strong.py:92-120): move tensors, inject specaug=False, run the model,
+    truncate frame_sim/label to a common length and clamp length."""
+    b = {}
+    for k, v in batch.items():
+        if isinstance(v, torch.Tensor):
+            b[k] = v.long().to(device) if k == "text" else v.float().to(device)
+        else:
+            b[k] = v
+    input_dict = {"specaug": False}
+    input_dict.update(b)
+    output = model(input_dict)
+    if training:
+        label = b["label"]
+        frame_sim = output["frame_sim"]
+        trunc = min(frame_sim.size(1), label.size(1))
+        output.update({
+            "frame_sim": frame_sim[..., :trunc],
+            "label": label[..., :trunc],
+            "length": torch.clamp(output["length"], 1, trunc),
+        })
+    return output
+
+
+def train_step(model: nn.Module, batch: Dict, optimizer: torch.optim.Optimizer, loss_fn=None,
+               max_grad_norm: float = 1.0, device="cuda"):
+    """One iteration of Runner.train_epoch (run_strong.py:139-147)."""
+    loss_fn = loss_fn or FrameBceLoss()
+    optimizer.zero_grad()
+    output = runner_forward(model, batch, device, training=True)
+    loss = loss_fn(output)
+    loss.backward()
+    total_norm = torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)
+    optimizer.step()
+    return loss, total_norm
+
+
+class FusedTrainStep:
+    """Flat-buffer, CUDA-graph-captured train step for BiEncoder(Cnn8Rnn, EmbeddingAgg, DotProduct)."""
+
+    def __init__(self, model: nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 max_grad_norm: float = 1.0, process_group=None, use_graph: bool = True,
+                 base_seed: int = 1):
+        self.model = model
+        self.enc = model.audio_encoder
+        self.txt = model.text_encoder
+        self.lr, self.betas, self.eps, self.max_grad_norm = lr, betas, eps, max_grad_norm
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.use_graph = use_graph
+        self.base_seed = base_seed
+        self.scale = 1.0 / (self.enc.embed_dim ** 0.5) if getattr(model.match_fn, "scale", True) else 1.0
+        self.device = next(model.parameters()).device
+        self._flatten()
+        self._graphs = {}
+        self._static = None
+        self._calls = 0
+
+    # ------------------------------------------------------------------ flat buffers
+    def _flatten(self):
+        params = self.enc._param_list() + [self.txt.embedding.core.weight]
+        if not all(p.requires_grad for p in params):
+            raise NotImplementedError("FusedTrainStep trains all parameters; use the autograd path "
+                                      "(train_step) with frozen sub-modules")
+        known = {id(p) for p in params}
+        extra = [n for n, p in self.model.named_parameters() if id(p) not in known]
+        if extra:
+            raise NotImplementedError(f"parameters outside the fused path: {extra}")
+        n = sum(p.numel() for p in params)
+        dev = self.device
+        self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.n_params = n
+        off = 0
+        self._views = []
+        for p in params:
+            k = p.numel()
+            if p.dim() == 4:      # conv weight: keep [Cout][kh][kw][Cin] memory, [Cout,Cin,3,3] shape
+                co, ci, kh, kw = p.shape
+                pv = self.flat_p[off:off + k].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+                gv = self.flat_g[off:off + k].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+            else:
+                pv = self.flat_p[off:off + k].view(p.shape)
+                gv = self.flat_g[off:off + k].view(p.shape)
+            pv.copy_(p.data)
+            p.data = pv
+            p.grad = gv
+            self._views.append((off, k))
+            off += k
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.norm_out = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.loss_out = torch.zeros((), device=dev, dtype=torch.float32)
+        self.Wt = self.enc._weights()
+        assert self.Wt.w_ih.data_ptr() == self.enc.rnn.weight_ih_l0.data_ptr()
+        self.G = self._grad_bundle()
+
+    def _grad_bundle(self) -> engine.EncoderGrads:
+        enc = self.enc
+        r = enc.rnn
+        from .models.audio_encoder import _cat_if_needed, _packed_conv
+        return engine.EncoderGrads(
+            bn=[(bn.weight.grad, bn.bias.grad) for bn in enc._bns()],
+            conv=[_packed_conv(c.weight.grad) for c in enc._convs()],
+            fc_w=enc.fc1.weight.grad, fc_b=enc.fc1.bias.grad,
+            w_ih=_cat_if_needed(r.weight_ih_l0.grad, r.weight_ih_l0_reverse.grad),
+            b_ih=_cat_if_needed(r.bias_ih_l0.grad, r.bias_ih_l0_reverse.grad),
+            w_hh=_cat_if_needed(r.weight_hh_l0.grad, r.weight_hh_l0_reverse.grad).view(2, 768, 256),
+            b_hh=_cat_if_needed(r.bias_hh_l0.grad, r.bias_hh_l0_reverse.grad))
+
+    # ------------------------------------------------------------------ the step
+    def _fwd_bwd(self, wav, text, text_len, label, length):
+        """Forward + backward into flat_g; returns nothing (loss in self.loss_out)."""
+        enc = self.enc
+        self.flat_g.zero_()
+        emb, ectx = engine.encoder_forward(
+            self.Wt, wav, training=True, bn_training=enc.bn0.training, dropout=enc.dropout_enabled,
+            seed=self.base_seed, dtype=enc.compute_dtype, save=True, seed_dev=self.step_dev)
+        B, Tp, D = emb.shape
+        ew = self.txt.embedding.core.weight
+        V = ew.shape[0]
+        N = text.shape[1]
+        seq = torch.empty(B, D, device=emb.device, dtype=torch.float32)
+        call("tag_embed_mean_fwd", text, text_len, ew.data, None, seq, B, N, D, V)
+        sim = torch.empty(B, Tp, device=emb.device, dtype=torch.float32)
+        call("tag_dot_sigmoid_fwd", emb, seq, sim, None, B, Tp, D, self.scale)
+        trunc = min(Tp, label.shape[1])
+        d_sim = torch.zeros(B, Tp, device=emb.device, dtype=torch.float32)
+        call("tag_frame_bce", sim, Tp, label, label.stride(0), length, B, trunc, self.loss_out, d_sim, Tp, 1.0)
+        d_emb = torch.empty_like(emb)
+        d_seq = torch.empty_like(seq)
+        ws = torch.empty(B, Tp, device=emb.device, dtype=torch.float32)
+        call("tag_dot_sigmoid_bwd", d_sim, sim, emb, seq, d_emb, d_seq, ws, B, Tp, D, self.scale)
+        call("tag_embed_mean_bwd", text, text_len, d_seq, ew.grad, B, N, D, V)
+        engine.encoder_backward(self.Wt, ectx, d_emb, self.G)
+        self.sim = sim
+
+    def _optim(self):
+        self.sumsq.zero_()
+        call("tag_sumsq", self.flat_g, self.n_params, self.sumsq)
+        call("tag_clip_adam", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_params,
+             self.sumsq, self.step_dev, 1.0 / self.world, float(self.max_grad_norm), float(self.lr),
+             float(self.betas[0]), float(self.betas[1]), float(self.eps), self.norm_out)
+
+    def _allreduce(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.pg)
+
+    def _eager(self, s):
+        self._fwd_bwd(s["waveform"], s["text"], s["text_len"], s["label"], s["length"])
+        self._allreduce()
+        self._optim()
+
+    def _prepare_static(self, batch: Dict):
+        """Device-resident static input buffers (graph inputs)."""
+        dev = self.device
+        wav = batch["waveform"]
+        B, L = wav.shape
+        Tp = (L // engine.HOP + 1) // 4
+        label = batch["label"]
+        trunc = min(Tp, label.shape[1])
+        key = (B, L, batch["text"].shape[1], label.shape[1])
+        if self._static is None or self._static["key"] != key:
+            self._static = {
+                "key": key,
+                "waveform": torch.empty(B, L, device=dev, dtype=torch.float32),
+                "text": torch.empty(B, batch["text"].shape[1], device=dev, dtype=torch.long),
+                "text_len": torch.empty(B, device=dev, dtype=torch.long),
+                "label": torch.empty(B, label.shape[1], device=dev, dtype=torch.float32),
+                "length": torch.empty(B, device=dev, dtype=torch.long),
+            }
+            self._graphs = {}
+        s = self._static
+        s["waveform"].copy_(wav, non_blocking=True)
+        s["text"].copy_(batch["text"], non_blocking=True)
+        s["text_len"].copy_(torch.as_tensor(batch["text_len"]).to(torch.long), non_blocking=True)
+        s["label"].copy_(label, non_blocking=True)
+        length = torch.as_tensor(batch["waveform_len"]).to(torch.long)
+        length = torch.clamp((length // engine.HOP + 1) // 4, 1, trunc)      # run_strong.py:107-118
+        s["length"].copy_(length, non_blocking=True)
+        return s
+
+    def step(self, batch: Dict) -> torch.Tensor:
+        """One train step on ``batch`` (collate schema; host or device tensors).  Returns the
+        device scalar holding the loss of this step."""
+        s = self._prepare_static(batch)
+        if self.enc.training:
+            for bn in self.enc._bns():
+                if bn.training:
+                    bn.num_batches_tracked += 1
+        self._calls += 1
+        if not self.use_graph or self._calls == 1:
+            # the first step runs eagerly (sets kernel attributes, primes the allocator)
+            self._eager(s)
+            return self.loss_out
+        if not self._graphs:
+            torch.cuda.synchronize()
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._fwd_bwd(s["waveform"], s["text"], s["text_len"], s["label"], s["length"])
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self._optim()
+            self._graphs = {"fwd_bwd": g1, "optim": g2}      # capture executes nothing
+        self._graphs["fwd_bwd"].replay()
+        self._allreduce()
+        self._graphs["optim"].replay()
+        return self.loss_out
