@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py — clips/s of the cnn8rnn-w2vmean train step (fwd + bwd + clip + Adam) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16|fp32]
+
+One "step" = one pass of the hot path over one batch of 64 synthetic 10 s @ 32 kHz clips with
+8-token phrases PER GPU (weak scaling; BASELINE.json configs[2]).  Prints ONE JSON line (rank 0).
+`value` is device-timed with inputs resident in HBM; `e2e` runs the same step through the public
+API (`FusedTrainStep.step(host_batch)`) with pinned host buffers, H2D copies and the loss D2H read
+inside the timed region.  `--impl reference` times the CPU restatement of the reference's train
+step (oracle/, torch CPU ops with all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "clips/sec (10 s @32 kHz, bs=64) cnn8rnn-w2vmean fwd+bwd at 1/2/4/8 B200"
+BATCH = 64
+N_SAMPLES = 320000
+N_TOKENS = 8
+FWD_GFLOP_PER_CLIP = 33.83          # conv 33.11 + fc1 0.131 + GRU 0.590
+TRAIN_GFLOP_PER_CLIP = 3 * FWD_GFLOP_PER_CLIP
+
+
+def cpu_reference_step_time(batch_size: int, n_samples: int, steps: int, warmup: int):
+    """Seconds per train step of the CPU restatement (oracle) on all host threads."""
+    import torch
+    from oracle import tag_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    sd = O.synth_state_dict(seed=1)
+    batch = O.synth_batch(batch_size, n_samples, N_TOKENS, seed=0, tonal=False)
+    opt = O.AdamState(O.trainable_keys())
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.train_step(sd, batch, opt, dropout=True, fast_gru=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    times.sort()
+    return times[len(times) // 2], os.cpu_count()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    bs = 8
+    sec, cores = cpu_reference_step_time(bs, N_SAMPLES, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    v = bs / sec
+    sample = f"train step on {bs} of the 64 clips (10 s @32 kHz, 8 tokens), median of {max(1, min(args.steps, 3))}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cnn8rnn-w2vmean train step, bs=64/GPU, 10 s @32 kHz clips, 8-token phrases"},
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from texttoaudiogrounding_b200 import _lib, ops
+    from texttoaudiogrounding_b200.models.audio_encoder import Cnn8Rnn
+    from texttoaudiogrounding_b200.models.audio_text_model import BiEncoder
+    from texttoaudiogrounding_b200.models.match import DotProduct
+    from texttoaudiogrounding_b200.models.text_encoder import EmbeddingAgg
+    from texttoaudiogrounding_b200.train import FusedTrainStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not os.path.exists(_lib.LIB_PATH):
+        raise RuntimeError("libtag_b200.so missing: run __graft_entry__.build() (no fallback path)")
+
+    B = args.batch
+    torch.manual_seed(1)
+    model = BiEncoder(Cnn8Rnn(32000, compute_dtype=args.precision), EmbeddingAgg(5221, 512), DotProduct(), 512)
+    model = model.cuda().train()
+    ts = FusedTrainStep(model, lr=1e-3, max_grad_norm=1.0, use_graph=not args.no_graph, base_seed=1 + rank)
+
+    g = torch.Generator().manual_seed(100 + rank)
+    host = {
+        "waveform": (0.1 * torch.randn(B, N_SAMPLES, generator=g)).pin_memory(),
+        "waveform_len": torch.full((B,), N_SAMPLES, dtype=torch.long).pin_memory(),
+        "text": torch.randint(2, 5221, (B, N_TOKENS), generator=g).pin_memory(),
+        "text_len": torch.full((B,), N_TOKENS, dtype=torch.long).pin_memory(),
+        "label": (torch.rand(B, 251, generator=g) > 0.5).float().pin_memory(),
+    }
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (first step eager, second captures the graphs)
+    launches0 = ops.LAUNCHES
+    ts.step(host)
+    launches_per_step = ops.LAUNCHES - launches0
+    for _ in range(args.warmup - 1):
+        ts.step(host)
+    barrier()
+
+    # ---- device-resident timing
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ts.step(None)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    loss_dev = float(ts.loss_out.item())
+
+    # ---- end-to-end timing through the public API with host buffers
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    last = 0.0
+    for _ in range(args.steps):
+        last = ts.step(host).item()           # D2H read of the step's loss
+    f1.record()
+    barrier()
+    ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms, max(ms_e2e, 0.0), wall_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, wall_e2e = [float(x) for x in t.tolist()]
+    ms_e2e = max(ms_e2e, wall_e2e)            # the host-visible time bounds the end-to-end figure
+
+    # ---- live per-kernel timing of one eager step (CUDA events around every C-ABI call)
+    roofline, kernels = None, None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        ts_use_graph = ts.use_graph
+        ts.use_graph = False
+        ops.PROFILE = []
+        ts.step(None)
+        torch.cuda.synchronize()
+        recs, ops.PROFILE = ops.PROFILE, None
+        ts.use_graph = ts_use_graph
+        agg = {}
+        total_ms = 0.0
+        for name, tag, flops, nbytes, s, e in recs:
+            d = s.elapsed_time(e)
+            total_ms += d
+            a = agg.setdefault(name, {"ms": 0.0, "launches": 0, "flops": 0.0})
+            a["ms"] += d; a["launches"] += 1; a["flops"] += flops
+        top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
+        kernels = {k: {"ms_per_step": round(v["ms"], 3), "launches": v["launches"],
+                       "share": round(v["ms"] / total_ms, 4),
+                       **({"tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)} if v["flops"] else {})}
+                   for k, v in top[:8]}
+        dom_name, dom = top[0]
+        if dom["flops"] > 0:
+            peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            ach = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
+            roofline = {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                        if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
+                        "flops_per_launch": dom["flops"] / dom["launches"],
+                        "avg_launch_ms": dom["ms"] / dom["launches"], "launches_per_step": dom["launches"],
+                        "share_of_step": dom["ms"] / total_ms}
+        else:
+            peak = peaks.get("hbm_gbs", 6650.0)
+            roofline = {"kernel": dom_name, "bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s",
+                        "frac": None, "traffic": None}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        bs = 8
+        sec, cores = cpu_reference_step_time(bs, N_SAMPLES, 2, 1)
+        cpu_baseline = {"value": bs / sec, "unit": "clips/s", "cores": cores, "kind": "port",
+                        "sample": f"oracle train step on {bs} of the 64 clips (10 s @32 kHz), median of 2 after 1 warm-up"}
+
+    if rank == 0:
+        clips = B * world * args.steps
+        value = clips / (ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"cnn8rnn-w2vmean full train step (fwd+bwd+clip+Adam), bs={B}/GPU, "
+                                   "10 s @32 kHz clips, 8-token phrases (BASELINE.json configs[2])",
+                       "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (>5 GB of activations) is far larger than the 126 MB L2",
+                       "cuda_graph": ts.use_graph, "dropout": True},
+            "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "launches_per_step": launches_per_step,
+            "clocks": clocks, "loss": last, "loss_resident": loss_dev,
+            "algorithmic_tflops": value * TRAIN_GFLOP_PER_CLIP / 1e3 / world,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -623,7 +623,8 @@ static int pool_bwd_dispatch(const void* y, const void* dout, void* dy, const fl
     const int CV = C / 8;
     if (CV > 256 || 256 % CV != 0) return TAG_ERR_BAD_ARG;
     const int spb = 256 / CV;
-    const long n_slots = (long)B * ((H + ph - 1) / ph) * ((W + pw - 1) / pw);
+    const int ph_e = ph > 0 ? ph : 1, pw_e = pw > 0 ? pw : 1;
+    const long n_slots = (long)B * ((H + ph_e - 1) / ph_e) * ((W + pw_e - 1) / pw_e);
     const int blocks = grid_for((n_slots + spb - 1) / spb, 1, 148 * 8);
 #define TAG_LAUNCH_POOL_BWD(PH_, PW_, POOL_)                                                          \
     bn_relu_pool_bwd_kernel<T, PH_, PW_, POOL_, MODE><<<blocks, 256, 0, stream>>>(                     \

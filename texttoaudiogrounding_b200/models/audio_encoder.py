@@ -96,7 +96,7 @@ class _Cnn8RnnFunction(torch.autograd.Function):
     def forward(ctx, module, waveform, *params):
         training = module.training
         Wt = module._weights()
-        save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        save = any(ctx.needs_input_grad)
         module._call_count += 1
         seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * module._call_count) & 0x7FFFFFFFFFFFFFFF
         out, ectx = engine.encoder_forward(

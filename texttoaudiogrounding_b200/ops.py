@@ -43,10 +43,12 @@ def call(name: str, *args) -> None:
 
 
 def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps):
+    annotate(f"fwd M={B * H * W} N={Cout} K={taps * Cin}", 2.0 * B * H * W * Cout * taps * Cin)
     call("tag_conv_fwd", x, dt(x), w, y, dt(y), bias, int(relu), stats, B, H, W, Cin, Cout, taps)
 
 
 def conv_wgrad(dy, x, dw, B, H, W, Cin, Cout, taps, splits):
+    annotate(f"wgrad P={B * H * W} Cout={Cout} K={taps * Cin}", 2.0 * B * H * W * Cout * taps * Cin)
     call("tag_conv_wgrad", dy, dt(dy), x, dt(x), dw, B, H, W, Cin, Cout, taps, splits)
 
 
@@ -66,3 +68,33 @@ def bn_finalize(stats, count, C, gamma, beta, rm, rv, momentum, eps, training, u
 
 def scale_shift_act(x, y, scale, shift, C, relu):
     call("tag_scale_shift_act", x, dt(x), y, dt(y), scale, shift, x.numel(), C, int(relu))
+
+
+# ---------------------------------------------------------------------------------------------
+# Live per-kernel timing (bench.py): when PROFILE is a list, every C-ABI call is bracketed by
+# CUDA events on the launching stream and recorded as [name, tag, flops, bytes, start, end].
+PROFILE = None
+_PENDING_META = None
+
+
+def annotate(tag: str, flops: float = 0.0, nbytes: float = 0.0) -> None:
+    """Attach a shape tag and the algorithmic FLOPs / bytes to the next call (profiling only)."""
+    global _PENDING_META
+    if PROFILE is not None:
+        _PENDING_META = (tag, flops, nbytes)
+
+
+_plain_call = call
+
+
+def call(name: str, *args) -> None:  # noqa: F811  (profiling wrapper around the plain call)
+    global _PENDING_META
+    if PROFILE is None:
+        return _plain_call(name, *args)
+    meta, _PENDING_META = _PENDING_META or ("", 0.0, 0.0), None
+    s = torch.cuda.Event(enable_timing=True)
+    e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    _plain_call(name, *args)
+    e.record()
+    PROFILE.append([name, meta[0], meta[1], meta[2], s, e])

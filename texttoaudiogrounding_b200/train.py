@@ -207,10 +207,11 @@ class FusedTrainStep:
         s["length"].copy_(length, non_blocking=True)
         return s
 
-    def step(self, batch: Dict) -> torch.Tensor:
+    def step(self, batch: Optional[Dict]) -> torch.Tensor:
         """One train step on ``batch`` (collate schema; host or device tensors).  Returns the
-        device scalar holding the loss of this step."""
-        s = self._prepare_static(batch)
+        device scalar holding the loss of this step.  ``batch=None`` re-uses the inputs already
+        resident in the static device buffers (device-only timing)."""
+        s = self._static if batch is None else self._prepare_static(batch)
         if self.enc.training:
             for bn in self.enc._bns():
                 if bn.training:
