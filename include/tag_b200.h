@@ -69,6 +69,16 @@ int tag_conv_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype, flo
                    int W, int Cin, int Cout, int taps, int splits, cudaStream_t stream);
 int tag_weight_flip_transpose(const float* w, float* wt, int Co, int Ci, int taps, cudaStream_t stream);
 
+/* bf16 tensor-core (tcgen05 + TMA) versions of the two contractions above.  x / dy are bf16 NHWC,
+ * w is bf16 [Cout][taps*Cin] (tag_cast_f32_to_bf16 of the fp32 master, or
+ * tag_weight_flip_transpose_bf16 for dgrad), y is bf16 or fp32, dw is fp32 (accumulated).
+ * Requirements: Cin, Cout multiples of 64; W in {1,2,4,...,64}. */
+int tag_conv_tc_fwd(const void* x, const void* w, void* y, int y_dtype, const float* bias, int relu,
+                    double* stats, int B, int H, int W, int Cin, int Cout, int taps, cudaStream_t stream);
+int tag_conv_tc_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout,
+                      int taps, int splits, cudaStream_t stream);
+int tag_weight_flip_transpose_bf16(const float* w, void* wt, int Co, int Ci, int taps, cudaStream_t stream);
+
 /* ---- BN + ReLU + avg+max pool + dropout — models/panns.py:50-58, audio_encoder.py:202-211 */
 int tag_bn_relu_pool_fwd(const void* y, void* out, int dtype, const float* scale, const float* shift,
                          int B, int H, int W, int C, int ph, int pw, float dropout_p, uint64_t seed,

@@ -1,0 +1,121 @@
+"""tcgen05 implicit-GEMM kernels (through the C ABI) against fp32 PyTorch convolutions of the same
+bf16-rounded operands, on every (W, Cin, Cout) shape the model uses plus odd heights / batches
+(TMA out-of-bounds halo, partial M tiles, multi-tile persistence, accumulator double buffering)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def g(seed=0):
+    return torch.Generator().manual_seed(seed)
+
+
+def _bf(x):
+    return x.bfloat16().float()
+
+
+SHAPES = [
+    # B, H, W, Cin, Cout
+    (2, 13, 64, 64, 64),      # block 1 conv2 (TH = 2, odd H -> clipped tile)
+    (3, 10, 32, 64, 128),     # block 2 conv1
+    (2, 9, 32, 128, 128),     # block 2 conv2
+    (2, 17, 16, 128, 256),    # block 3 conv1
+    (1, 25, 16, 256, 256),    # block 3 conv2
+    (3, 50, 8, 256, 512),     # block 4 conv1 (two N tiles)
+    (2, 33, 8, 512, 512),     # block 4 conv2
+    (40, 50, 8, 256, 512),    # > 148 tiles: persistent loop + both TMEM stages
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", SHAPES)
+def test_tc_conv3x3_fwd(B, H, W, Cin, Cout):
+    from texttoaudiogrounding_b200 import ops
+    x = _bf(torch.randn(B, Cin, H, W, generator=g(1)))
+    w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g(2)) * (1.0 / (3 * Cin ** 0.5)))
+    ref = F.conv2d(x.cuda(), w.cuda(), padding=1).permute(0, 2, 3, 1).contiguous()   # fp32 NHWC
+    xn = x.permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
+    wp = w.permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
+    # fp32 output + statistics
+    y32 = torch.empty(B, H, W, Cout, device="cuda")
+    stats = torch.zeros(2 * Cout, device="cuda", dtype=torch.float64)
+    ops.conv_fwd(xn, wp, y32, None, False, stats, B, H, W, Cin, Cout, 9)
+    torch.cuda.synchronize()
+    assert rel_err(y32, ref) < 2e-3, rel_err(y32, ref)
+    np.testing.assert_allclose(stats[:Cout].cpu().numpy(), y32.double().sum((0, 1, 2)).cpu().numpy(),
+                               rtol=1e-3, atol=1e-2)
+    np.testing.assert_allclose(stats[Cout:].cpu().numpy(), y32.double().pow(2).sum((0, 1, 2)).cpu().numpy(),
+                               rtol=1e-3)
+    # bf16 output
+    yb = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    ops.conv_fwd(xn, wp, yb, None, False, None, B, H, W, Cin, Cout, 9)
+    assert rel_err(yb.float(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", SHAPES[:7])
+def test_tc_conv3x3_dgrad_and_wgrad(B, H, W, Cin, Cout):
+    from texttoaudiogrounding_b200 import ops
+    x = _bf(torch.randn(B, Cin, H, W, generator=g(3))).cuda().requires_grad_(True)
+    w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g(4)) * (1.0 / (3 * Cin ** 0.5))).cuda().requires_grad_(True)
+    dy = _bf(torch.randn(B, Cout, H, W, generator=g(5))).cuda()
+    F.conv2d(x, w, padding=1).backward(dy)
+    xn = x.detach().permute(0, 2, 3, 1).contiguous().bfloat16()
+    dyn = dy.permute(0, 2, 3, 1).contiguous().bfloat16()
+    wp32 = w.detach().permute(0, 2, 3, 1).contiguous()
+    wt = ops.prep_weight_t(wp32, Cout, Cin, 9, torch.bfloat16)
+    dx = torch.empty(B, H, W, Cin, device="cuda")
+    ops.conv_fwd(dyn, wt, dx, None, False, None, B, H, W, Cout, Cin, 9)
+    assert rel_err(dx.permute(0, 3, 1, 2), x.grad) < 2e-3, rel_err(dx.permute(0, 3, 1, 2), x.grad)
+    dw = torch.zeros(Cout, 3, 3, Cin, device="cuda")
+    ops.conv_wgrad(dyn, xn, dw, B, H, W, Cin, Cout, 9, 1)
+    torch.cuda.synchronize()
+    assert rel_err(dw.permute(0, 3, 1, 2), w.grad) < 2e-3, rel_err(dw.permute(0, 3, 1, 2), w.grad)
+
+
+@pytest.mark.parametrize("M,K,N", [(300, 512, 512), (1000, 512, 1536), (16000, 1536, 512)])
+def test_tc_linear_fwd_and_wgrad(M, K, N):
+    from texttoaudiogrounding_b200 import ops
+    x = _bf(torch.randn(M, K, generator=g(6))).cuda()
+    w = _bf(torch.randn(N, K, generator=g(7)) * 0.03).cuda()
+    b = torch.randn(N, generator=g(8)).cuda()
+    ref = F.relu(F.linear(x, w, b))
+    y = torch.empty(M, N, device="cuda")
+    ops.conv_fwd(x.bfloat16(), w.bfloat16(), y, b, True, None, 1, M, 1, K, N, 1)
+    assert rel_err(y, ref) < 2e-3, rel_err(y, ref)
+    dy = _bf(torch.randn(M, N, generator=g(9))).cuda()
+    dw = torch.zeros(N, K, device="cuda")
+    ops.conv_wgrad(dy.bfloat16(), x.bfloat16(), dw, 1, M, 1, K, N, 1, 1)
+    ref_dw = dy.t() @ x
+    assert rel_err(dw, ref_dw) < 2e-3, rel_err(dw, ref_dw)
+
+
+def test_tc_matches_simt_on_model_shapes_end_to_end():
+    """Same bf16 train step with the tensor-core kernels and with the SIMT kernels."""
+    from oracle import tag_oracle as O
+    from helpers import build_model
+    from texttoaudiogrounding_b200 import ops
+    from texttoaudiogrounding_b200.train import FusedTrainStep
+    sd = O.synth_state_dict(seed=1, sharpen=300.0, perturb_bn=True)
+    batch = O.synth_batch(4, 64000, seed=0)
+    res = {}
+    for use_tc in (True, False):
+        ops.USE_TC = use_tc
+        try:
+            model = build_model(sd, "bf16")
+            model.train()
+            model.audio_encoder.dropout_enabled = False
+            ts = FusedTrainStep(model, use_graph=False)
+            loss = ts.step(batch).item()
+            torch.cuda.synchronize()
+            res[use_tc] = (loss, ts.norm_out.item(), ts.flat_g.clone())
+        finally:
+            ops.USE_TC = True
+    np.testing.assert_allclose(res[True][0], res[False][0], rtol=2e-2)
+    np.testing.assert_allclose(res[True][1], res[False][1], rtol=5e-2)
+    a, b = res[True][2], res[False][2]
+    cos = float((a * b).sum() / (a.norm() * b.norm()))
+    assert cos > 0.98, cos

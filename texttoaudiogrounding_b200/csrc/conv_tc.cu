@@ -1,0 +1,621 @@
+// bf16 implicit-GEMM convolutions on the 5th-generation tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+//   tag_conv_tc_fwd   : y[p, co] = sum_{tap,ci} x[p + d(tap), ci] * w[co][tap][ci]      (fwd and dgrad)
+//   tag_conv_tc_wgrad : dw[co][tap][ci] += sum_p dy[p, co] * x[p + d(tap), ci]
+//
+// Replaces the cuDNN conv fwd / dgrad / wgrad behind F.conv2d (reference models/panns.py:49-50)
+// and, with taps = 1, the cuBLAS GEMMs of fc1 and the GRU input projection
+// (models/audio_encoder.py:216-217).
+//
+// Forward tile: 128 output pixels (a TH x W patch of one clip, TH = 128 / W) x BLOCK_N output
+// channels.  For every (tap, 64-channel slab) the A operand is ONE 4-D TMA box of the NHWC
+// activation tensor whose start coordinate is shifted by the tap offset — the halo is produced
+// by TMA out-of-bounds zero fill, so there is no im2col buffer and no padding pass.  The B
+// operand is a 2-D box of the [Cout][tap*Cin] weight matrix.  Both land in 128B-swizzled
+// K-major shared memory and are consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16) with the fp32
+// accumulator in TMEM (double-buffered: the epilogue of tile i overlaps the MMAs of tile i+1).
+// Warp roles: warps 0-3 epilogue (TMEM -> registers -> bias/ReLU/round -> per-channel sum and
+// sum-of-squares for the following BatchNorm -> global), warp 4 TMA producer, warp 5 MMA issuer.
+//
+// wgrad tile: M = 128 rows of (tap, ci) — two 64-channel boxes of x, shifted by their tap —
+// x N = BLOCK_N output channels of dy, contracted over pixels.  Both operands are MN-major
+// (channels contiguous, pixels strided), which is exactly how NHWC boxes land in shared memory.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr uint32_t WAIT_SPIN_LIMIT = 1u << 24;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > WAIT_SPIN_LIMIT) __trap();     // never hang the GPU on a pipeline bug
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, bf16 x bf16 -> fp32.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// After the call lane l holds sum over the 32 lanes of a[l] (butterfly transpose-reduce, 31 shuffles).
+__device__ __forceinline__ float warp_transpose_sum(float (&a)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? a[i] : a[i + off];
+            const float keep = upper ? a[i + off] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return a[0];
+}
+
+constexpr int A_TILE_BYTES = 128 * 128;          // 128 pixels x 64 bf16 channels
+
+template <int BLOCK_N, int STAGES>
+struct FwdSmem {
+    static constexpr int B_TILE_BYTES = BLOCK_N * 128;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int STATS_OFFSET = BAR_OFFSET + 256;
+    static constexpr int TOTAL = STATS_OFFSET + 2 * BLOCK_N * 4 + 1024;   // +1024: manual alignment slack
+};
+
+template <int BLOCK_N, typename TO, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                   TO* __restrict__ y, const float* __restrict__ bias, int relu, double* __restrict__ stats,
+                   int B, int H, int W, int Cin, int Cout, int taps) {
+    using L = FwdSmem<BLOCK_N, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - raw);
+    const uint32_t full_bar = base + L::BAR_OFFSET;             // STAGES x 8 B
+    const uint32_t empty_bar = full_bar + 8 * STAGES;           // STAGES x 8 B
+    const uint32_t tmem_full = empty_bar + 8 * STAGES;          // 2 x 8 B
+    const uint32_t tmem_empty = tmem_full + 16;                 // 2 x 8 B
+    const uint32_t tmem_slot = tmem_empty + 16;                 // 4 B
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L::BAR_OFFSET + 16 * STAGES + 32);
+    float* s_stats = reinterpret_cast<float*>(base_ptr + L::STATS_OFFSET);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int TH = 128 / W;
+    const int tiles_h = (H + TH - 1) / TH;
+    const int m_tiles = B * tiles_h;
+    const int n_tiles = Cout / BLOCK_N;
+    const int total_tiles = m_tiles * n_tiles;
+    const int KC = Cin / 64;
+    const int k_blocks = taps * KC;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + 8 * a, 1); mbar_init(tmem_empty + 8 * a, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
+    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x < 2 * BLOCK_N && threadIdx.x < 128) {
+        for (int i = threadIdx.x; i < 2 * BLOCK_N; i += 128) s_stats[i] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile / m_tiles, m_tile = tile - n_tile * m_tiles;
+                const int b = m_tile / tiles_h, h0 = (m_tile - b * tiles_h) * TH;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    const int tap = kb / KC, kc = kb - tap * KC;
+                    const int dh = taps == 9 ? tap / 3 - 1 : 0;
+                    const int dw = taps == 9 ? tap % 3 - 1 : 0;
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    mbar_arrive_expect_tx(full_bar + 8 * stage, L::STAGE_BYTES);
+                    const uint32_t sa = base + stage * L::STAGE_BYTES;
+                    tma_load_4d(sa, &tmap_x, full_bar + 8 * stage, kc * 64, dw, h0 + dh, b);
+                    tma_load_2d(sa + A_TILE_BYTES, &tmap_w, full_bar + 8 * stage, kb * 64, n_tile * BLOCK_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 0, 0);
+        int stage = 0; uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(tmem_empty + 8 * as, aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait(full_bar + 8 * stage, phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = base + stage * L::STAGE_BYTES;
+                    const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+                    const uint64_t bdesc = make_smem_desc(sa + A_TILE_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(empty_bar + 8 * stage);          // frees the smem slot when the MMAs retire
+                    if (kb == k_blocks - 1) umma_commit(tmem_full + 8 * as);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 0-3; warp w owns TMEM lanes 32w..32w+31) =====================
+        int it = 0;
+        int cur_n_tile = -1;
+        auto flush_stats = [&](int n_tile) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = threadIdx.x; i < BLOCK_N; i += 128) {
+                atomicAdd(stats + n_tile * BLOCK_N + i, (double)s_stats[i]);
+                atomicAdd(stats + Cout + n_tile * BLOCK_N + i, (double)s_stats[BLOCK_N + i]);
+                s_stats[i] = 0.f;
+                s_stats[BLOCK_N + i] = 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int n_tile = tile / m_tiles, m_tile = tile - n_tile * m_tiles;
+            const int b = m_tile / tiles_h, h0 = (m_tile - b * tiles_h) * TH;
+            if (stats != nullptr && cur_n_tile >= 0 && n_tile != cur_n_tile) flush_stats(cur_n_tile);
+            cur_n_tile = n_tile;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(tmem_full + 8 * as, aphase);
+            tc_fence_after();
+            const int row = warp * 32 + lane;
+            const int h = h0 + row / W, w = row - (row / W) * W;
+            const bool valid = h < H;
+            TO* yrow = y + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * BLOCK_N + c * 32, r);
+                tmem_ld_wait();
+                float v[32], q[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float f = __uint_as_float(r[j]);
+                    if (bias != nullptr) f += __ldg(bias + n_tile * BLOCK_N + c * 32 + j);
+                    if (relu) f = fmaxf(f, 0.f);
+                    f = round_to<TO>(f);
+                    v[j] = valid ? f : 0.f;
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) Vec4<TO>::store(yrow + c * 32 + j, &v[j]);
+                }
+                if (stats != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) q[j] = v[j] * v[j];
+                    const float cs = warp_transpose_sum(v, lane);
+                    const float cq = warp_transpose_sum(q, lane);
+                    atomicAdd(&s_stats[c * 32 + lane], cs);
+                    atomicAdd(&s_stats[BLOCK_N + c * 32 + lane], cq);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * as);
+        }
+        if (stats != nullptr && cur_n_tile >= 0) flush_stats(cur_n_tile);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: D[(tap,ci) 128, co BLOCK_N] = sum over 64-pixel K tiles; both operands MN-major.
+// ---------------------------------------------------------------------------------------------
+constexpr int WG_BOX_BYTES = 64 * 128;           // 64 pixels x 64 bf16 channels
+
+template <int BLOCK_N, int STAGES>
+struct WgSmem {
+    static constexpr int A_BYTES = 2 * WG_BOX_BYTES;
+    static constexpr int B_BYTES = (BLOCK_N / 64) * WG_BOX_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                     float* __restrict__ dw, int B, int H, int W, int Cin, int Cout, int taps,
+                     int m_blocks, int n_blocks, int k_tiles_per_split) {
+    using L = WgSmem<BLOCK_N, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - raw);
+    const uint32_t full_bar = base + L::BAR_OFFSET;
+    const uint32_t empty_bar = full_bar + 8 * STAGES;
+    const uint32_t tmem_full = empty_bar + 8 * STAGES;
+    const uint32_t tmem_slot = tmem_full + 8;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L::BAR_OFFSET + 16 * STAGES + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int THK = 64 / W > 0 ? 64 / W : 1;        // rows of one clip per 64-pixel K tile
+    const int tiles_h = (H + THK - 1) / THK;
+    const int k_tiles = B * tiles_h;
+
+    int wi = blockIdx.x;
+    const int m_blk = wi % m_blocks; wi /= m_blocks;
+    const int n_blk = wi % n_blocks; wi /= n_blocks;
+    const int split = wi;
+    const int kt_begin = split * k_tiles_per_split;
+    const int kt_end = min(k_tiles, kt_begin + k_tiles_per_split);
+    if (kt_begin >= kt_end) return;
+
+    // the two 64-row halves of the M tile: (tap, ci0) each
+    int tap_h[2], ci_h[2];
+    if (Cin >= 128) {
+        const int per_tap = Cin / 128;
+        tap_h[0] = tap_h[1] = m_blk / per_tap;
+        ci_h[0] = (m_blk % per_tap) * 128;
+        ci_h[1] = ci_h[0] + 64;
+    } else {                                         // Cin == 64: two taps share one M tile
+        tap_h[0] = 2 * m_blk;
+        tap_h[1] = min(2 * m_blk + 1, taps - 1);
+        ci_h[0] = ci_h[1] = 0;
+    }
+    const bool half1_live = (Cin >= 128) || (2 * m_blk + 1 < taps);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_dy); }
+    if (warp == 5) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kt = kt_begin; kt < kt_end; ++kt) {
+                const int b = kt / tiles_h, h0 = (kt - b * tiles_h) * THK;
+                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                mbar_arrive_expect_tx(full_bar + 8 * stage, L::STAGE_BYTES);
+                const uint32_t sa = base + stage * L::STAGE_BYTES;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int dh = taps == 9 ? tap_h[hh] / 3 - 1 : 0;
+                    const int dw = taps == 9 ? tap_h[hh] % 3 - 1 : 0;
+                    tma_load_4d(sa + hh * WG_BOX_BYTES, &tmap_x, full_bar + 8 * stage, ci_h[hh], dw, h0 + dh, b);
+                }
+#pragma unroll
+                for (int j = 0; j < BLOCK_N / 64; ++j)
+                    tma_load_4d(sa + L::A_BYTES + j * WG_BOX_BYTES, &tmap_dy, full_bar + 8 * stage,
+                                n_blk * BLOCK_N + j * 64, 0, h0, b);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 5) {
+        constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 1, 1);
+        int stage = 0; uint32_t phase = 0;
+        for (int kt = kt_begin; kt < kt_end; ++kt) {
+            mbar_wait(full_bar + 8 * stage, phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = base + stage * L::STAGE_BYTES;
+                // MN-major SWIZZLE_128B: LBO = distance between 64-channel boxes, SBO = 8 pixel rows
+                const uint64_t adesc = make_smem_desc(sa, WG_BOX_BYTES, 1024);
+                const uint64_t bdesc = make_smem_desc(sa + L::A_BYTES, WG_BOX_BYTES, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)      // 16 pixels = 2 swizzle atoms = 2048 B per K step
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc,
+                              (kt > kt_begin || k > 0) ? 1u : 0u);
+                umma_commit(empty_bar + 8 * stage);
+                if (kt == kt_end - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int row = warp * 32 + lane;
+        const int half = row >> 6;
+        const int tap = tap_h[half];
+        const int ci = ci_h[half] + (row & 63);
+        const bool live = half == 0 || half1_live;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, r);
+            tmem_ld_wait();
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int co = n_blk * BLOCK_N + c * 32 + j;
+                    atomicAdd(dw + ((long)co * taps + tap) * Cin + ci, __uint_as_float(r[j]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 5) tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight preparation: fp32 master [Co][T][Ci] -> bf16 flipped + transposed [Ci][T][Co] (dgrad operand)
+// ---------------------------------------------------------------------------------------------
+__global__ void weight_flip_transpose_bf16_kernel(const float* __restrict__ w, bf16* __restrict__ wt, int Co,
+                                                  int Ci, int T) {
+    const long n = (long)Co * Ci * T;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        int co = (int)(i % Co);
+        long r = i / Co;
+        int t = (int)(r % T);
+        int ci = (int)(r / T);
+        wt[i] = __float2bfloat16_rn(w[((long)co * T + (T - 1 - t)) * Ci + ci]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// NHWC bf16 activation [B,H,W,C] viewed as (C, W, H, B); box = (64, box_w, box_h, 1)
+int make_act_tmap(CUtensorMap* map, const void* ptr, int B, int H, int W, int C, int box_w, int box_h) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc == nullptr) return TAG_ERR_UNSUPPORTED;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? TAG_OK : 20000 + (int)r;
+}
+
+// weight matrix [Cout][K] bf16 viewed as (K, Cout); box = (64, block_n)
+int make_w_tmap(CUtensorMap* map, const void* ptr, int Cout, int K, int block_n) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc == nullptr) return TAG_ERR_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? TAG_OK : 20000 + (int)r;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BLOCK_N, typename TO>
+int launch_tc_fwd(const CUtensorMap& tx, const CUtensorMap& tw, void* y, const float* bias, int relu,
+                  double* stats, int B, int H, int W, int Cin, int Cout, int taps, cudaStream_t stream) {
+    constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    using L = FwdSmem<BLOCK_N, STAGES>;
+    auto kern = conv_tc_fwd_kernel<BLOCK_N, TO, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int TH = 128 / W;
+    const int total_tiles = B * ((H + TH - 1) / TH) * (Cout / BLOCK_N);
+    const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+    kern<<<grid, 192, L::TOTAL, stream>>>(tx, tw, (TO*)y, bias, relu, stats, B, H, W, Cin, Cout, taps);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+template <int BLOCK_N>
+int launch_tc_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, float* dw, int B, int H, int W, int Cin,
+                    int Cout, int taps, int splits, cudaStream_t stream) {
+    constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    using L = WgSmem<BLOCK_N, STAGES>;
+    auto kern = conv_tc_wgrad_kernel<BLOCK_N, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int THK = 64 / W > 0 ? 64 / W : 1;
+    const int k_tiles = B * ((H + THK - 1) / THK);
+    const int m_blocks = Cin >= 128 ? taps * (Cin / 128) : (taps + 1) / 2;
+    const int n_blocks = Cout / BLOCK_N;
+    if (splits > k_tiles) splits = k_tiles;
+    const int kps = (k_tiles + splits - 1) / splits;
+    splits = (k_tiles + kps - 1) / kps;
+    const long grid = (long)m_blocks * n_blocks * splits;
+    kern<<<(unsigned)grid, 192, L::TOTAL, stream>>>(tx, tdy, dw, B, H, W, Cin, Cout, taps, m_blocks, n_blocks, kps);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+bool width_ok(int W) { return W == 1 || W == 2 || W == 4 || W == 8 || W == 16 || W == 32 || W == 64; }
+
+}  // namespace
+
+// x: bf16 NHWC [B,H,W,Cin]; w: bf16 [Cout][taps*Cin]; y: NHWC [B,H,W,Cout] (bf16 or fp32)
+extern "C" int tag_conv_tc_fwd(const void* x, const void* w, void* y, int y_dtype, const float* bias, int relu,
+                               double* stats, int B, int H, int W, int Cin, int Cout, int taps,
+                               cudaStream_t stream) {
+    if ((taps != 1 && taps != 9) || Cin % 64 != 0 || Cout % 64 != 0 || !width_ok(W) || B <= 0 || H <= 0)
+        return TAG_ERR_BAD_ARG;
+    const int TH = 128 / W;
+    if (TH > 256) return TAG_ERR_BAD_ARG;
+    const int block_n = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    CUtensorMap tx, tw;
+    int rc = make_act_tmap(&tx, x, B, H, W, Cin, W, TH);
+    if (rc != TAG_OK) return rc;
+    rc = make_w_tmap(&tw, w, Cout, taps * Cin, block_n);
+    if (rc != TAG_OK) return rc;
+#define TAG_TC_FWD(BN_)                                                                                       \
+    (y_dtype == TAG_DTYPE_BF16                                                                               \
+         ? launch_tc_fwd<BN_, bf16>(tx, tw, y, bias, relu, stats, B, H, W, Cin, Cout, taps, stream)          \
+         : launch_tc_fwd<BN_, float>(tx, tw, y, bias, relu, stats, B, H, W, Cin, Cout, taps, stream))
+    if (block_n == 256) return TAG_TC_FWD(256);
+    if (block_n == 128) return TAG_TC_FWD(128);
+    return TAG_TC_FWD(64);
+#undef TAG_TC_FWD
+}
+
+// dy: bf16 NHWC [B,H,W,Cout]; x: bf16 NHWC [B,H,W,Cin]; dw: fp32 [Cout][taps][Cin], accumulated (+=)
+extern "C" int tag_conv_tc_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin,
+                                 int Cout, int taps, int splits, cudaStream_t stream) {
+    if ((taps != 1 && taps != 9) || Cin % 64 != 0 || Cout % 64 != 0 || !width_ok(W) || splits <= 0)
+        return TAG_ERR_BAD_ARG;
+    if (taps == 1 && Cin < 128) return TAG_ERR_BAD_ARG;
+    const int THK = 64 / W > 0 ? 64 / W : 1;
+    const int box_w = W < 64 ? W : 64;
+    if (W > 64) return TAG_ERR_BAD_ARG;
+    const int block_n = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    CUtensorMap tx, tdy;
+    int rc = make_act_tmap(&tx, x, B, H, W, Cin, box_w, THK);
+    if (rc != TAG_OK) return rc;
+    rc = make_act_tmap(&tdy, dy, B, H, W, Cout, box_w, THK);
+    if (rc != TAG_OK) return rc;
+    if (block_n == 256) return launch_tc_wgrad<256>(tx, tdy, dw, B, H, W, Cin, Cout, taps, splits, stream);
+    if (block_n == 128) return launch_tc_wgrad<128>(tx, tdy, dw, B, H, W, Cin, Cout, taps, splits, stream);
+    return launch_tc_wgrad<64>(tx, tdy, dw, B, H, W, Cin, Cout, taps, splits, stream);
+}
+
+extern "C" int tag_weight_flip_transpose_bf16(const float* w, void* wt, int Co, int Ci, int taps,
+                                              cudaStream_t stream) {
+    const long n = (long)Co * Ci * taps;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 4096) blocks = 4096;
+    weight_flip_transpose_bf16_kernel<<<blocks, 256, 0, stream>>>(w, (bf16*)wt, Co, Ci, taps);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}

@@ -146,7 +146,7 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
         if cin == 1:
             call("tag_conv_c1_fwd", x, Wt.conv[0], y1, ops.dt(y1), st1, B, H, W)
         else:
-            ops.conv_fwd(x, Wt.conv[2 * blk], y1, None, False, st1, B, H, W, cin, cout, 9)
+            ops.conv_fwd(x, ops.prep_weight(Wt.conv[2 * blk], dtype), y1, None, False, st1, B, H, W, cin, cout, 9)
         aux1 = bn_aux(cout)
         finalize(st1, count, cout, 1 + 2 * blk, aux1)
         a1 = torch.empty(B, H, W, cout, **act)
@@ -154,7 +154,7 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
         # conv2
         y2 = torch.empty(B, H, W, cout, **act)
         st2 = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if bn_training else None
-        ops.conv_fwd(a1, Wt.conv[2 * blk + 1], y2, None, False, st2, B, H, W, cout, cout, 9)
+        ops.conv_fwd(a1, ops.prep_weight(Wt.conv[2 * blk + 1], dtype), y2, None, False, st2, B, H, W, cout, cout, 9)
         aux2 = bn_aux(cout)
         finalize(st2, count, cout, 2 + 2 * blk, aux2)
         # bn2 + relu + pool + dropout
@@ -180,9 +180,9 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
     call("tag_freq_mean_fwd", x, m, ops.dt(m), rows, Wf, C, P_FC if use_dropout else 0.0,
          _seed_for(seed, 4), seed_dev)
     f = torch.empty(rows, 512, **act)
-    ops.conv_fwd(m, Wt.fc_w, f, Wt.fc_b, True, None, 1, rows, 1, C, 512, 1)
+    ops.conv_fwd(m, ops.prep_weight(Wt.fc_w, dtype), f, Wt.fc_b, True, None, 1, rows, 1, C, 512, 1)
     gi = torch.empty(rows, 1536, **f32)
-    ops.conv_fwd(f, Wt.w_ih, gi, Wt.b_ih, False, None, 1, rows, 1, 512, 1536, 1)
+    ops.conv_fwd(f, ops.prep_weight(Wt.w_ih, dtype), gi, Wt.b_ih, False, None, 1, rows, 1, 512, 1536, 1)
     out = torch.empty(B, Tp, 512, **f32)
     gates = torch.empty(B, Tp, 2, 4, 256, **f32) if save else None
     call("tag_gru_fwd", gi, Wt.w_hh, Wt.b_hh, out, gates, B, Tp)
@@ -216,19 +216,19 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         call("tag_colsum", dgh[d], ops.F32, rows, 768, G.b_hh[d * 768:(d + 1) * 768])
         ops.conv_wgrad(dgh[d], hprev[d], G.w_hh[d], 1, rows, 1, 256, 768, 1,
                        ops.wgrad_splits(rows, 256, 768, 1))
-    ops.conv_wgrad(dgi, ctx.f, G.w_ih, 1, rows, 1, 512, 1536, 1, ops.wgrad_splits(rows, 512, 1536, 1))
-    w_ih_t = torch.empty(512, 1536, **f32)
-    call("tag_weight_flip_transpose", Wt.w_ih, w_ih_t, 1536, 512, 1)
+    tc = dtype == torch.bfloat16 and ops.USE_TC
+    dgi_op = ops.to_bf16(dgi) if tc else dgi
+    ops.conv_wgrad(dgi_op, ctx.f, G.w_ih, 1, rows, 1, 512, 1536, 1, ops.wgrad_splits(rows, 512, 1536, 1))
+    w_ih_t = ops.prep_weight_t(Wt.w_ih, 1536, 512, 1, dtype)
     df = torch.empty(rows, 512, **f32)
-    ops.conv_fwd(dgi, w_ih_t, df, None, False, None, 1, rows, 1, 1536, 512, 1)
+    ops.conv_fwd(dgi_op, w_ih_t, df, None, False, None, 1, rows, 1, 1536, 512, 1)
 
     # ---- fc1
     dpre = torch.empty(rows, 512, **act)
     call("tag_relu_bwd", df, ops.F32, ctx.f, ops.dt(ctx.f), dpre, ops.dt(dpre), df.numel())
     call("tag_colsum", dpre, ops.dt(dpre), rows, 512, G.fc_b)
     ops.conv_wgrad(dpre, ctx.m, G.fc_w, 1, rows, 1, 512, 512, 1, ops.wgrad_splits(rows, 512, 512, 1))
-    fc_t = torch.empty(512, 512, **f32)
-    call("tag_weight_flip_transpose", Wt.fc_w, fc_t, 512, 512, 1)
+    fc_t = ops.prep_weight_t(Wt.fc_w, 512, 512, 1, dtype)
     dm = torch.empty(rows, 512, **act)
     ops.conv_fwd(dpre, fc_t, dm, None, False, None, 1, rows, 1, 512, 512, 1)
 
@@ -261,8 +261,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         # conv2
         ops.conv_wgrad(dy2, a1, G.conv[2 * blk + 1], B, H, W, cout, cout, 9,
                        ops.wgrad_splits(P, cout, cout, 9))
-        w2t = torch.empty(cout * 9 * cout, **f32)
-        call("tag_weight_flip_transpose", Wt.conv[2 * blk + 1], w2t, cout, cout, 9)
+        w2t = ops.prep_weight_t(Wt.conv[2 * blk + 1], cout, cout, 9, dtype)
         da1 = torch.empty_like(a1)
         ops.conv_fwd(dy2, w2t, da1, None, False, None, B, H, W, cout, cout, 9)
         del dy2
@@ -289,8 +288,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
             x_in = ctx.p[blk - 1]
             ops.conv_wgrad(dy1, x_in, G.conv[2 * blk], B, H, W, cin, cout, 9,
                            ops.wgrad_splits(P, cin, cout, 9))
-            w1t = torch.empty(cin * 9 * cout, **f32)
-            call("tag_weight_flip_transpose", Wt.conv[2 * blk], w1t, cout, cin, 9)
+            w1t = ops.prep_weight_t(Wt.conv[2 * blk], cout, cin, 9, dtype)
             dp = torch.empty_like(x_in)
             ops.conv_fwd(dy1, w1t, dp, None, False, None, B, H, W, cout, cin, 9)
         del dy1

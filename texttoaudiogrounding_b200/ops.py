@@ -6,6 +6,8 @@ through this module (bench.py reports it as ``gpu_launches``).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -42,14 +44,69 @@ def call(name: str, *args) -> None:
     LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
 
 
+USE_TC = os.environ.get("TAG_B200_NO_TC", "0") != "1"
+
+
+def tc_eligible(W: int, Cin: int, Cout: int) -> bool:
+    return USE_TC and Cin % 64 == 0 and Cout % 64 == 0 and W in (1, 2, 4, 8, 16, 32, 64)
+
+
 def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps):
+    """Dispatch on the weight dtype: bf16 weights -> tcgen05 kernel, fp32 weights -> SIMT kernel."""
     annotate(f"fwd M={B * H * W} N={Cout} K={taps * Cin}", 2.0 * B * H * W * Cout * taps * Cin)
-    call("tag_conv_fwd", x, dt(x), w, y, dt(y), bias, int(relu), stats, B, H, W, Cin, Cout, taps)
+    if w.dtype == torch.bfloat16:
+        if x.dtype != torch.bfloat16 or not tc_eligible(W, Cin, Cout):
+            raise _lib.TagError("tag_conv_tc_fwd: needs bf16 activations and Cin, Cout multiples of 64")
+        call("tag_conv_tc_fwd", x, w, y, dt(y), bias, int(relu), stats, B, H, W, Cin, Cout, taps)
+    else:
+        call("tag_conv_fwd", x, dt(x), w, y, dt(y), bias, int(relu), stats, B, H, W, Cin, Cout, taps)
 
 
-def conv_wgrad(dy, x, dw, B, H, W, Cin, Cout, taps, splits):
+def conv_wgrad(dy, x, dw, B, H, W, Cin, Cout, taps, splits, tc=None):
     annotate(f"wgrad P={B * H * W} Cout={Cout} K={taps * Cin}", 2.0 * B * H * W * Cout * taps * Cin)
-    call("tag_conv_wgrad", dy, dt(dy), x, dt(x), dw, B, H, W, Cin, Cout, taps, splits)
+    if tc is None:
+        tc = (dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and tc_eligible(W, Cin, Cout)
+              and (taps == 9 or Cin >= 128))
+    if tc:
+        call("tag_conv_tc_wgrad", dy, x, dw, B, H, W, Cin, Cout, taps, tc_wgrad_splits(B, H, W, Cin, Cout, taps))
+    else:
+        call("tag_conv_wgrad", dy, dt(dy), x, dt(x), dw, B, H, W, Cin, Cout, taps, splits)
+
+
+def tc_wgrad_splits(B, H, W, Cin, Cout, taps) -> int:
+    thk = max(1, 64 // W)
+    k_tiles = B * ((H + thk - 1) // thk)
+    bn = 256 if Cout % 256 == 0 else (128 if Cout % 128 == 0 else 64)
+    m_blocks = taps * (Cin // 128) if Cin >= 128 else (taps + 1) // 2
+    base = m_blocks * (Cout // bn)
+    s = max(1, (148 * 2 + base - 1) // base)
+    return max(1, min(s, k_tiles // 8 if k_tiles >= 8 else 1))
+
+
+def prep_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """fp32 master weight -> GEMM operand of the compute dtype ([Cout][taps*Cin], same layout)."""
+    if dtype != torch.bfloat16 or not USE_TC:
+        return w
+    wb = torch.empty(w.shape, device=w.device, dtype=torch.bfloat16)
+    call("tag_cast_f32_to_bf16", w, wb, w.numel())
+    return wb
+
+
+def prep_weight_t(w: torch.Tensor, Co: int, Ci: int, taps: int, dtype: torch.dtype) -> torch.Tensor:
+    """fp32 master [Co][taps][Ci] -> flipped + transposed [Ci][taps][Co] dgrad operand."""
+    if dtype == torch.bfloat16 and USE_TC:
+        wt = torch.empty(Ci * taps * Co, device=w.device, dtype=torch.bfloat16)
+        call("tag_weight_flip_transpose_bf16", w, wt, Co, Ci, taps)
+    else:
+        wt = torch.empty(Ci * taps * Co, device=w.device, dtype=torch.float32)
+        call("tag_weight_flip_transpose", w, wt, Co, Ci, taps)
+    return wt
+
+
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    call("tag_cast_f32_to_bf16", x, y, x.numel())
+    return y
 
 
 def wgrad_splits(P: int, Cin: int, Cout: int, taps: int) -> int:
