@@ -119,3 +119,41 @@ def test_tc_matches_simt_on_model_shapes_end_to_end():
     a, b = res[True][2], res[False][2]
     cos = float((a * b).sum() / (a.norm() * b.norm()))
     assert cos > 0.98, cos
+
+
+@pytest.mark.parametrize("B,T", [(3, 7), (8, 25), (11, 50)])
+def test_bigru_bf16_tensor_core_variant_close_to_oracle(B, T):
+    """mma.sync GRU (bf16 W_hh / exchanged state, fp32 cell) vs the fp32 oracle recurrence."""
+    from oracle import tag_oracle as O
+    from texttoaudiogrounding_b200 import ops
+    sd = O.synth_state_dict(seed=5)
+    pre = "audio_encoder.rnn."
+    names = ["weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0",
+             "weight_ih_l0_reverse", "weight_hh_l0_reverse", "bias_ih_l0_reverse", "bias_hh_l0_reverse"]
+    ws = {k: sd[pre + k].clone().requires_grad_(True) for k in names}
+    x = (torch.randn(B, T, 512, generator=g(18)) * 0.5).requires_grad_(True)
+    ref = O.bigru(x, {pre + k: v for k, v in ws.items()}, pre)
+    d_out = torch.randn(ref.shape, generator=g(19))
+    ref.backward(d_out)
+    w_ih = torch.cat([ws["weight_ih_l0"], ws["weight_ih_l0_reverse"]]).detach().cuda()
+    b_ih = torch.cat([ws["bias_ih_l0"], ws["bias_ih_l0_reverse"]]).detach().cuda()
+    w_hh = torch.stack([ws["weight_hh_l0"], ws["weight_hh_l0_reverse"]]).detach().cuda().contiguous()
+    b_hh = torch.cat([ws["bias_hh_l0"], ws["bias_hh_l0_reverse"]]).detach().cuda()
+    rows = B * T
+    gi = torch.nn.functional.linear(x.detach().cuda().reshape(rows, 512), w_ih, b_ih).contiguous()
+    out = torch.empty(B, T, 512, device="cuda")
+    gates = torch.empty(B, T, 2, 4, 256, device="cuda")
+    ops.call("tag_gru_fwd_bf16", gi, w_hh, b_hh, out, gates, B, T)
+    torch.cuda.synchronize()
+    assert (out.cpu() - ref.detach()).abs().max().item() < 1e-2
+    dgi = torch.empty(rows, 1536, device="cuda")
+    dgh = torch.empty(2, rows, 768, device="cuda")
+    hprev = torch.empty(2, rows, 256, device="cuda")
+    ops.call("tag_gru_bwd_bf16", d_out.cuda(), out, gates, w_hh, dgi, dgh, hprev, B, T)
+    dx = (dgi @ w_ih).cpu().reshape(B, T, 512)
+    assert rel_err(dx, x.grad) < 3e-2, rel_err(dx, x.grad)
+    dw = dgh[0].t() @ hprev[0]
+    assert rel_err(dw.cpu(), ws["weight_hh_l0"].grad) < 3e-2
+    # hprev is the state each step consumed: forward direction = out shifted by one step
+    hp = hprev[0].reshape(B, T, 256)
+    assert torch.equal(hp[:, 1:], out[:, :-1, :256]) and float(hp[:, 0].abs().max()) == 0.0

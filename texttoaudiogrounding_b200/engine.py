@@ -185,7 +185,8 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
     ops.conv_fwd(f, ops.prep_weight(Wt.w_ih, dtype), gi, Wt.b_ih, False, None, 1, rows, 1, 512, 1536, 1)
     out = torch.empty(B, Tp, 512, **f32)
     gates = torch.empty(B, Tp, 2, 4, 256, **f32) if save else None
-    call("tag_gru_fwd", gi, Wt.w_hh, Wt.b_hh, out, gates, B, Tp)
+    gru_fwd = "tag_gru_fwd_bf16" if (dtype == torch.bfloat16 and ops.USE_TC) else "tag_gru_fwd"
+    call(gru_fwd, gi, Wt.w_hh, Wt.b_hh, out, gates, B, Tp)
     if stages is not None:
         stages["fc1"] = f.view(B, Tp, 512)
         stages["rnn"] = out
@@ -210,7 +211,8 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
     dgi = torch.empty(rows, 1536, **f32)
     dgh = torch.empty(2, rows, 768, **f32)
     hprev = torch.empty(2, rows, 256, **f32)
-    call("tag_gru_bwd", d_emb, ctx.out, ctx.gates, Wt.w_hh, dgi, dgh, hprev, B, Tp)
+    gru_bwd = "tag_gru_bwd_bf16" if (dtype == torch.bfloat16 and ops.USE_TC) else "tag_gru_bwd"
+    call(gru_bwd, d_emb, ctx.out, ctx.gates, Wt.w_hh, dgi, dgh, hprev, B, Tp)
     call("tag_colsum", dgi, ops.F32, rows, 1536, G.b_ih)
     for d in range(2):
         call("tag_colsum", dgh[d], ops.F32, rows, 768, G.b_hh[d * 768:(d + 1) * 768])
