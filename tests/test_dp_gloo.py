@@ -1,0 +1,67 @@
+"""World-size-2 `gloo` test (CPU) of the data-parallel host logic of FusedTrainStep: the flat
+parameter / gradient bucket layout, parameter views aliasing the bucket, and the single all-reduce
+per step.  (The kernels themselves need a GPU; the NCCL path runs under `bench.py --gpus N`.)"""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from helpers import build_model
+        from texttoaudiogrounding_b200.train import FusedTrainStep
+        torch.manual_seed(1)
+        model = build_model(None, "fp32", device="cpu", vocab=300)
+        ts = FusedTrainStep(model, use_graph=False)
+        assert ts.world == world
+        n = ts.n_params
+        assert n == sum(p.numel() for p in model.parameters())
+        # parameters and .grad are views of the flat buffers, in the fixed order
+        off = 0
+        for p in model.audio_encoder._param_list() + [model.text_encoder.embedding.core.weight]:
+            assert p.data_ptr() == ts.flat_p.data_ptr() + 4 * off
+            assert p.grad.data_ptr() == ts.flat_g.data_ptr() + 4 * off
+            off += p.numel()
+        assert off == n
+        # GRU operands exist without copies
+        assert ts.Wt.w_ih.shape == (1536, 512) and ts.Wt.w_hh.shape == (2, 768, 256)
+        assert ts.Wt.w_ih.data_ptr() == model.audio_encoder.rnn.weight_ih_l0.data_ptr()
+        # conv weights keep the reference's shape while their memory is [Cout][kh][kw][Cin]
+        w = model.audio_encoder.conv_block3.conv2.weight
+        assert tuple(w.shape) == (256, 256, 3, 3) and w.permute(0, 2, 3, 1).is_contiguous()
+        # identical replicas on every rank
+        chk = ts.flat_p.double().sum().reshape(1)
+        gathered = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(gathered, chk)
+        assert all(torch.equal(gathered[0], g) for g in gathered)
+        # one all-reduce(sum) over the whole bucket; the mean's 1/world is applied by the Adam kernel
+        ts.flat_g.copy_(torch.arange(n, dtype=torch.float32) % 7 + rank)
+        ts._allreduce()
+        expect = (torch.arange(n, dtype=torch.float32) % 7) * world + sum(range(world))
+        assert torch.equal(ts.flat_g, expect)
+        assert torch.equal(model.audio_encoder.fc1.bias.grad, expect[ts._views[27][0]:ts._views[27][0] + 512])
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_world2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
