@@ -231,6 +231,13 @@ def main():
                        "share": round(v["ms"] / total_ms, 4),
                        **({"tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)} if v["flops"] else {})}
                    for k, v in top[:8]}
+        layers = {}
+        for name, tag, flops, nbytes, s, e in recs:
+            if flops > 0:
+                a = layers.setdefault(f"{name.replace('tag_conv_', '')} {tag}", [0.0, 0.0])
+                a[0] += flops; a[1] += s.elapsed_time(e)
+        kernels["_dense_layers_tflops"] = {k: [round(v[0] / (v[1] * 1e-3) / 1e12, 1), round(v[1], 3)]
+                                           for k, v in layers.items()}
         dom_name, dom = top[0]
         if dom["flops"] > 0:
             peak = peaks.get("bf16_tflops_sustained", 1400.0)

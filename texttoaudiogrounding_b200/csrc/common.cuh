@@ -63,9 +63,24 @@ template <typename T> __device__ __forceinline__ void load8(const T* p, float* o
     Vec4<T>::load(p, o);
     Vec4<T>::load(p + 4, o + 4);
 }
+template <> __device__ __forceinline__ void load8<bf16>(const bf16* p, float* o) {   // one LDG.128
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    o[0] = __uint_as_float(r.x << 16); o[1] = __uint_as_float(r.x & 0xFFFF0000u);
+    o[2] = __uint_as_float(r.y << 16); o[3] = __uint_as_float(r.y & 0xFFFF0000u);
+    o[4] = __uint_as_float(r.z << 16); o[5] = __uint_as_float(r.z & 0xFFFF0000u);
+    o[6] = __uint_as_float(r.w << 16); o[7] = __uint_as_float(r.w & 0xFFFF0000u);
+}
 template <typename T> __device__ __forceinline__ void store8(T* p, const float* o) {
     Vec4<T>::store(p, o);
     Vec4<T>::store(p + 4, o + 4);
+}
+template <> __device__ __forceinline__ void store8<bf16>(bf16* p, const float* o) {  // one STG.128
+    __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b = __floats2bfloat162_rn(o[2], o[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(o[4], o[5]), d = __floats2bfloat162_rn(o[6], o[7]);
+    uint4 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+    r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(p) = r;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -83,6 +98,41 @@ __device__ __forceinline__ uint32_t tag_hash32(uint64_t seed, uint64_t idx) {
     z = z ^ (z >> 31);
     return (uint32_t)(z >> 32);
 }
+// 16-byte raw vector access: 8 bf16 or 4 fp32 channels per load
+template <typename T> struct Raw16 { static constexpr int VEC = 16 / (int)sizeof(T); static constexpr int NSUB = VEC / 4; };
+// unpack 4 consecutive channels (sub-chunk `sub`) of a raw 16-byte vector
+template <typename T> __device__ __forceinline__ void unpack4(const uint4& raw, int sub, float* o);
+template <> __device__ __forceinline__ void unpack4<float>(const uint4& raw, int, float* o) {
+    o[0] = __uint_as_float(raw.x); o[1] = __uint_as_float(raw.y);
+    o[2] = __uint_as_float(raw.z); o[3] = __uint_as_float(raw.w);
+}
+template <> __device__ __forceinline__ void unpack4<bf16>(const uint4& raw, int sub, float* o) {
+    const uint32_t lo = sub == 0 ? raw.x : raw.z, hi = sub == 0 ? raw.y : raw.w;
+    o[0] = __uint_as_float(lo << 16); o[1] = __uint_as_float(lo & 0xFFFF0000u);
+    o[2] = __uint_as_float(hi << 16); o[3] = __uint_as_float(hi & 0xFFFF0000u);
+}
+template <typename T> __device__ __forceinline__ void pack4(uint4& raw, int sub, const float* o);
+template <> __device__ __forceinline__ void pack4<float>(uint4& raw, int, const float* o) {
+    raw.x = __float_as_uint(o[0]); raw.y = __float_as_uint(o[1]);
+    raw.z = __float_as_uint(o[2]); raw.w = __float_as_uint(o[3]);
+}
+template <> __device__ __forceinline__ void pack4<bf16>(uint4& raw, int sub, const float* o) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(o[2], o[3]);
+    const uint32_t lo = *reinterpret_cast<uint32_t*>(&a), hi = *reinterpret_cast<uint32_t*>(&b);
+    if (sub == 0) { raw.x = lo; raw.y = hi; } else { raw.z = lo; raw.w = hi; }
+}
+__device__ __forceinline__ uint4 ld16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void st16(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+inline void tag_dropout_params(float p, uint32_t* thresh, float* keep_scale) {
+    if (p <= 0.f) { *thresh = 0u; *keep_scale = 1.f; return; }
+    double t = (double)p * 4294967296.0;
+    if (t > 4294967295.0) t = 4294967295.0;
+    *thresh = (uint32_t)t;
+    *keep_scale = 1.0f / (1.0f - p);
+}
+
 // keep-scale: 0 when dropped, 1/(1-p) when kept.  thresh = p * 2^32.
 __device__ __forceinline__ float tag_dropout_scale(uint64_t seed, uint64_t idx, uint32_t thresh,
                                                    float keep_scale) {

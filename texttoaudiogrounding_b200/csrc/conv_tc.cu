@@ -281,7 +281,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 }
                 if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) Vec4<TO>::store(yrow + c * 32 + j, &v[j]);
+                    for (int j = 0; j < 32; j += 8) store8<TO>(yrow + c * 32 + j, &v[j]);
                 }
                 if (stats != nullptr) {
 #pragma unroll

@@ -73,146 +73,39 @@ template <typename TI, typename TO>
 __global__ void scale_shift_act_kernel(const TI* __restrict__ x, TO* __restrict__ y,
                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                        long n_vec, int C, int relu) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n_vec; i += (long)gridDim.x * blockDim.x) {
-        const long e = i * 4;
-        const int c = (int)(e % C);
-        float v[4], sc[4], sh[4];
-        Vec4<TI>::load(x + e, v);
-        Vec4<float>::load(scale + c, sc);
-        Vec4<float>::load(shift + c, sh);
+    // n_vec counts 8-element vectors; two independent vectors per thread per iteration
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n_vec; i += 2 * stride) {
+        const long i2 = i + stride;
+        const bool has2 = i2 < n_vec;
+        float v[8], u[8];
+        load8<TI>(x + i * 8, v);
+        if (has2) load8<TI>(x + i2 * 8, u);
+        {
+            const int c = (int)((i * 8) % C);
+            float sc[8], sh[8];
+            load8<float>(scale + c, sc);
+            load8<float>(shift + c, sh);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            v[k] = fmaf(v[k], sc[k], sh[k]);
-            if (relu) v[k] = fmaxf(v[k], 0.f);
-        }
-        Vec4<TO>::store(y + e, v);
-    }
-}
-
-// ------------------------------------------------------------------ first conv (Cin = 1)
-// y[b,h,w,co] = sum_tap x[b,h+dh,w+dw] * w[co][tap]; 64 output channels; W == 64.
-template <typename T>
-__global__ void __launch_bounds__(256)
-conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
-                   double* __restrict__ stats, int B, int H, int W) {
-    constexpr int CO = 64;
-    __shared__ float ws[CO * 9];
-    __shared__ float s_sum[CO], s_sq[CO];
-    for (int i = threadIdx.x; i < CO * 9; i += blockDim.x) ws[i] = w[i];
-    if (threadIdx.x < CO) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-    __syncthreads();
-    // thread -> (pixel, group of 4 channels); 16 channel groups per pixel, 16 pixels per pass
-    const int cg = threadIdx.x & 15;
-    const int pl = threadIdx.x >> 4;
-    const long P = (long)B * H * W;
-    float cs[4] = {0, 0, 0, 0}, cq[4] = {0, 0, 0, 0};
-    constexpr int PIX_PER_BLOCK = 256;
-    const long p_base = (long)blockIdx.x * PIX_PER_BLOCK;
-    for (int it = 0; it < PIX_PER_BLOCK / 16; ++it) {
-        const long p = p_base + it * 16 + pl;
-        if (p >= P) break;
-        const int pw = (int)(p % W);
-        const long t = p / W;
-        const int ph = (int)(t % H);
-        float xin[9];
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int hh = ph + tap / 3 - 1, ww = pw + tap % 3 - 1;
-            xin[tap] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                           ? to_f<T>(x[p + (long)(tap / 3 - 1) * W + (tap % 3 - 1)]) : 0.f;
-        }
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float* wr = ws + (cg * 4 + e) * 9;
-            float a = 0.f;
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) a = fmaf(xin[tap], wr[tap], a);
-            a = round_to<T>(a);
-            o[e] = a;
-            cs[e] += a;
-            cq[e] += a * a;
-        }
-        Vec4<T>::store(y + p * CO + cg * 4, o);
-    }
-    if (stats != nullptr) {
-        // lanes l and l+16 share the channel group
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float sv = cs[e] + __shfl_xor_sync(0xffffffffu, cs[e], 16);
-            float qv = cq[e] + __shfl_xor_sync(0xffffffffu, cq[e], 16);
-            if ((threadIdx.x & 31) < 16) {
-                atomicAdd(&s_sum[cg * 4 + e], sv);
-                atomicAdd(&s_sq[cg * 4 + e], qv);
+            for (int k = 0; k < 8; ++k) {
+                v[k] = fmaf(v[k], sc[k], sh[k]);
+                if (relu) v[k] = fmaxf(v[k], 0.f);
             }
+            store8<TO>(y + i * 8, v);
         }
-        __syncthreads();
-        if (threadIdx.x < CO) {
-            atomicAdd(stats + threadIdx.x, (double)s_sum[threadIdx.x]);
-            atomicAdd(stats + CO + threadIdx.x, (double)s_sq[threadIdx.x]);
+        if (has2) {
+            const int c = (int)((i2 * 8) % C);
+            float sc[8], sh[8];
+            load8<float>(scale + c, sc);
+            load8<float>(shift + c, sh);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                u[k] = fmaf(u[k], sc[k], sh[k]);
+                if (relu) u[k] = fmaxf(u[k], 0.f);
+            }
+            store8<TO>(y + i2 * 8, u);
         }
     }
-}
-
-// backward of the Cin = 1 conv: dw[co][tap] = sum_p dy[p,co] x[p+d(tap)];
-// dx[p] = sum_{tap,co} dy[p - d(tap), co] w[co][tap]
-template <typename T>
-__global__ void __launch_bounds__(256)
-conv_c1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ w,
-                   float* __restrict__ dw, float* __restrict__ dx, int B, int H, int W) {
-    constexpr int CO = 64;
-    __shared__ float ws[CO * 9];
-    __shared__ float s_dw[CO * 9];
-    for (int i = threadIdx.x; i < CO * 9; i += blockDim.x) { ws[i] = w[i]; s_dw[i] = 0.f; }
-    __syncthreads();
-    const long P = (long)B * H * W;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int PIX_PER_BLOCK = 256;
-    const long p_base = (long)blockIdx.x * PIX_PER_BLOCK;
-    // a warp handles one pixel at a time; lane handles channels {lane, lane + 32}
-    float acc_dw[2][9];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) acc_dw[j][tap] = 0.f;
-    for (int it = 0; it < PIX_PER_BLOCK / 8; ++it) {
-        const long p = p_base + it * 8 + warp;
-        if (p >= P) break;
-        const int pw = (int)(p % W);
-        const long t = p / W;
-        const int ph = (int)(t % H);
-        // wgrad part
-        const float g0 = to_f<T>(dy[p * CO + lane]);
-        const float g1 = to_f<T>(dy[p * CO + 32 + lane]);
-        float dxv = 0.f;
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int dh = tap / 3 - 1, dwv = tap % 3 - 1;
-            const int hh = ph + dh, ww = pw + dwv;
-            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-                const float xv = to_f<T>(x[p + (long)dh * W + dwv]);
-                acc_dw[0][tap] = fmaf(g0, xv, acc_dw[0][tap]);
-                acc_dw[1][tap] = fmaf(g1, xv, acc_dw[1][tap]);
-            }
-            // dgrad part: dx[p] += dy[p - d(tap), co] * w[co][tap]
-            const int h2 = ph - dh, w2 = pw - dwv;
-            if (dx != nullptr && h2 >= 0 && h2 < H && w2 >= 0 && w2 < W) {
-                const long q = p - (long)dh * W - dwv;
-                dxv = fmaf(to_f<T>(dy[q * CO + lane]), ws[lane * 9 + tap], dxv);
-                dxv = fmaf(to_f<T>(dy[q * CO + 32 + lane]), ws[(lane + 32) * 9 + tap], dxv);
-            }
-        }
-        if (dx != nullptr) {
-            dxv = warp_sum(dxv);
-            if (lane == 0) dx[p] = dxv;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) atomicAdd(&s_dw[(lane + 32 * j) * 9 + tap], acc_dw[j][tap]);
-    __syncthreads();
-    for (int i = threadIdx.x; i < CO * 9; i += blockDim.x) atomicAdd(dw + i, s_dw[i]);
 }
 
 // ------------------------------------------------------------------ BN + ReLU + avg+max pool + dropout
@@ -261,135 +154,6 @@ __global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ y, T* __restrict__
     }
 }
 
-// Backward through dropout -> avg+max pool -> ReLU -> BN(train).  MODE 0: reduce
-// (dbeta = sum g, dgamma = sum g * xhat); MODE 1: write dy = scale * (g - dbeta/N - xhat * dgamma/N).
-// POOL == false: the incoming gradient is already at conv resolution (bn1 of a block).
-template <typename T, int PH, int PW, bool POOL, int MODE>
-__global__ void __launch_bounds__(256)
-bn_relu_pool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dout, T* __restrict__ dy,
-                        const float* __restrict__ scale, const float* __restrict__ shift,
-                        const float* __restrict__ mean, const float* __restrict__ invstd,
-                        double* __restrict__ red, float inv_count, int bn_training,
-                        int B, int H, int W, int C, uint64_t seed, const uint64_t* __restrict__ seed_dev, uint32_t thresh, float keep_scale) {
-    if (seed_dev != nullptr) seed += *seed_dev;
-    const int Ho = POOL ? H / PH : H, Wo = POOL ? W / PW : W;
-    const int Hs = (H + PH - 1) / PH, Ws = (W + PW - 1) / PW;   // window slots incl. partial ones
-    const int CV = C / 8;
-    // threads of a block share cv = threadIdx.x % CV when CV divides blockDim (C <= 2048)
-    const int cv = threadIdx.x % CV;
-    const int slot_lane = threadIdx.x / CV;
-    const int slots_per_block = blockDim.x / CV;
-    const long n_slots = (long)B * Hs * Ws;
-    float sc[8], sh[8], mu[8], is[8], dbe[8], dga[8];
-    load8<float>(scale + cv * 8, sc);
-    load8<float>(shift + cv * 8, sh);
-    load8<float>(mean + cv * 8, mu);
-    load8<float>(invstd + cv * 8, is);
-    if (MODE == 1) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            dbe[k] = bn_training ? (float)red[cv * 8 + k] * inv_count : 0.f;
-            dga[k] = bn_training ? (float)red[C + cv * 8 + k] * inv_count : 0.f;
-        }
-    }
-    float rs[8], rq[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { rs[k] = 0.f; rq[k] = 0.f; }
-
-    for (long s = (long)blockIdx.x * slots_per_block + slot_lane; s < n_slots;
-         s += (long)gridDim.x * slots_per_block) {
-        const int ws_ = (int)(s % Ws);
-        long r = s / Ws;
-        const int hs = (int)(r % Hs);
-        const int b = (int)(r / Hs);
-        const bool full = POOL ? (hs < Ho && ws_ < Wo) : true;
-        float g_out[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) g_out[k] = 0.f;
-        if (full) {
-            const long oidx = ((((long)b * Ho + hs) * Wo + ws_) * CV + cv) * 8;
-            load8<T>(dout + oidx, g_out);
-            if (POOL && thresh != 0u) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    g_out[k] *= tag_dropout_scale(seed, (uint64_t)(oidx + k), thresh, keep_scale);
-            }
-        }
-        // window values
-        float v[PH * PW][8], a[PH * PW][8];
-        bool inb[PH * PW];
-#pragma unroll
-        for (int dh = 0; dh < PH; ++dh)
-#pragma unroll
-            for (int dw = 0; dw < PW; ++dw) {
-                const int h = hs * PH + dh, w = ws_ * PW + dw;
-                const int e = dh * PW + dw;
-                inb[e] = (h < H && w < W);
-                if (inb[e]) {
-                    load8<T>(y + (((long)b * H + h) * W + w) * C + cv * 8, v[e]);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) a[e][k] = fmaf(v[e][k], sc[k], sh[k]);
-                }
-            }
-#pragma unroll
-        for (int e = 0; e < PH * PW; ++e) {
-            if (!inb[e]) continue;
-            float g[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float gk = 0.f;
-                if (full && a[e][k] > 0.f) {
-                    if (POOL) {
-                        // first maximum in scan order takes the max-pool gradient (torch semantics)
-                        bool is_max = true;
-#pragma unroll
-                        for (int e2 = 0; e2 < PH * PW; ++e2) {
-                            if (e2 < e) is_max = is_max && (a[e2][k] < a[e][k]);
-                            else if (e2 > e) is_max = is_max && (a[e2][k] <= a[e][k]);
-                        }
-                        gk = g_out[k] * ((1.0f / (PH * PW)) + (is_max ? 1.f : 0.f));
-                    } else {
-                        gk = g_out[k];
-                    }
-                }
-                g[k] = gk;
-            }
-            if (MODE == 0) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    rs[k] += g[k];
-                    rq[k] += g[k] * (v[e][k] - mu[k]) * is[k];
-                }
-            } else {
-                float o[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float xhat = (v[e][k] - mu[k]) * is[k];
-                    o[k] = sc[k] * (g[k] - dbe[k] - xhat * dga[k]);
-                }
-                const int h = hs * PH + e / PW, w = ws_ * PW + e % PW;
-                store8<T>(dy + (((long)b * H + h) * W + w) * C + cv * 8, o);
-            }
-        }
-    }
-    if (MODE == 0) {
-        __shared__ float sm[2][256][9];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { sm[0][threadIdx.x][k] = rs[k]; sm[1][threadIdx.x][k] = rq[k]; }
-        __syncthreads();
-        for (int i = threadIdx.x; i < C; i += blockDim.x) {
-            if (i >= CV * 8) break;
-            const int cvi = i / 8, k = i % 8;
-            double ds = 0.0, dq = 0.0;
-            for (int l = 0; l < slots_per_block; ++l) {
-                ds += sm[0][l * CV + cvi][k];
-                dq += sm[1][l * CV + cvi][k];
-            }
-            atomicAdd(red + i, ds);
-            atomicAdd(red + C + i, dq);
-        }
-    }
-}
 
 // ------------------------------------------------------------------ mean over the frequency axis (+dropout)
 template <typename T>
@@ -548,9 +312,9 @@ extern "C" int tag_bn_finalize(const double* stats, double count, int C, const f
 
 extern "C" int tag_scale_shift_act(const void* x, int x_dtype, void* y, int y_dtype, const float* scale,
                                    const float* shift, long n, int C, int relu, cudaStream_t stream) {
-    if (n % 4 != 0 || C % 4 != 0) return TAG_ERR_BAD_ARG;
-    const long nv = n / 4;
-    const int blocks = grid_for(nv, 256);
+    if (n % 8 != 0 || C % 8 != 0) return TAG_ERR_BAD_ARG;
+    const long nv = n / 8;
+    const int blocks = grid_for((nv + 1) / 2, 256, 148 * 24);
     if (x_dtype == TAG_DTYPE_F32 && y_dtype == TAG_DTYPE_F32)
         scale_shift_act_kernel<float, float><<<blocks, 256, 0, stream>>>((const float*)x, (float*)y, scale, shift, nv, C, relu);
     else if (x_dtype == TAG_DTYPE_F32 && y_dtype == TAG_DTYPE_BF16)
@@ -561,30 +325,6 @@ extern "C" int tag_scale_shift_act(const void* x, int x_dtype, void* y, int y_dt
         scale_shift_act_kernel<bf16, float><<<blocks, 256, 0, stream>>>((const bf16*)x, (float*)y, scale, shift, nv, C, relu);
     else
         return TAG_ERR_BAD_ARG;
-    TAG_RETURN_IF_LAUNCH_FAILED();
-    return TAG_OK;
-}
-
-extern "C" int tag_conv_c1_fwd(const void* x, const float* w, void* y, int dtype, double* stats, int B,
-                               int H, int W, cudaStream_t stream) {
-    const long P = (long)B * H * W;
-    const int blocks = (int)((P + 255) / 256);
-    if (dtype == TAG_DTYPE_F32)
-        conv_c1_fwd_kernel<float><<<blocks, 256, 0, stream>>>((const float*)x, w, (float*)y, stats, B, H, W);
-    else
-        conv_c1_fwd_kernel<bf16><<<blocks, 256, 0, stream>>>((const bf16*)x, w, (bf16*)y, stats, B, H, W);
-    TAG_RETURN_IF_LAUNCH_FAILED();
-    return TAG_OK;
-}
-
-extern "C" int tag_conv_c1_bwd(const void* dy, const void* x, const float* w, int dtype, float* dw,
-                               float* dx, int B, int H, int W, cudaStream_t stream) {
-    const long P = (long)B * H * W;
-    const int blocks = (int)((P + 255) / 256);
-    if (dtype == TAG_DTYPE_F32)
-        conv_c1_bwd_kernel<float><<<blocks, 256, 0, stream>>>((const float*)dy, (const float*)x, w, dw, dx, B, H, W);
-    else
-        conv_c1_bwd_kernel<bf16><<<blocks, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, w, dw, dx, B, H, W);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }
@@ -615,48 +355,6 @@ extern "C" int tag_bn_relu_pool_fwd(const void* y, void* out, int dtype, const f
     return pool_fwd_dispatch<bf16>(y, out, scale, shift, B, H, W, C, ph, pw, seed, seed_dev, thresh, ks, stream);
 }
 
-template <typename T, int MODE>
-static int pool_bwd_dispatch(const void* y, const void* dout, void* dy, const float* scale,
-                             const float* shift, const float* mean, const float* invstd, double* red,
-                             float inv_count, int bn_training, int B, int H, int W, int C, int ph, int pw,
-                             uint64_t seed, const uint64_t* __restrict__ seed_dev, uint32_t thresh, float ks, cudaStream_t stream) {
-    const int CV = C / 8;
-    if (CV > 256 || 256 % CV != 0) return TAG_ERR_BAD_ARG;
-    const int spb = 256 / CV;
-    const int ph_e = ph > 0 ? ph : 1, pw_e = pw > 0 ? pw : 1;
-    const long n_slots = (long)B * ((H + ph_e - 1) / ph_e) * ((W + pw_e - 1) / pw_e);
-    const int blocks = grid_for((n_slots + spb - 1) / spb, 1, 148 * 8);
-#define TAG_LAUNCH_POOL_BWD(PH_, PW_, POOL_)                                                          \
-    bn_relu_pool_bwd_kernel<T, PH_, PW_, POOL_, MODE><<<blocks, 256, 0, stream>>>(                     \
-        (const T*)y, (const T*)dout, (T*)dy, scale, shift, mean, invstd, red, inv_count, bn_training, \
-        B, H, W, C, seed, seed_dev, thresh, ks)
-    if (ph == 2 && pw == 2) TAG_LAUNCH_POOL_BWD(2, 2, true);
-    else if (ph == 1 && pw == 2) TAG_LAUNCH_POOL_BWD(1, 2, true);
-    else if (ph == 0 && pw == 0) TAG_LAUNCH_POOL_BWD(1, 1, false);
-    else return TAG_ERR_UNSUPPORTED;
-#undef TAG_LAUNCH_POOL_BWD
-    TAG_RETURN_IF_LAUNCH_FAILED();
-    return TAG_OK;
-}
-
-// mode 0: accumulate red[0:C] += sum g, red[C:2C] += sum g*xhat.  mode 1: write dy.
-// ph = pw = 0 selects the "no pooling" variant (dout has the conv resolution).
-extern "C" int tag_bn_relu_pool_bwd(int mode, const void* y, const void* dout, void* dy, int dtype,
-                                    const float* scale, const float* shift, const float* mean,
-                                    const float* invstd, double* red, int bn_training, int B, int H,
-                                    int W, int C, int ph, int pw, float dropout_p, uint64_t seed,
-                                    const uint64_t* seed_dev, cudaStream_t stream) {
-    if (C % 8 != 0) return TAG_ERR_BAD_ARG;
-    uint32_t thresh; float ks;
-    dropout_params(dropout_p, &thresh, &ks);
-    const float inv_count = 1.0f / (float)((double)B * H * W);
-    if (dtype == TAG_DTYPE_F32) {
-        if (mode == 0) return pool_bwd_dispatch<float, 0>(y, dout, dy, scale, shift, mean, invstd, red, inv_count, bn_training, B, H, W, C, ph, pw, seed, seed_dev, thresh, ks, stream);
-        return pool_bwd_dispatch<float, 1>(y, dout, dy, scale, shift, mean, invstd, red, inv_count, bn_training, B, H, W, C, ph, pw, seed, seed_dev, thresh, ks, stream);
-    }
-    if (mode == 0) return pool_bwd_dispatch<bf16, 0>(y, dout, dy, scale, shift, mean, invstd, red, inv_count, bn_training, B, H, W, C, ph, pw, seed, seed_dev, thresh, ks, stream);
-    return pool_bwd_dispatch<bf16, 1>(y, dout, dy, scale, shift, mean, invstd, red, inv_count, bn_training, B, H, W, C, ph, pw, seed, seed_dev, thresh, ks, stream);
-}
 
 extern "C" int tag_freq_mean_fwd(const void* x, void* out, int dtype, long rows, int Wf, int C,
                                  float dropout_p, uint64_t seed, const uint64_t* seed_dev, cudaStream_t stream) {
