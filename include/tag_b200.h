@@ -77,6 +77,10 @@ int tag_conv_tc_fwd(const void* x, const void* w, void* y, int y_dtype, const fl
                     double* stats, int B, int H, int W, int Cin, int Cout, int taps, cudaStream_t stream);
 int tag_conv_tc_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout,
                       int taps, int splits, cudaStream_t stream);
+/* 3x3 only: same result as tag_conv_tc_fwd(taps=9, no bias/relu) with the input halo tile re-used
+ * across the three vertical taps (16x8-pixel output tiles; W must be a multiple of 8). */
+int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, double* stats, int B, int H,
+                         int W, int Cin, int Cout, cudaStream_t stream);
 int tag_weight_flip_transpose_bf16(const float* w, void* wt, int Co, int Ci, int taps, cudaStream_t stream);
 
 /* ---- BN + ReLU + avg+max pool + dropout — models/panns.py:50-58, audio_encoder.py:202-211 */

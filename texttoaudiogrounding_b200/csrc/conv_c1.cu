@@ -90,7 +90,10 @@ conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __re
     }
 }
 
-template <typename T>
+// WGRAD / DGRAD select the half of the backward this instantiation computes: the two halves run
+// as two launches so that neither needs more than 128 registers (72 wgrad accumulators vs the
+// projection state); dy is then read twice from HBM (2 x 8.2 MB per clip), still far from the bound.
+template <typename T, bool WGRAD, bool DGRAD>
 __global__ void __launch_bounds__(256, 2)
 conv_c1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ w,
                    float* __restrict__ dw, float* __restrict__ dx, int B, int H, int W) {
@@ -130,6 +133,7 @@ conv_c1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const floa
 #pragma unroll
             for (int c = 0; c < 8; ++c) g[c] = 0.f;
         }
+        if (DGRAD) {
         float s[9];
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
@@ -149,8 +153,9 @@ conv_c1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const floa
 #pragma unroll
             for (int t = 0; t < 9; ++t) S[r][c0][t] = s[t];
         }
+        }
         // wgrad for interior pixels
-        if (r >= 1 && r <= TH && row_ok) {
+        if (WGRAD && r >= 1 && r <= TH && row_ok) {
             float xn[9];
 #pragma unroll
             for (int t = 0; t < 9; ++t) xn[t] = xs[r - 1 + t / 3][c0 + t % 3];
@@ -161,6 +166,7 @@ conv_c1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const floa
         }
     }
     // ---- wgrad: reduce the per-thread accumulators (lanes with equal cg, then across warps)
+    if (WGRAD) {
 #pragma unroll
     for (int c = 0; c < 8; ++c)
 #pragma unroll
@@ -170,10 +176,12 @@ conv_c1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const floa
             v += __shfl_xor_sync(0xffffffffu, v, 16);
             if (lane < 8) atomicAdd(&s_dw[(cg * 8 + c) * 9 + t], v);
         }
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < CO * 9; i += blockDim.x) atomicAdd(dw + i, s_dw[i]);
+    if (WGRAD)
+        for (int i = threadIdx.x; i < CO * 9; i += blockDim.x) atomicAdd(dw + i, s_dw[i]);
     // ---- phase B: dx[p] = sum_tap S[p - d(tap)][tap]
-    if (dx != nullptr) {
+    if (DGRAD && dx != nullptr) {
         for (int pix = threadIdx.x; pix < TH * TW; pix += blockDim.x) {
             const int r = pix / TW, c0 = pix - r * TW;
             const int h = h0 + r;
@@ -208,10 +216,15 @@ extern "C" int tag_conv_c1_bwd(const void* dy, const void* x, const float* w, in
                                float* dx, int B, int H, int W, cudaStream_t stream) {
     if (W != TW || B <= 0 || H <= 0) return TAG_ERR_BAD_ARG;
     const int blocks = B * ((H + TH - 1) / TH);
-    if (dtype == TAG_DTYPE_F32)
-        conv_c1_bwd_kernel<float><<<blocks, 256, 0, stream>>>((const float*)dy, (const float*)x, w, dw, dx, B, H, W);
-    else
-        conv_c1_bwd_kernel<bf16><<<blocks, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, w, dw, dx, B, H, W);
+    if (dtype == TAG_DTYPE_F32) {
+        conv_c1_bwd_kernel<float, true, false><<<blocks, 256, 0, stream>>>((const float*)dy, (const float*)x, w, dw, dx, B, H, W);
+        if (dx != nullptr)
+            conv_c1_bwd_kernel<float, false, true><<<blocks, 256, 0, stream>>>((const float*)dy, (const float*)x, w, dw, dx, B, H, W);
+    } else {
+        conv_c1_bwd_kernel<bf16, true, false><<<blocks, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, w, dw, dx, B, H, W);
+        if (dx != nullptr)
+            conv_c1_bwd_kernel<bf16, false, true><<<blocks, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, w, dw, dx, B, H, W);
+    }
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }

@@ -1,0 +1,249 @@
+// 3x3 convolution forward / dgrad on tcgen05 with the input halo RE-USED across taps.
+//
+// conv_tc.cu loads one shifted 128-pixel box per (tap, 64-channel slab): every input element goes
+// through the L2 -> SM path nine times.  Here an output tile is 16 time rows x 8 frequency bins; for
+// each horizontal shift dw in {-1,0,+1} ONE box of (16+2) rows x 8 columns x 64 channels lands in
+// shared memory (18 KB, rows = pixels, 128 B each, SWIZZLE_128B) and serves the three vertical taps:
+// the tap (dh, dw) A operand is the same buffer with its start address advanced by (dh+1) * 8 rows
+// = 1024 B — exactly one swizzle atom, so the descriptor stays canonical (SBO = 1024 B: 8-pixel groups
+// = consecutive image rows).  A traffic drops from 144 KB to 54 KB per tile and slab; the weight
+// tiles stream through their own ring.  Same warp roles / TMEM double buffering / epilogue as
+// conv_tc_fwd_kernel.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TILE_H = 16, TILE_W = 8;
+constexpr int A_SUB_BYTES = (TILE_H + 2) * TILE_W * 128;      // 18432
+constexpr int A_STAGES = 4;
+
+template <int BLOCK_N, int B_STAGES>
+struct HaloSmem {
+    static constexpr int B_TILE_BYTES = BLOCK_N * 128;
+    static constexpr int A_OFFSET = 0;
+    static constexpr int B_OFFSET = A_STAGES * A_SUB_BYTES;
+    static constexpr int BAR_OFFSET = B_OFFSET + B_STAGES * B_TILE_BYTES;
+    static constexpr int STATS_OFFSET = BAR_OFFSET + 512;
+    static constexpr int TOTAL = STATS_OFFSET + 2 * BLOCK_N * 4 + 1024;
+};
+
+template <int BLOCK_N, typename TO, int B_STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                        TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W, int Cin, int Cout) {
+    using L = HaloSmem<BLOCK_N, B_STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - raw);
+    const uint32_t a_full = base + L::BAR_OFFSET;
+    const uint32_t a_empty = a_full + 8 * A_STAGES;
+    const uint32_t b_full = a_empty + 8 * A_STAGES;
+    const uint32_t b_empty = b_full + 8 * B_STAGES;
+    const uint32_t tmem_full = b_empty + 8 * B_STAGES;
+    const uint32_t tmem_empty = tmem_full + 16;
+    const uint32_t tmem_slot = tmem_empty + 16;
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(base_ptr + L::BAR_OFFSET + 16 * A_STAGES + 16 * B_STAGES + 32);
+    float* s_stats = reinterpret_cast<float*>(base_ptr + L::STATS_OFFSET);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_w = W / TILE_W;
+    const int tiles_h = (H + TILE_H - 1) / TILE_H;
+    const int tiles_img = tiles_w * tiles_h;
+    const int m_tiles = B * tiles_img;
+    const int n_tiles = Cout / BLOCK_N;
+    const int total_tiles = m_tiles * n_tiles;
+    const int KC = Cin / 64;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < A_STAGES; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
+        for (int s = 0; s < B_STAGES; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + 8 * a, 1); mbar_init(tmem_empty + 8 * a, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
+    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x < 128)
+        for (int i = threadIdx.x; i < 2 * BLOCK_N; i += 128) s_stats[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    auto decode = [&](int tile, int& n_tile, int& b, int& h0, int& w0) {
+        n_tile = tile / m_tiles;
+        int m_tile = tile - n_tile * m_tiles;
+        b = m_tile / tiles_img;
+        m_tile -= b * tiles_img;
+        const int th = m_tile / tiles_w;
+        h0 = th * TILE_H;
+        w0 = (m_tile - th * tiles_w) * TILE_W;
+    };
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int n_tile, b, h0, w0;
+                decode(tile, n_tile, b, h0, w0);
+                for (int kc = 0; kc < KC; ++kc) {
+                    for (int dwi = 0; dwi < 3; ++dwi) {
+                        mbar_wait(a_empty + 8 * as, aph ^ 1);
+                        mbar_arrive_expect_tx(a_full + 8 * as, A_SUB_BYTES);
+                        tma_load_4d(base + L::A_OFFSET + as * A_SUB_BYTES, &tmap_x, a_full + 8 * as, kc * 64,
+                                    w0 + dwi - 1, h0 - 1, b);
+                        if (++as == A_STAGES) { as = 0; aph ^= 1; }
+                        for (int dhi = 0; dhi < 3; ++dhi) {
+                            const int tap = dhi * 3 + dwi;
+                            mbar_wait(b_empty + 8 * bs, bph ^ 1);
+                            mbar_arrive_expect_tx(b_full + 8 * bs, L::B_TILE_BYTES);
+                            tma_load_2d(base + L::B_OFFSET + bs * L::B_TILE_BYTES, &tmap_w, b_full + 8 * bs,
+                                        tap * Cin + kc * 64, n_tile * BLOCK_N);
+                            if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 0, 0);
+        int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(tmem_empty + 8 * acc, acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            uint32_t first = 1;
+            for (int kc = 0; kc < KC; ++kc) {
+                for (int dwi = 0; dwi < 3; ++dwi) {
+                    mbar_wait(a_full + 8 * as, aph);
+                    const uint32_t sa = base + L::A_OFFSET + as * A_SUB_BYTES;
+                    for (int dhi = 0; dhi < 3; ++dhi) {
+                        mbar_wait(b_full + 8 * bs, bph);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint64_t adesc = make_smem_desc(sa + dhi * (TILE_W * 128), 16, 1024);
+                            const uint64_t bdesc = make_smem_desc(base + L::B_OFFSET + bs * L::B_TILE_BYTES, 16, 1024);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
+                            umma_commit(b_empty + 8 * bs);
+                            if (dhi == 2) umma_commit(a_empty + 8 * as);
+                            if (kc == KC - 1 && dwi == 2 && dhi == 2) umma_commit(tmem_full + 8 * acc);
+                        }
+                        __syncwarp();
+                        if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
+                    }
+                    if (++as == A_STAGES) { as = 0; aph ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        int it = 0;
+        int cur_n_tile = -1;
+        auto flush_stats = [&](int n_tile) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = threadIdx.x; i < BLOCK_N; i += 128) {
+                atomicAdd(stats + n_tile * BLOCK_N + i, (double)s_stats[i]);
+                atomicAdd(stats + Cout + n_tile * BLOCK_N + i, (double)s_stats[BLOCK_N + i]);
+                s_stats[i] = 0.f;
+                s_stats[BLOCK_N + i] = 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            int n_tile, b, h0, w0;
+            decode(tile, n_tile, b, h0, w0);
+            if (stats != nullptr && cur_n_tile >= 0 && n_tile != cur_n_tile) flush_stats(cur_n_tile);
+            cur_n_tile = n_tile;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(tmem_full + 8 * acc, acc_phase);
+            tc_fence_after();
+            const int row = warp * 32 + lane;
+            const int h = h0 + (row >> 3), w = w0 + (row & 7);
+            const bool valid = h < H;
+            TO* yrow = y + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BLOCK_N + c * 32, r);
+                tmem_ld_wait();
+                float v[32], q[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float f = round_to<TO>(__uint_as_float(r[j]));
+                    v[j] = valid ? f : 0.f;
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) store8<TO>(yrow + c * 32 + j, &v[j]);
+                }
+                if (stats != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) q[j] = v[j] * v[j];
+                    const float cs = warp_transpose_sum(v, lane);
+                    const float cq = warp_transpose_sum(q, lane);
+                    atomicAdd(&s_stats[c * 32 + lane], cs);
+                    atomicAdd(&s_stats[BLOCK_N + c * 32 + lane], cq);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
+        }
+        if (stats != nullptr && cur_n_tile >= 0) flush_stats(cur_n_tile);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+template <int BLOCK_N, typename TO>
+int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* stats, int B, int H, int W,
+                int Cin, int Cout, cudaStream_t stream) {
+    constexpr int B_STAGES = BLOCK_N == 256 ? 4 : 8;
+    using L = HaloSmem<BLOCK_N, B_STAGES>;
+    auto kern = conv_tc_fwd_halo_kernel<BLOCK_N, TO, B_STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int total_tiles = B * ((H + TILE_H - 1) / TILE_H) * (W / TILE_W) * (Cout / BLOCK_N);
+    const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+    kern<<<grid, 192, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+}  // namespace
+
+// 3x3 only, no bias / ReLU.  x: bf16 NHWC, W a multiple of 8; w: bf16 [Cout][9*Cin]; y bf16 or fp32.
+extern "C" int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, double* stats, int B,
+                                    int H, int W, int Cin, int Cout, cudaStream_t stream) {
+    if (Cin % 64 != 0 || Cout % 64 != 0 || W % TILE_W != 0 || B <= 0 || H <= 0) return TAG_ERR_BAD_ARG;
+    const int block_n = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    CUtensorMap tx, tw;
+    int rc = make_act_tmap(&tx, x, B, H, W, Cin, TILE_W, TILE_H + 2);
+    if (rc != TAG_OK) return rc;
+    rc = make_w_tmap(&tw, w, Cout, 9 * Cin, block_n);
+    if (rc != TAG_OK) return rc;
+#define TAG_HALO(BN_)                                                                              \
+    (y_dtype == TAG_DTYPE_BF16 ? launch_halo<BN_, bf16>(tx, tw, y, stats, B, H, W, Cin, Cout, stream)  \
+                               : launch_halo<BN_, float>(tx, tw, y, stats, B, H, W, Cin, Cout, stream))
+    if (block_n == 256) return TAG_HALO(256);
+    if (block_n == 128) return TAG_HALO(128);
+    return TAG_HALO(64);
+#undef TAG_HALO
+}

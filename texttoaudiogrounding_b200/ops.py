@@ -15,7 +15,7 @@ from . import _lib
 F32, BF16 = 0, 1
 LAUNCHES = 0
 # kernels per C-ABI call (default 1)
-_KERNELS_PER_CALL = {"tag_clip_adam": 2, "tag_dot_sigmoid_bwd": 2}
+_KERNELS_PER_CALL = {"tag_clip_adam": 2, "tag_dot_sigmoid_bwd": 2, "tag_conv_c1_bwd": 2}
 
 
 def dt(t: torch.Tensor) -> int:
@@ -45,6 +45,7 @@ def call(name: str, *args) -> None:
 
 
 USE_TC = os.environ.get("TAG_B200_NO_TC", "0") != "1"
+USE_HALO = os.environ.get("TAG_B200_NO_HALO", "0") != "1"
 
 
 def tc_eligible(W: int, Cin: int, Cout: int) -> bool:
@@ -57,7 +58,10 @@ def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps):
     if w.dtype == torch.bfloat16:
         if x.dtype != torch.bfloat16 or not tc_eligible(W, Cin, Cout):
             raise _lib.TagError("tag_conv_tc_fwd: needs bf16 activations and Cin, Cout multiples of 64")
-        call("tag_conv_tc_fwd", x, w, y, dt(y), bias, int(relu), stats, B, H, W, Cin, Cout, taps)
+        if USE_HALO and taps == 9 and bias is None and not relu and W % 8 == 0:
+            call("tag_conv_tc_fwd_halo", x, w, y, dt(y), stats, B, H, W, Cin, Cout)
+        else:
+            call("tag_conv_tc_fwd", x, w, y, dt(y), bias, int(relu), stats, B, H, W, Cin, Cout, taps)
     else:
         call("tag_conv_fwd", x, dt(x), w, y, dt(y), bias, int(relu), stats, B, H, W, Cin, Cout, taps)
 
