@@ -81,6 +81,10 @@ int tag_conv_tc_wgrad(const void* dy, const void* x, float* dw, int B, int H, in
  * across the three vertical taps (16x8-pixel output tiles; W must be a multiple of 8). */
 int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, double* stats, int B, int H,
                          int W, int Cin, int Cout, cudaStream_t stream);
+/* its weight operand: bf16 tap-major [9][Cout][Cin] (flip_transpose=0) or, for dgrad,
+ * [9][Cin][Cout] of the 180-degree rotated kernel (flip_transpose=1), from the fp32 master. */
+int tag_weight_prep_tapmajor_bf16(const float* w, void* out, int Co, int Ci, int flip_transpose,
+                                  cudaStream_t stream);
 int tag_weight_flip_transpose_bf16(const float* w, void* wt, int Co, int Ci, int taps, cudaStream_t stream);
 
 /* ---- BN + ReLU + avg+max pool + dropout — models/panns.py:50-58, audio_encoder.py:202-211 */

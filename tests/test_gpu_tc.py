@@ -32,14 +32,16 @@ SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("halo", [True, False])
 @pytest.mark.parametrize("B,H,W,Cin,Cout", SHAPES)
-def test_tc_conv3x3_fwd(B, H, W, Cin, Cout):
+def test_tc_conv3x3_fwd(B, H, W, Cin, Cout, halo):
     from texttoaudiogrounding_b200 import ops
     x = _bf(torch.randn(B, Cin, H, W, generator=g(1)))
     w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g(2)) * (1.0 / (3 * Cin ** 0.5)))
     ref = F.conv2d(x.cuda(), w.cuda(), padding=1).permute(0, 2, 3, 1).contiguous()   # fp32 NHWC
     xn = x.permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
-    wp = w.permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
+    wp = w.permute(0, 2, 3, 1).contiguous().cuda()
+    wp = ops.prep_weight(wp, torch.bfloat16, W) if halo else wp.bfloat16()
     # fp32 output + statistics
     y32 = torch.empty(B, H, W, Cout, device="cuda")
     stats = torch.zeros(2 * Cout, device="cuda", dtype=torch.float64)
@@ -56,8 +58,9 @@ def test_tc_conv3x3_fwd(B, H, W, Cin, Cout):
     assert rel_err(yb.float(), ref) < 6e-3
 
 
+@pytest.mark.parametrize("halo", [True, False])
 @pytest.mark.parametrize("B,H,W,Cin,Cout", SHAPES[:7])
-def test_tc_conv3x3_dgrad_and_wgrad(B, H, W, Cin, Cout):
+def test_tc_conv3x3_dgrad_and_wgrad(B, H, W, Cin, Cout, halo):
     from texttoaudiogrounding_b200 import ops
     x = _bf(torch.randn(B, Cin, H, W, generator=g(3))).cuda().requires_grad_(True)
     w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g(4)) * (1.0 / (3 * Cin ** 0.5))).cuda().requires_grad_(True)
@@ -66,7 +69,7 @@ def test_tc_conv3x3_dgrad_and_wgrad(B, H, W, Cin, Cout):
     xn = x.detach().permute(0, 2, 3, 1).contiguous().bfloat16()
     dyn = dy.permute(0, 2, 3, 1).contiguous().bfloat16()
     wp32 = w.detach().permute(0, 2, 3, 1).contiguous()
-    wt = ops.prep_weight_t(wp32, Cout, Cin, 9, torch.bfloat16)
+    wt = ops.prep_weight_t(wp32, Cout, Cin, 9, torch.bfloat16, W if halo else None)
     dx = torch.empty(B, H, W, Cin, device="cuda")
     ops.conv_fwd(dyn, wt, dx, None, False, None, B, H, W, Cout, Cin, 9)
     assert rel_err(dx.permute(0, 3, 1, 2), x.grad) < 2e-3, rel_err(dx.permute(0, 3, 1, 2), x.grad)

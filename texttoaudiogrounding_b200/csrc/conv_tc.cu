@@ -194,23 +194,25 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 // ---------------------------------------------------------------------------------------------
 // wgrad: D[(tap,ci) 128, co BLOCK_N] = sum over 64-pixel K tiles; both operands MN-major.
 // ---------------------------------------------------------------------------------------------
-constexpr int WG_BOX_BYTES = 64 * 128;           // 64 pixels x 64 bf16 channels
-
-template <int BLOCK_N, int STAGES>
+// PIX = pixels (K extent) per pipeline stage: narrow N tiles get more pixels per stage so that every
+// barrier round trip of the single MMA-issuing thread covers ~512 cycles of tensor work.
+template <int BLOCK_N, int STAGES, int PIX>
 struct WgSmem {
-    static constexpr int A_BYTES = 2 * WG_BOX_BYTES;
-    static constexpr int B_BYTES = (BLOCK_N / 64) * WG_BOX_BYTES;
+    static constexpr int BOX_BYTES = PIX * 128;      // PIX pixels x 64 bf16 channels
+    static constexpr int A_BYTES = 2 * BOX_BYTES;
+    static constexpr int B_BYTES = (BLOCK_N / 64) * BOX_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int PIX>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                      float* __restrict__ dw, int B, int H, int W, int Cin, int Cout, int taps,
                      int m_blocks, int n_blocks, int k_tiles_per_split) {
-    using L = WgSmem<BLOCK_N, STAGES>;
+    using L = WgSmem<BLOCK_N, STAGES, PIX>;
+    constexpr int WG_BOX_BYTES = L::BOX_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -222,7 +224,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L::BAR_OFFSET + 16 * STAGES + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int THK = 64 / W > 0 ? 64 / W : 1;        // rows of one clip per 64-pixel K tile
+    const int THK = PIX / W > 0 ? PIX / W : 1;      // rows of one clip per PIX-pixel K tile
     const int tiles_h = (H + THK - 1) / THK;
     const int k_tiles = B * tiles_h;
 
@@ -293,7 +295,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 const uint64_t adesc = make_smem_desc(sa, WG_BOX_BYTES, 1024);
                 const uint64_t bdesc = make_smem_desc(sa + L::A_BYTES, WG_BOX_BYTES, 1024);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)      // 16 pixels = 2 swizzle atoms = 2048 B per K step
+                for (int k = 0; k < PIX / 16; ++k)   // 16 pixels = 2 swizzle atoms = 2048 B per K step
                     umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc,
                               (kt > kt_begin || k > 0) ? 1u : 0u);
                 umma_commit(empty_bar + 8 * stage);
@@ -367,19 +369,20 @@ int launch_tc_fwd(const CUtensorMap& tx, const CUtensorMap& tw, void* y, const f
     return TAG_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int PIX>
 int launch_tc_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, float* dw, int B, int H, int W, int Cin,
                     int Cout, int taps, int splits, cudaStream_t stream) {
-    constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
-    using L = WgSmem<BLOCK_N, STAGES>;
-    auto kern = conv_tc_wgrad_kernel<BLOCK_N, STAGES>;
+    constexpr int STAGE_BYTES = (2 + BLOCK_N / 64) * PIX * 128;
+    constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    using L = WgSmem<BLOCK_N, STAGES, PIX>;
+    auto kern = conv_tc_wgrad_kernel<BLOCK_N, STAGES, PIX>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    const int THK = 64 / W > 0 ? 64 / W : 1;
+    const int THK = PIX / W > 0 ? PIX / W : 1;
     const int k_tiles = B * ((H + THK - 1) / THK);
     const int m_blocks = Cin >= 128 ? taps * (Cin / 128) : (taps + 1) / 2;
     const int n_blocks = Cout / BLOCK_N;
@@ -426,18 +429,24 @@ extern "C" int tag_conv_tc_wgrad(const void* dy, const void* x, float* dw, int B
     if ((taps != 1 && taps != 9) || Cin % 64 != 0 || Cout % 64 != 0 || !width_ok(W) || splits <= 0)
         return TAG_ERR_BAD_ARG;
     if (taps == 1 && Cin < 128) return TAG_ERR_BAD_ARG;
-    const int THK = 64 / W > 0 ? 64 / W : 1;
-    const int box_w = W < 64 ? W : 64;
     if (W > 64) return TAG_ERR_BAD_ARG;
     const int block_n = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    // pixels per stage: 64 / 128 / 256 for N = 256 / 128 / 64 (3x3 convs; the GEMM form keeps 64)
+    int pix = block_n == 256 ? 64 : (block_n == 128 ? 128 : 256);
+    if (taps == 1 || W * 256 < pix) pix = 64;
+    const int box_w = W < pix ? W : pix;
+    const int THK = pix / box_w;
+    if (THK > 256) return TAG_ERR_BAD_ARG;
     CUtensorMap tx, tdy;
     int rc = make_act_tmap(&tx, x, B, H, W, Cin, box_w, THK);
     if (rc != TAG_OK) return rc;
     rc = make_act_tmap(&tdy, dy, B, H, W, Cout, box_w, THK);
     if (rc != TAG_OK) return rc;
-    if (block_n == 256) return launch_tc_wgrad<256>(tx, tdy, dw, B, H, W, Cin, Cout, taps, splits, stream);
-    if (block_n == 128) return launch_tc_wgrad<128>(tx, tdy, dw, B, H, W, Cin, Cout, taps, splits, stream);
-    return launch_tc_wgrad<64>(tx, tdy, dw, B, H, W, Cin, Cout, taps, splits, stream);
+#define TAG_WG(BN_, PIX_) launch_tc_wgrad<BN_, PIX_>(tx, tdy, dw, B, H, W, Cin, Cout, taps, splits, stream)
+    if (block_n == 256) return TAG_WG(256, 64);
+    if (block_n == 128) return pix == 128 ? TAG_WG(128, 128) : TAG_WG(128, 64);
+    return pix == 256 ? TAG_WG(64, 256) : TAG_WG(64, 64);
+#undef TAG_WG
 }
 
 extern "C" int tag_weight_flip_transpose_bf16(const float* w, void* wt, int Co, int Ci, int taps,

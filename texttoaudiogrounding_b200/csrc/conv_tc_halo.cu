@@ -17,9 +17,12 @@ constexpr int TILE_H = 16, TILE_W = 8;
 constexpr int A_SUB_BYTES = (TILE_H + 2) * TILE_W * 128;      // 18432
 constexpr int A_STAGES = 4;
 
-template <int BLOCK_N, int B_STAGES>
+// TPS = taps per weight stage: for narrow tiles (BLOCK_N <= 128) the three vertical taps of one
+// horizontal shift travel as ONE 3-D TMA box of the tap-major weight tensor [tap'][Cout][Cin]
+// (tap' = dwi*3 + dhi), so the single MMA-issuing thread gets 12 MMAs per barrier round trip.
+template <int BLOCK_N, int B_STAGES, int TPS>
 struct HaloSmem {
-    static constexpr int B_TILE_BYTES = BLOCK_N * 128;
+    static constexpr int B_TILE_BYTES = TPS * BLOCK_N * 128;
     static constexpr int A_OFFSET = 0;
     static constexpr int B_OFFSET = A_STAGES * A_SUB_BYTES;
     static constexpr int BAR_OFFSET = B_OFFSET + B_STAGES * B_TILE_BYTES;
@@ -27,11 +30,11 @@ struct HaloSmem {
     static constexpr int TOTAL = STATS_OFFSET + 2 * BLOCK_N * 4 + 1024;
 };
 
-template <int BLOCK_N, typename TO, int B_STAGES>
+template <int BLOCK_N, typename TO, int B_STAGES, int TPS>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W, int Cin, int Cout) {
-    using L = HaloSmem<BLOCK_N, B_STAGES>;
+    using L = HaloSmem<BLOCK_N, B_STAGES, TPS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -95,12 +98,11 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                         tma_load_4d(base + L::A_OFFSET + as * A_SUB_BYTES, &tmap_x, a_full + 8 * as, kc * 64,
                                     w0 + dwi - 1, h0 - 1, b);
                         if (++as == A_STAGES) { as = 0; aph ^= 1; }
-                        for (int dhi = 0; dhi < 3; ++dhi) {
-                            const int tap = dhi * 3 + dwi;
+                        for (int dhi = 0; dhi < 3; dhi += TPS) {
                             mbar_wait(b_empty + 8 * bs, bph ^ 1);
                             mbar_arrive_expect_tx(b_full + 8 * bs, L::B_TILE_BYTES);
-                            tma_load_2d(base + L::B_OFFSET + bs * L::B_TILE_BYTES, &tmap_w, b_full + 8 * bs,
-                                        tap * Cin + kc * 64, n_tile * BLOCK_N);
+                            tma_load_3d(base + L::B_OFFSET + bs * L::B_TILE_BYTES, &tmap_w, b_full + 8 * bs,
+                                        kc * 64, n_tile * BLOCK_N, dwi * 3 + dhi);
                             if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
                         }
                     }
@@ -123,20 +125,24 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                 for (int dwi = 0; dwi < 3; ++dwi) {
                     mbar_wait(a_full + 8 * as, aph);
                     const uint32_t sa = base + L::A_OFFSET + as * A_SUB_BYTES;
-                    for (int dhi = 0; dhi < 3; ++dhi) {
+                    for (int dhi = 0; dhi < 3; dhi += TPS) {
                         mbar_wait(b_full + 8 * bs, bph);
                         tc_fence_after();
                         if (lane == 0) {
-                            const uint64_t adesc = make_smem_desc(sa + dhi * (TILE_W * 128), 16, 1024);
-                            const uint64_t bdesc = make_smem_desc(base + L::B_OFFSET + bs * L::B_TILE_BYTES, 16, 1024);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
-                                first = 0;
+                            for (int tt = 0; tt < TPS; ++tt) {
+                                const uint64_t adesc = make_smem_desc(sa + (dhi + tt) * (TILE_W * 128), 16, 1024);
+                                const uint64_t bdesc = make_smem_desc(
+                                    base + L::B_OFFSET + bs * L::B_TILE_BYTES + tt * (BLOCK_N * 128), 16, 1024);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
+                                    first = 0;
+                                }
                             }
                             umma_commit(b_empty + 8 * bs);
-                            if (dhi == 2) umma_commit(a_empty + 8 * as);
-                            if (kc == KC - 1 && dwi == 2 && dhi == 2) umma_commit(tmem_full + 8 * acc);
+                            if (dhi + TPS >= 3) umma_commit(a_empty + 8 * as);
+                            if (kc == KC - 1 && dwi == 2 && dhi + TPS >= 3) umma_commit(tmem_full + 8 * acc);
                         }
                         __syncwarp();
                         if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
@@ -211,9 +217,10 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 template <int BLOCK_N, typename TO>
 int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* stats, int B, int H, int W,
                 int Cin, int Cout, cudaStream_t stream) {
-    constexpr int B_STAGES = BLOCK_N == 256 ? 4 : 8;
-    using L = HaloSmem<BLOCK_N, B_STAGES>;
-    auto kern = conv_tc_fwd_halo_kernel<BLOCK_N, TO, B_STAGES>;
+    constexpr int TPS = BLOCK_N == 256 ? 1 : 3;
+    constexpr int B_STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 3 : 5);
+    using L = HaloSmem<BLOCK_N, B_STAGES, TPS>;
+    auto kern = conv_tc_fwd_halo_kernel<BLOCK_N, TO, B_STAGES, TPS>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
@@ -229,7 +236,56 @@ int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* s
 
 }  // namespace
 
-// 3x3 only, no bias / ReLU.  x: bf16 NHWC, W a multiple of 8; w: bf16 [Cout][9*Cin]; y bf16 or fp32.
+namespace {
+
+// fp32 master [Co][tap][Ci] -> bf16 tap-major operand of the halo kernel, tap' = dwi*3 + dhi:
+//   flip_transpose = 0 (forward): out[tap'][co][ci] = w[co][dhi*3+dwi][ci]
+//   flip_transpose = 1 (dgrad)  : out[tap'][ci][co] = w[co][8 - (dhi*3+dwi)][ci]
+__global__ void weight_prep_tapmajor_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Ci,
+                                            int flip_transpose) {
+    const long n = (long)Co * Ci * 9;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int rows = flip_transpose ? Ci : Co, cols = flip_transpose ? Co : Ci;
+        const int c = (int)(i % cols);
+        const long r = i / cols;
+        const int row = (int)(r % rows);
+        const int tp = (int)(r / rows);
+        const int tap = (tp % 3) * 3 + tp / 3;
+        float v;
+        if (flip_transpose) v = w[((long)c * 9 + (8 - tap)) * Ci + row];      // row = ci, c = co
+        else v = w[((long)row * 9 + tap) * Ci + c];                           // row = co, c = ci
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// weights [9][Cout][Cin] bf16 viewed as (Cin, Cout, 9); box = (64, block_n, tps)
+int make_w3_tmap(CUtensorMap* map, const void* ptr, int Cout, int Cin, int block_n, int tps) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc == nullptr) return TAG_ERR_UNSUPPORTED;
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)block_n, (cuuint32_t)tps};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? TAG_OK : 20000 + (int)r;
+}
+
+}  // namespace
+
+extern "C" int tag_weight_prep_tapmajor_bf16(const float* w, void* out, int Co, int Ci, int flip_transpose,
+                                             cudaStream_t stream) {
+    const long n = (long)Co * Ci * 9;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 4096) blocks = 4096;
+    weight_prep_tapmajor_kernel<<<blocks, 256, 0, stream>>>(w, (bf16*)out, Co, Ci, flip_transpose);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+// 3x3 only, no bias / ReLU.  x: bf16 NHWC, W a multiple of 8; w: bf16 TAP-MAJOR [9][Cout][Cin]
+// (tag_weight_prep_tapmajor_bf16); y bf16 or fp32.
 extern "C" int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, double* stats, int B,
                                     int H, int W, int Cin, int Cout, cudaStream_t stream) {
     if (Cin % 64 != 0 || Cout % 64 != 0 || W % TILE_W != 0 || B <= 0 || H <= 0) return TAG_ERR_BAD_ARG;
@@ -237,7 +293,7 @@ extern "C" int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y
     CUtensorMap tx, tw;
     int rc = make_act_tmap(&tx, x, B, H, W, Cin, TILE_W, TILE_H + 2);
     if (rc != TAG_OK) return rc;
-    rc = make_w_tmap(&tw, w, Cout, 9 * Cin, block_n);
+    rc = make_w3_tmap(&tw, w, Cout, Cin, block_n, block_n == 256 ? 1 : 3);
     if (rc != TAG_OK) return rc;
 #define TAG_HALO(BN_)                                                                              \
     (y_dtype == TAG_DTYPE_BF16 ? launch_halo<BN_, bf16>(tx, tw, y, stats, B, H, W, Cin, Cout, stream)  \

@@ -146,7 +146,7 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
         if cin == 1:
             call("tag_conv_c1_fwd", x, Wt.conv[0], y1, ops.dt(y1), st1, B, H, W)
         else:
-            ops.conv_fwd(x, ops.prep_weight(Wt.conv[2 * blk], dtype), y1, None, False, st1, B, H, W, cin, cout, 9)
+            ops.conv_fwd(x, ops.prep_weight(Wt.conv[2 * blk], dtype, W), y1, None, False, st1, B, H, W, cin, cout, 9)
         aux1 = bn_aux(cout)
         finalize(st1, count, cout, 1 + 2 * blk, aux1)
         a1 = torch.empty(B, H, W, cout, **act)
@@ -154,7 +154,7 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
         # conv2
         y2 = torch.empty(B, H, W, cout, **act)
         st2 = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if bn_training else None
-        ops.conv_fwd(a1, ops.prep_weight(Wt.conv[2 * blk + 1], dtype), y2, None, False, st2, B, H, W, cout, cout, 9)
+        ops.conv_fwd(a1, ops.prep_weight(Wt.conv[2 * blk + 1], dtype, W), y2, None, False, st2, B, H, W, cout, cout, 9)
         aux2 = bn_aux(cout)
         finalize(st2, count, cout, 2 + 2 * blk, aux2)
         # bn2 + relu + pool + dropout
@@ -263,7 +263,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         # conv2
         ops.conv_wgrad(dy2, a1, G.conv[2 * blk + 1], B, H, W, cout, cout, 9,
                        ops.wgrad_splits(P, cout, cout, 9))
-        w2t = ops.prep_weight_t(Wt.conv[2 * blk + 1], cout, cout, 9, dtype)
+        w2t = ops.prep_weight_t(Wt.conv[2 * blk + 1], cout, cout, 9, dtype, W)
         da1 = torch.empty_like(a1)
         ops.conv_fwd(dy2, w2t, da1, None, False, None, B, H, W, cout, cout, 9)
         del dy2
@@ -290,7 +290,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
             x_in = ctx.p[blk - 1]
             ops.conv_wgrad(dy1, x_in, G.conv[2 * blk], B, H, W, cin, cout, 9,
                            ops.wgrad_splits(P, cin, cout, 9))
-            w1t = ops.prep_weight_t(Wt.conv[2 * blk], cout, cin, 9, dtype)
+            w1t = ops.prep_weight_t(Wt.conv[2 * blk], cout, cin, 9, dtype, W)
             dp = torch.empty_like(x_in)
             ops.conv_fwd(dy1, w1t, dp, None, False, None, B, H, W, cout, cin, 9)
         del dy1

@@ -58,7 +58,9 @@ def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps):
     if w.dtype == torch.bfloat16:
         if x.dtype != torch.bfloat16 or not tc_eligible(W, Cin, Cout):
             raise _lib.TagError("tag_conv_tc_fwd: needs bf16 activations and Cin, Cout multiples of 64")
-        if USE_HALO and taps == 9 and bias is None and not relu and W % 8 == 0:
+        if getattr(w, "_tag_tapmajor", False):
+            if taps != 9 or bias is not None or relu or W % 8 != 0:
+                raise _lib.TagError("tap-major weights are only valid for the 3x3 halo kernel")
             call("tag_conv_tc_fwd_halo", x, w, y, dt(y), stats, B, H, W, Cin, Cout)
         else:
             call("tag_conv_tc_fwd", x, w, y, dt(y), bias, int(relu), stats, B, H, W, Cin, Cout, taps)
@@ -78,29 +80,44 @@ def conv_wgrad(dy, x, dw, B, H, W, Cin, Cout, taps, splits, tc=None):
 
 
 def tc_wgrad_splits(B, H, W, Cin, Cout, taps) -> int:
-    thk = max(1, 64 // W)
-    k_tiles = B * ((H + thk - 1) // thk)
     bn = 256 if Cout % 256 == 0 else (128 if Cout % 128 == 0 else 64)
+    pix = 64 if taps == 1 else {256: 64, 128: 128, 64: 256}[bn]
+    thk = max(1, pix // min(W, pix))
+    k_tiles = B * ((H + thk - 1) // thk)
     m_blocks = taps * (Cin // 128) if Cin >= 128 else (taps + 1) // 2
     base = m_blocks * (Cout // bn)
     s = max(1, (148 * 2 + base - 1) // base)
     return max(1, min(s, k_tiles // 8 if k_tiles >= 8 else 1))
 
 
-def prep_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """fp32 master weight -> GEMM operand of the compute dtype ([Cout][taps*Cin], same layout)."""
+def _halo_ok(halo_W) -> bool:
+    return USE_HALO and halo_W is not None and halo_W % 8 == 0
+
+
+def prep_weight(w: torch.Tensor, dtype: torch.dtype, halo_W=None) -> torch.Tensor:
+    """fp32 master weight -> GEMM operand of the compute dtype.  bf16: [Cout][taps*Cin] (same layout)
+    or, for a 3x3 conv on a feature map of width ``halo_W`` (multiple of 8), the tap-major
+    [9][Cout][Cin] operand of the halo kernel (marked with ``_tag_tapmajor``)."""
     if dtype != torch.bfloat16 or not USE_TC:
         return w
     wb = torch.empty(w.shape, device=w.device, dtype=torch.bfloat16)
-    call("tag_cast_f32_to_bf16", w, wb, w.numel())
+    if w.dim() == 4 and _halo_ok(halo_W):
+        call("tag_weight_prep_tapmajor_bf16", w, wb, w.shape[0], w.shape[3], 0)
+        wb._tag_tapmajor = True
+    else:
+        call("tag_cast_f32_to_bf16", w, wb, w.numel())
     return wb
 
 
-def prep_weight_t(w: torch.Tensor, Co: int, Ci: int, taps: int, dtype: torch.dtype) -> torch.Tensor:
+def prep_weight_t(w: torch.Tensor, Co: int, Ci: int, taps: int, dtype: torch.dtype, halo_W=None) -> torch.Tensor:
     """fp32 master [Co][taps][Ci] -> flipped + transposed [Ci][taps][Co] dgrad operand."""
     if dtype == torch.bfloat16 and USE_TC:
         wt = torch.empty(Ci * taps * Co, device=w.device, dtype=torch.bfloat16)
-        call("tag_weight_flip_transpose_bf16", w, wt, Co, Ci, taps)
+        if taps == 9 and _halo_ok(halo_W):
+            call("tag_weight_prep_tapmajor_bf16", w, wt, Co, Ci, 1)
+            wt._tag_tapmajor = True
+        else:
+            call("tag_weight_flip_transpose_bf16", w, wt, Co, Ci, taps)
     else:
         wt = torch.empty(Ci * taps * Co, device=w.device, dtype=torch.float32)
         call("tag_weight_flip_transpose", w, wt, Co, Ci, taps)
