@@ -230,13 +230,14 @@ def main():
         kernels = {k: {"ms_per_step": round(v["ms"], 3), "launches": v["launches"],
                        "share": round(v["ms"] / total_ms, 4),
                        **({"tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)} if v["flops"] else {})}
-                   for k, v in top[:8]}
+                   for k, v in top[:24]}
         layers = {}
         for name, tag, flops, nbytes, s, e in recs:
             if flops > 0:
                 a = layers.setdefault(f"{name.replace('tag_conv_', '')} {tag}", [0.0, 0.0])
                 a[0] += flops; a[1] += s.elapsed_time(e)
-        kernels["_dense_layers_tflops"] = {k: [round(v[0] / (v[1] * 1e-3) / 1e12, 1), round(v[1], 3)]
+        kernels["_sum_of_kernel_ms_eager_step"] = round(total_ms, 3)
+        kernels["_dense_layers_tflops"] ={k: [round(v[0] / (v[1] * 1e-3) / 1e12, 1), round(v[1], 3)]
                                            for k, v in layers.items()}
         dom_name, dom = top[0]
         if dom["flops"] > 0:

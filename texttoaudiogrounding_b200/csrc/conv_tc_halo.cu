@@ -31,7 +31,7 @@ struct HaloSmem {
 };
 
 template <int BLOCK_N, typename TO, int B_STAGES, int TPS>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W, int Cin, int Cout) {
     using L = HaloSmem<BLOCK_N, B_STAGES, TPS>;
@@ -62,13 +62,13 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     if (threadIdx.x == 0) {
         for (int s = 0; s < A_STAGES; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
         for (int s = 0; s < B_STAGES; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + 8 * a, 1); mbar_init(tmem_empty + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + 8 * a, 1); mbar_init(tmem_empty + 8 * a, 8); }
         fence_barrier_init();
     }
-    if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
-    if (warp == 5) tmem_alloc(tmem_slot, 512);
-    if (threadIdx.x < 128)
-        for (int i = threadIdx.x; i < 2 * BLOCK_N; i += 128) s_stats[i] = 0.f;
+    if (warp == 8 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
+    if (warp == 9) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x < 256)
+        for (int i = threadIdx.x; i < 2 * BLOCK_N; i += 256) s_stats[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -84,7 +84,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         w0 = (m_tile - th * tiles_w) * TILE_W;
     };
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
@@ -109,7 +109,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 0, 0);
         int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
@@ -152,18 +152,18 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             }
         }
     } else {
-        // ===================== epilogue =====================
+        // ===================== epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., column half w/4
         int it = 0;
         int cur_n_tile = -1;
         auto flush_stats = [&](int n_tile) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = threadIdx.x; i < BLOCK_N; i += 128) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int i = threadIdx.x; i < BLOCK_N; i += 256) {
                 atomicAdd(stats + n_tile * BLOCK_N + i, (double)s_stats[i]);
                 atomicAdd(stats + Cout + n_tile * BLOCK_N + i, (double)s_stats[BLOCK_N + i]);
                 s_stats[i] = 0.f;
                 s_stats[BLOCK_N + i] = 0.f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         };
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             int n_tile, b, h0, w0;
@@ -174,14 +174,15 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(tmem_full + 8 * acc, acc_phase);
             tc_fence_after();
-            const int row = warp * 32 + lane;
+            const int lq = warp & 3, chalf = warp >> 2;
+            const int row = lq * 32 + lane;
             const int h = h0 + (row >> 3), w = w0 + (row & 7);
             const bool valid = h < H;
             TO* yrow = y + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
+            for (int c = chalf * (BLOCK_N / 64); c < (chalf + 1) * (BLOCK_N / 64); ++c) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BLOCK_N + c * 32, r);
+                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + acc * BLOCK_N + c * 32, r);
                 tmem_ld_wait();
                 float v[32], q[32];
 #pragma unroll
@@ -211,7 +212,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 5) tmem_dealloc(tmem_base, 512);
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
 template <int BLOCK_N, typename TO>
@@ -229,7 +230,7 @@ int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* s
     }
     const int total_tiles = B * ((H + TILE_H - 1) / TILE_H) * (W / TILE_W) * (Cout / BLOCK_N);
     const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
-    kern<<<grid, 192, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout);
+    kern<<<grid, 320, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }
