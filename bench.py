@@ -212,13 +212,14 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        ts_use_graph = ts.use_graph
+        ts_use_graph, ts_world = ts.use_graph, ts.world
         ts.use_graph = False
+        ts.world = 1            # rank-0-only pass: no collective (the other ranks are not in it)
         ops.PROFILE = []
         ts.step(None)
         torch.cuda.synchronize()
         recs, ops.PROFILE = ops.PROFILE, None
-        ts.use_graph = ts_use_graph
+        ts.use_graph, ts.world = ts_use_graph, ts_world
         agg = {}
         total_ms = 0.0
         for name, tag, flops, nbytes, s, e in recs:
@@ -285,6 +286,7 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -120,19 +120,29 @@ conv_c1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const floa
         for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
 
     // ---- phase A: every halo pixel q = (h0 - 1 + r, c0): project dy[q, :] onto the 9 taps
+    // the wgrad-only instantiation skips the halo rows; loads are software-pipelined one pass ahead
+    constexpr int IT0 = DGRAD ? 0 : TW / 32;
+    constexpr int IT1 = DGRAD ? (TH + 2) * TW / 32 : (TH + 1) * TW / 32;
+    auto fetch = [&](int it, float* gg) {
+        const int pix = it * 32 + pl;
+        const int r = pix / TW, c0 = pix - r * TW;
+        const int h = h0 - 1 + r;
+        if (it < IT1 && h >= 0 && h < H) {
+            load8<T>(dy + (((long)b * H + h) * W + c0) * CO + cg * 8, gg);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) gg[c] = 0.f;
+        }
+    };
+    float g[8], gn[8];
+    fetch(IT0, g);
 #pragma unroll 1
-    for (int it = 0; it < (TH + 2) * TW / 32; ++it) {
+    for (int it = IT0; it < IT1; ++it) {
+        fetch(it + 1, gn);
         const int pix = it * 32 + pl;
         const int r = pix / TW, c0 = pix - r * TW;
         const int h = h0 - 1 + r;
         const bool row_ok = h >= 0 && h < H;
-        float g[8];
-        if (row_ok) {
-            load8<T>(dy + (((long)b * H + h) * W + c0) * CO + cg * 8, g);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) g[c] = 0.f;
-        }
         if (DGRAD) {
         float s[9];
 #pragma unroll
@@ -164,6 +174,8 @@ conv_c1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const floa
 #pragma unroll
                 for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], xn[t], acc[c][t]);
         }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) g[c] = gn[c];
     }
     // ---- wgrad: reduce the per-thread accumulators (lanes with equal cg, then across warps)
     if (WGRAD) {

@@ -5,7 +5,7 @@
 // (reference models/audio_encoder.py:113-124,183-184), which materialises the complex
 // spectrum, the magnitude and the power tensors in HBM (SURVEY.md §8a rows a1,a2).
 // Here one CTA stages 8 frames worth of contiguous samples (3264 floats, coalesced),
-// runs four 1024-point complex FFTs (two real frames packed per FFT) entirely in shared
+// runs four 1024-point complex FFTs (Stockham radix-4; two real frames packed per FFT) in shared
 // memory and writes only the [B, T0, 64] dB tensor.
 #include "common.cuh"
 
@@ -24,13 +24,11 @@ constexpr int THREADS = 256;
 struct FrontendSmem {
     float samples[SPAN];
     float2 z[PAIRS][N_FFT];
-    float2 tw[N_FFT / 2];
+    float2 tw[3 * N_FFT / 4];
     float win[N_FFT];
     float power[FRAMES_PER_CTA][P_STRIDE];
     float db[FRAMES_PER_CTA][N_MELS];
 };
-
-__device__ __forceinline__ int bitrev10(int x) { return (int)(__brev((unsigned)x) >> 22); }
 
 __global__ void __launch_bounds__(THREADS)
 logmel_kernel(const float* __restrict__ wav, int L, long wav_stride, int T0,
@@ -54,7 +52,7 @@ logmel_kernel(const float* __restrict__ wav, int L, long wav_stride, int T0,
         if (src >= 0 && src < L) v = __ldg(w + src);
         s.samples[i] = v;
     }
-    for (int i = tid; i < N_FFT / 2; i += THREADS) {
+    for (int i = tid; i < 3 * N_FFT / 4; i += THREADS) {
         float sn, cs;
         sincospif(2.0f * (float)i / (float)N_FFT, &sn, &cs);
         s.tw[i] = make_float2(cs, -sn);
@@ -62,31 +60,53 @@ logmel_kernel(const float* __restrict__ wav, int L, long wav_stride, int T0,
     for (int i = tid; i < N_FFT; i += THREADS) s.win[i] = __ldg(window + i);
     __syncthreads();
 
-    // ---- windowed load in bit-reversed order; frame 2p -> real part, 2p+1 -> imaginary
+    // ---- windowed load (natural order); frame 2p -> real part, 2p+1 -> imaginary part
     for (int i = tid; i < PAIRS * N_FFT; i += THREADS) {
         int p = i >> 10, n = i & (N_FFT - 1);
         float wn = s.win[n];
         float xa = s.samples[(2 * p) * HOP + n] * wn;
         float xb = s.samples[(2 * p + 1) * HOP + n] * wn;
-        s.z[p][bitrev10(n)] = make_float2(xa, xb);
+        s.z[p][n] = make_float2(xa, xb);
     }
     __syncthreads();
 
-    // ---- radix-2 decimation-in-time, 10 stages, 4 x 512 butterflies per stage
+    // ---- Stockham radix-4, 5 stages (1024 = 4^5); each thread owns 4 butterflies per stage.
+    //      in-place on one buffer: all reads of a stage complete before its writes.
 #pragma unroll 1
-    for (int stage = 0; stage < 10; ++stage) {
-        const int half = 1 << stage;
-        const int tw_step = (N_FFT / 2) >> stage;
-        for (int i = tid; i < PAIRS * (N_FFT / 2); i += THREADS) {
-            int p = i >> 9, j = i & 511;
-            int pos = j & (half - 1);
-            int i0 = ((j >> stage) << (stage + 1)) + pos;
-            int i1 = i0 + half;
-            float2 wv = s.tw[pos * tw_step];
-            float2 a = s.z[p][i0], c = s.z[p][i1];
-            float2 t = make_float2(c.x * wv.x - c.y * wv.y, c.x * wv.y + c.y * wv.x);
-            s.z[p][i0] = make_float2(a.x + t.x, a.y + t.y);
-            s.z[p][i1] = make_float2(a.x - t.x, a.y - t.y);
+    for (int ns_log = 0; ns_log < 10; ns_log += 2) {
+        const int Ns = 1 << ns_log;                 // size of the sub-transforms already formed
+        const int tw_step = (N_FFT / 4) >> ns_log;  // N / (4 Ns)
+        float2 u[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int q = tid + THREADS * i;
+            const int p = q >> 8, j = q & 255;
+            const int k = j & (Ns - 1);
+            const int m1 = k * tw_step;
+            u[i][0] = s.z[p][j];
+#pragma unroll
+            for (int r = 1; r < 4; ++r) {
+                const float2 x = s.z[p][j + r * (N_FFT / 4)];
+                const float2 wv = s.tw[r * m1];
+                u[i][r] = make_float2(x.x * wv.x - x.y * wv.y, x.x * wv.y + x.y * wv.x);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int q = tid + THREADS * i;
+            const int p = q >> 8, j = q & 255;
+            const int k = j & (Ns - 1);
+            const int j0 = ((j - k) << 2) + k;
+            const float2 v0 = make_float2(u[i][0].x + u[i][2].x, u[i][0].y + u[i][2].y);
+            const float2 v1 = make_float2(u[i][0].x - u[i][2].x, u[i][0].y - u[i][2].y);
+            const float2 v2 = make_float2(u[i][1].x + u[i][3].x, u[i][1].y + u[i][3].y);
+            const float2 d = make_float2(u[i][1].x - u[i][3].x, u[i][1].y - u[i][3].y);
+            const float2 v3 = make_float2(d.y, -d.x);                   // (u1 - u3) * (-i)
+            s.z[p][j0] = make_float2(v0.x + v2.x, v0.y + v2.y);
+            s.z[p][j0 + Ns] = make_float2(v1.x + v3.x, v1.y + v3.y);
+            s.z[p][j0 + 2 * Ns] = make_float2(v0.x - v2.x, v0.y - v2.y);
+            s.z[p][j0 + 3 * Ns] = make_float2(v1.x - v3.x, v1.y - v3.y);
         }
         __syncthreads();
     }

@@ -11,6 +11,7 @@
 // Replaces the cuDNN RNN behind nn.GRU (reference models/audio_encoder.py:141,217).
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <utility>
 namespace cg = cooperative_groups;
 
 namespace {
@@ -83,15 +84,24 @@ gru_fwd_tc_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, 
 #pragma unroll
     for (int r = 0; r < NCTA; ++r) peer_h[r] = cluster.map_shared_rank(&s.h[0][0][0], r);
 
+    // input projections are fetched two steps ahead (their L2/HBM latency is off the critical path)
+    auto fetch_gi = [&](int step, float (&g3)[3]) {
+        g3[0] = g3[1] = g3[2] = 0.f;
+        if (b_ok && step < T) {
+            const int t = dir == 0 ? step : T - 1 - step;
+            const float* g = gi + ((long)bglob * T + t) * (2 * G3) + dir * G3;
+            g3[0] = __ldg(g + jg); g3[1] = __ldg(g + HID + jg); g3[2] = __ldg(g + 2 * HID + jg);
+        }
+    };
+    float gi_cur[3], gi_nxt[3], gi_nn[3];
+    fetch_gi(0, gi_cur);
+    fetch_gi(1, gi_nxt);
     float hprev = 0.f;
     int cur = 0;
     for (int step = 0; step < T; ++step) {
         const int t = dir == 0 ? step : T - 1 - step;
-        float gi_r = 0.f, gi_z = 0.f, gi_n = 0.f;
-        if (b_ok) {
-            const float* g = gi + ((long)bglob * T + t) * (2 * G3) + dir * G3;
-            gi_r = __ldg(g + jg); gi_z = __ldg(g + HID + jg); gi_n = __ldg(g + 2 * HID + jg);
-        }
+        fetch_gi(step + 2, gi_nn);
+        const float gi_r = gi_cur[0], gi_z = gi_cur[1], gi_n = gi_cur[2];
         // ---- partial product on the tensor cores
         uint32_t bfrag[2][2];
 #pragma unroll
@@ -124,6 +134,14 @@ gru_fwd_tc_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, 
         const float n = fast_tanh(gi_n + r * gh_n);
         const float hnew = (1.f - z) * n + z * hprev;
         hprev = hnew;
+        const int nxt = cur ^ 1;
+        const int off = (nxt * BS + bl) * HPAD + jg;
+        const bf16 hb = __float2bfloat16_rn(hnew);
+#pragma unroll
+        for (int rnk = 0; rnk < NCTA; ++rnk) peer_h[rnk][off] = hb;
+        // arrive first, then issue the HBM stores: the release of the NEXT arrive waits for them,
+        // a whole step later, instead of this one
+        auto token = cluster.barrier_arrive();
         if (b_ok) {
             out[((long)bglob * T + t) * (2 * HID) + dir * HID + jg] = hnew;
             if (gates != nullptr) {
@@ -131,12 +149,9 @@ gru_fwd_tc_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, 
                 gp[jg] = r; gp[HID + jg] = z; gp[2 * HID + jg] = n; gp[3 * HID + jg] = gh_n;
             }
         }
-        const int nxt = cur ^ 1;
-        const int off = (nxt * BS + bl) * HPAD + jg;
-        const bf16 hb = __float2bfloat16_rn(hnew);
 #pragma unroll
-        for (int rnk = 0; rnk < NCTA; ++rnk) peer_h[rnk][off] = hb;
-        cluster.sync();
+        for (int i = 0; i < 3; ++i) { gi_cur[i] = gi_nxt[i]; gi_nxt[i] = gi_nn[i]; }
+        cluster.barrier_wait(std::move(token));
         cur = nxt;
     }
 }
@@ -202,20 +217,15 @@ gru_bwd_tc_kernel(const float* __restrict__ d_out, const float* __restrict__ out
     int cur = 0;
     for (int step = 0; step < T; ++step) {
         const int t = dir == 0 ? T - 1 - step : step;
-        float g_r = 0.f, g_z = 0.f, g_n = 0.f, dh_direct = 0.f;
+        float g_r = 0.f, g_z = 0.f, g_n = 0.f, dh_direct = 0.f, s_dn = 0.f, s_hp = 0.f;
         if (b_ok) {
-            const long bt = (long)bglob * T + t;
             const float r = p_r, z = p_z, n = p_n, hn = p_hn, hprev = p_hp;
             const float dht = dh + p_do;
             const float dn_pre = dht * (1.f - z) * (1.f - n * n);
             const float dz_pre = dht * (hprev - n) * z * (1.f - z);
             const float dr_pre = dn_pre * hn * r * (1.f - r);
-            float* gi_p = dgi + bt * (2 * G3) + dir * G3;
-            gi_p[jg] = dr_pre; gi_p[HID + jg] = dz_pre; gi_p[2 * HID + jg] = dn_pre;
+            s_dn = dn_pre; s_hp = hprev;
             g_r = dr_pre; g_z = dz_pre; g_n = dn_pre * r;
-            float* gh_p = dgh_out + ((long)dir * B * T + bt) * G3;
-            gh_p[jg] = g_r; gh_p[HID + jg] = g_z; gh_p[2 * HID + jg] = g_n;
-            hprev_out[((long)dir * B * T + bt) * HID + jg] = hprev;
             dh_direct = dht * z;
         }
         {
@@ -226,8 +236,17 @@ gru_bwd_tc_kernel(const float* __restrict__ d_out, const float* __restrict__ out
                 peer[rnk][o] = v_r; peer[rnk][o + HID] = v_z; peer[rnk][o + 2 * HID] = v_n;
             }
         }
-        cluster.sync();
+        auto token = cluster.barrier_arrive();
+        if (b_ok) {          // HBM stores after the arrive (see the forward kernel)
+            const long bt = (long)bglob * T + t;
+            float* gi_p = dgi + bt * (2 * G3) + dir * G3;
+            gi_p[jg] = g_r; gi_p[HID + jg] = g_z; gi_p[2 * HID + jg] = s_dn;
+            float* gh_p = dgh_out + ((long)dir * B * T + bt) * G3;
+            gh_p[jg] = g_r; gh_p[HID + jg] = g_z; gh_p[2 * HID + jg] = g_n;
+            hprev_out[((long)dir * B * T + bt) * HID + jg] = s_hp;
+        }
         fetch(step + 1);
+        cluster.barrier_wait(std::move(token));
         // dh_prev[b][k_local] = sum_row dgh[b][row] * W_hh[row][32 cta + k_local]
         float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll

@@ -74,15 +74,16 @@ __global__ void scale_shift_act_kernel(const TI* __restrict__ x, TO* __restrict_
                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                        long n_vec, int C, int relu) {
     // n_vec counts 8-element vectors; two independent vectors per thread per iteration
-    const long stride = (long)gridDim.x * blockDim.x;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n_vec; i += 2 * stride) {
-        const long i2 = i + stride;
-        const bool has2 = i2 < n_vec;
+    const unsigned stride = gridDim.x * blockDim.x;            // n_vec < 2^31 (host-checked)
+    const unsigned CV = (unsigned)C / 8;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)n_vec; i += 2 * stride) {
+        const unsigned i2 = i + stride;
+        const bool has2 = i2 < (unsigned)n_vec;
         float v[8], u[8];
-        load8<TI>(x + i * 8, v);
-        if (has2) load8<TI>(x + i2 * 8, u);
+        load8<TI>(x + (long)i * 8, v);
+        if (has2) load8<TI>(x + (long)i2 * 8, u);
         {
-            const int c = (int)((i * 8) % C);
+            const int c = (int)(i % CV) * 8;
             float sc[8], sh[8];
             load8<float>(scale + c, sc);
             load8<float>(shift + c, sh);
@@ -91,10 +92,10 @@ __global__ void scale_shift_act_kernel(const TI* __restrict__ x, TO* __restrict_
                 v[k] = fmaf(v[k], sc[k], sh[k]);
                 if (relu) v[k] = fmaxf(v[k], 0.f);
             }
-            store8<TO>(y + i * 8, v);
+            store8<TO>(y + (long)i * 8, v);
         }
         if (has2) {
-            const int c = (int)((i2 * 8) % C);
+            const int c = (int)(i2 % CV) * 8;
             float sc[8], sh[8];
             load8<float>(scale + c, sc);
             load8<float>(shift + c, sh);
@@ -103,7 +104,7 @@ __global__ void scale_shift_act_kernel(const TI* __restrict__ x, TO* __restrict_
                 u[k] = fmaf(u[k], sc[k], sh[k]);
                 if (relu) u[k] = fmaxf(u[k], 0.f);
             }
-            store8<TO>(y + i2 * 8, u);
+            store8<TO>(y + (long)i2 * 8, u);
         }
     }
 }
@@ -116,13 +117,14 @@ __global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ y, T* __restrict__
                                         float keep_scale) {
     if (seed_dev != nullptr) seed += *seed_dev;
     const int Ho = H / PH, Wo = W / PW, CV = C / 8;
-    const long n = (long)B * Ho * Wo * CV;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % CV);
-        long r = i / CV;
-        const int wo = (int)(r % Wo); r /= Wo;
-        const int ho = (int)(r % Ho);
-        const int b = (int)(r / Ho);
+    const unsigned n = (unsigned)B * Ho * Wo * CV;             // < 2^31 (host-checked)
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned r = i / (unsigned)CV;
+        const int cv = (int)(i - r * CV);
+        const unsigned r2 = r / (unsigned)Wo;
+        const int wo = (int)(r - r2 * Wo);
+        const int b = (int)(r2 / (unsigned)Ho);
+        const int ho = (int)(r2 - (unsigned)b * Ho);
         float sc[8], sh[8];
         load8<float>(scale + cv * 8, sc);
         load8<float>(shift + cv * 8, sh);
@@ -143,7 +145,7 @@ __global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ y, T* __restrict__
                 }
             }
         float o[8];
-        const long obase = i * 8;
+        const long obase = (long)i * 8;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             float v = sum[k] * (1.0f / (PH * PW)) + mx[k];

@@ -56,19 +56,19 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dout, T* 
     const int cv = threadIdx.x % CV;
     const int slot_lane = threadIdx.x / CV;
     const int slots_per_block = blockDim.x / CV;
-    const long n_slots = (long)B * Hs * Ws;
+    const unsigned n_slots = (unsigned)B * Hs * Ws;          // < 2^31 (host-checked): 32-bit index math
     const int c_base = cv * VEC;
 
     float rs[VEC], rq[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) { rs[k] = 0.f; rq[k] = 0.f; }
 
-    for (long s = (long)blockIdx.x * slots_per_block + slot_lane; s < n_slots;
-         s += (long)gridDim.x * slots_per_block) {
-        const int ws_ = (int)(s % Ws);
-        const long r = s / Ws;
-        const int hs = (int)(r % Hs);
-        const int b = (int)(r / Hs);
+    for (unsigned s = blockIdx.x * slots_per_block + slot_lane; s < n_slots;
+         s += gridDim.x * slots_per_block) {
+        const unsigned r = s / (unsigned)Ws;
+        const int ws_ = (int)(s - r * Ws);
+        const int b = (int)(r / (unsigned)Hs);
+        const int hs = (int)(r - (unsigned)b * Hs);
         const bool full = POOL ? (hs < Ho && ws_ < Wo) : true;
         const long oidx = ((((long)b * Ho + hs) * Wo + ws_) * CV + cv) * VEC;
         uint4 raw_g = make_uint4(0u, 0u, 0u, 0u);
@@ -179,6 +179,7 @@ int pool_bwd_dispatch(const void* y, const void* dout, void* dy, const float* sc
     const int spb = 256 / CV;
     const int ph_e = ph > 0 ? ph : 1, pw_e = pw > 0 ? pw : 1;
     const long n_slots = (long)B * ((H + ph_e - 1) / ph_e) * ((W + pw_e - 1) / pw_e);
+    if (n_slots >= (1L << 31)) return TAG_ERR_BAD_ARG;
     long blocks = (n_slots + spb - 1) / spb;
     if (blocks > 148 * 12) blocks = 148 * 12;
     if (blocks < 1) blocks = 1;
