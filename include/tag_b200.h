@@ -77,6 +77,9 @@ int tag_conv_tc_fwd(const void* x, const void* w, void* y, int y_dtype, const fl
                     double* stats, int B, int H, int W, int Cin, int Cout, int taps, cudaStream_t stream);
 int tag_conv_tc_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout,
                       int taps, int splits, cudaStream_t stream);
+/* 3x3, Cin = 64 only: all nine taps accumulate in one CTA's TMEM (x boxes shared by the vertical taps). */
+int tag_conv_tc_wgrad64(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout, int splits,
+                        cudaStream_t stream);
 /* 3x3 only: same result as tag_conv_tc_fwd(taps=9, no bias/relu) with the input halo tile re-used
  * across the three vertical taps (16x8-pixel output tiles; W must be a multiple of 8). */
 int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, double* stats, int B, int H,

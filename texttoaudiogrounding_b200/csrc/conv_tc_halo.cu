@@ -30,7 +30,9 @@ struct HaloSmem {
     static constexpr int TOTAL = STATS_OFFSET + 2 * BLOCK_N * 4 + 1024;
 };
 
-template <int BLOCK_N, typename TO, int B_STAGES, int TPS>
+// WRES (Cin == 64, Cout == BLOCK_N <= 128): the whole 9-tap weight tensor (<= 144 KB) is loaded ONCE
+// per CTA into the three weight stages and stays resident; only the input boxes stream.
+template <int BLOCK_N, typename TO, int B_STAGES, int TPS, bool WRES>
 __global__ void __launch_bounds__(320, 1)
 conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W, int Cin, int Cout) {
@@ -88,6 +90,12 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         // ===================== TMA producer =====================
         if (lane == 0) {
             int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
+            if (WRES) {
+                for (int dwi = 0; dwi < 3; ++dwi) {
+                    mbar_arrive_expect_tx(b_full + 8 * dwi, L::B_TILE_BYTES);
+                    tma_load_3d(base + L::B_OFFSET + dwi * L::B_TILE_BYTES, &tmap_w, b_full + 8 * dwi, 0, 0, dwi * 3);
+                }
+            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int n_tile, b, h0, w0;
                 decode(tile, n_tile, b, h0, w0);
@@ -98,7 +106,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                         tma_load_4d(base + L::A_OFFSET + as * A_SUB_BYTES, &tmap_x, a_full + 8 * as, kc * 64,
                                     w0 + dwi - 1, h0 - 1, b);
                         if (++as == A_STAGES) { as = 0; aph ^= 1; }
-                        for (int dhi = 0; dhi < 3; dhi += TPS) {
+                        for (int dhi = 0; dhi < 3 && !WRES; dhi += TPS) {
                             mbar_wait(b_empty + 8 * bs, bph ^ 1);
                             mbar_arrive_expect_tx(b_full + 8 * bs, L::B_TILE_BYTES);
                             tma_load_3d(base + L::B_OFFSET + bs * L::B_TILE_BYTES, &tmap_w, b_full + 8 * bs,
@@ -126,6 +134,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                     mbar_wait(a_full + 8 * as, aph);
                     const uint32_t sa = base + L::A_OFFSET + as * A_SUB_BYTES;
                     for (int dhi = 0; dhi < 3; dhi += TPS) {
+                        if (WRES) { bs = dwi; bph = 0; }           // resident stage: completed once, stays readable
                         mbar_wait(b_full + 8 * bs, bph);
                         tc_fence_after();
                         if (lane == 0) {
@@ -140,12 +149,12 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                                     first = 0;
                                 }
                             }
-                            umma_commit(b_empty + 8 * bs);
+                            if (!WRES) umma_commit(b_empty + 8 * bs);
                             if (dhi + TPS >= 3) umma_commit(a_empty + 8 * as);
                             if (kc == KC - 1 && dwi == 2 && dhi + TPS >= 3) umma_commit(tmem_full + 8 * acc);
                         }
                         __syncwarp();
-                        if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
+                        if (!WRES && ++bs == B_STAGES) { bs = 0; bph ^= 1; }
                     }
                     if (++as == A_STAGES) { as = 0; aph ^= 1; }
                 }
@@ -215,13 +224,13 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
-template <int BLOCK_N, typename TO>
+template <int BLOCK_N, typename TO, bool WRES>
 int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* stats, int B, int H, int W,
                 int Cin, int Cout, cudaStream_t stream) {
     constexpr int TPS = BLOCK_N == 256 ? 1 : 3;
-    constexpr int B_STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 3 : 5);
+    constexpr int B_STAGES = WRES ? 3 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 3 : 5));
     using L = HaloSmem<BLOCK_N, B_STAGES, TPS>;
-    auto kern = conv_tc_fwd_halo_kernel<BLOCK_N, TO, B_STAGES, TPS>;
+    auto kern = conv_tc_fwd_halo_kernel<BLOCK_N, TO, B_STAGES, TPS, WRES>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
@@ -296,11 +305,12 @@ extern "C" int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y
     if (rc != TAG_OK) return rc;
     rc = make_w3_tmap(&tw, w, Cout, Cin, block_n, block_n == 256 ? 1 : 3);
     if (rc != TAG_OK) return rc;
-#define TAG_HALO(BN_)                                                                              \
-    (y_dtype == TAG_DTYPE_BF16 ? launch_halo<BN_, bf16>(tx, tw, y, stats, B, H, W, Cin, Cout, stream)  \
-                               : launch_halo<BN_, float>(tx, tw, y, stats, B, H, W, Cin, Cout, stream))
-    if (block_n == 256) return TAG_HALO(256);
-    if (block_n == 128) return TAG_HALO(128);
-    return TAG_HALO(64);
+#define TAG_HALO(BN_, WR_)                                                                               \
+    (y_dtype == TAG_DTYPE_BF16 ? launch_halo<BN_, bf16, WR_>(tx, tw, y, stats, B, H, W, Cin, Cout, stream)  \
+                               : launch_halo<BN_, float, WR_>(tx, tw, y, stats, B, H, W, Cin, Cout, stream))
+    const bool wres = Cin == 64 && Cout == block_n && block_n <= 128;
+    if (block_n == 256) return TAG_HALO(256, false);
+    if (block_n == 128) return wres ? TAG_HALO(128, true) : TAG_HALO(128, false);
+    return wres ? TAG_HALO(64, true) : TAG_HALO(64, false);
 #undef TAG_HALO
 }

@@ -73,7 +73,9 @@ def conv_wgrad(dy, x, dw, B, H, W, Cin, Cout, taps, splits, tc=None):
     if tc is None:
         tc = (dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and tc_eligible(W, Cin, Cout)
               and (taps == 9 or Cin >= 128))
-    if tc:
+    if tc and USE_HALO and taps == 9 and Cin == 64 and W % 8 == 0:
+        call("tag_conv_tc_wgrad64", dy, x, dw, B, H, W, Cout, max(1, 148 // (Cout // 64)))
+    elif tc:
         call("tag_conv_tc_wgrad", dy, x, dw, B, H, W, Cin, Cout, taps, tc_wgrad_splits(B, H, W, Cin, Cout, taps))
     else:
         call("tag_conv_wgrad", dy, dt(dy), x, dt(x), dw, B, H, W, Cin, Cout, taps, splits)
