@@ -79,7 +79,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 
     if (warp == 4) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_tile = tile / m_tiles, m_tile = tile - n_tile * m_tiles;
@@ -111,7 +111,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             for (int kb = 0; kb < k_blocks; ++kb) {
                 mbar_wait(full_bar + 8 * stage, phase);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     const uint32_t sa = base + stage * L::STAGE_BYTES;
                     const uint64_t adesc = make_smem_desc(sa, 16, 1024);
                     const uint64_t bdesc = make_smem_desc(sa + A_TILE_BYTES, 16, 1024);
@@ -263,7 +263,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 4) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             for (int kt = kt_begin; kt < kt_end; ++kt) {
                 const int b = kt / tiles_h, h0 = (kt - b * tiles_h) * THK;
@@ -289,7 +289,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         for (int kt = kt_begin; kt < kt_end; ++kt) {
             mbar_wait(full_bar + 8 * stage, phase);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one_sync()) {
                 const uint32_t sa = base + stage * L::STAGE_BYTES;
                 // MN-major SWIZZLE_128B: LBO = distance between 64-channel boxes, SBO = 8 pixel rows
                 const uint64_t adesc = make_smem_desc(sa, WG_BOX_BYTES, 1024);

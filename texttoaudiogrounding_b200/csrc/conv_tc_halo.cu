@@ -10,24 +10,30 @@
 // tiles stream through their own ring.  Same warp roles / TMEM double buffering / epilogue as
 // conv_tc_fwd_kernel.
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace {
 
 constexpr int TILE_H = 16, TILE_W = 8;
 constexpr int A_SUB_BYTES = (TILE_H + 2) * TILE_W * 128;      // 18432
-constexpr int A_STAGES = 4;
 
 // TPS = taps per weight stage: for narrow tiles (BLOCK_N <= 128) the three vertical taps of one
 // horizontal shift travel as ONE 3-D TMA box of the tap-major weight tensor [tap'][Cout][Cin]
 // (tap' = dwi*3 + dhi), so the single MMA-issuing thread gets 12 MMAs per barrier round trip.
-template <int BLOCK_N, int B_STAGES, int TPS>
+// A_STAGES: an input box feeds only 12 MMAs (384 cycles at N = 64), so the ring must be deep enough in
+// TIME to cover the ~2000-cycle L2/HBM latency of a TMA load: 8 boxes in flight for the narrow tiles.
+template <int BLOCK_N, int B_STAGES, int TPS, bool WRES>
 struct HaloSmem {
+    static constexpr int A_STAGES = BLOCK_N == 64 ? (WRES ? 6 : 4) : (BLOCK_N == 128 ? 3 : 4);
+    static_assert(true, "");
     static constexpr int B_TILE_BYTES = TPS * BLOCK_N * 128;
     static constexpr int A_OFFSET = 0;
     static constexpr int B_OFFSET = A_STAGES * A_SUB_BYTES;
     static constexpr int BAR_OFFSET = B_OFFSET + B_STAGES * B_TILE_BYTES;
     static constexpr int STATS_OFFSET = BAR_OFFSET + 512;
-    static constexpr int TOTAL = STATS_OFFSET + 2 * BLOCK_N * 4 + 1024;
+    static constexpr int TBUF_OFFSET = STATS_OFFSET + 2 * BLOCK_N * 4;
+    static constexpr int TOTAL = TBUF_OFFSET + 8 * 32 * 17 * 4 + 1024;
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
 // WRES (Cin == 64, Cout == BLOCK_N <= 128): the whole 9-tap weight tensor (<= 144 KB) is loaded ONCE
@@ -35,8 +41,10 @@ struct HaloSmem {
 template <int BLOCK_N, typename TO, int B_STAGES, int TPS, bool WRES>
 __global__ void __launch_bounds__(320, 1)
 conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                        TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W, int Cin, int Cout) {
-    using L = HaloSmem<BLOCK_N, B_STAGES, TPS>;
+                        TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W, int Cin, int Cout,
+                        int dbg) {
+    using L = HaloSmem<BLOCK_N, B_STAGES, TPS, WRES>;
+    constexpr int A_STAGES = L::A_STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -51,6 +59,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(base_ptr + L::BAR_OFFSET + 16 * A_STAGES + 16 * B_STAGES + 32);
     float* s_stats = reinterpret_cast<float*>(base_ptr + L::STATS_OFFSET);
+    float* t_buf = reinterpret_cast<float*>(base_ptr + L::TBUF_OFFSET);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_w = W / TILE_W;
@@ -88,7 +97,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 
     if (warp == 8) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
             if (WRES) {
                 for (int dwi = 0; dwi < 3; ++dwi) {
@@ -137,7 +146,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                         if (WRES) { bs = dwi; bph = 0; }           // resident stage: completed once, stays readable
                         mbar_wait(b_full + 8 * bs, bph);
                         tc_fence_after();
-                        if (lane == 0) {
+                        if (elect_one_sync()) {
 #pragma unroll
                             for (int tt = 0; tt < TPS; ++tt) {
                                 const uint64_t adesc = make_smem_desc(sa + (dhi + tt) * (TILE_W * 128), 16, 1024);
@@ -164,13 +173,32 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         // ===================== epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., column half w/4
         int it = 0;
         int cur_n_tile = -1;
+        constexpr int CPW = BLOCK_N / 64;            // 32-column chunks per warp
+        // running per-channel sums live in registers (lane l owns column l of each of the warp's chunks); shared-memory
+        // float atomics are CAS loops and were the epilogue bottleneck of the small-K layers
+        float run_s[CPW], run_q[CPW];
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) { run_s[i] = 0.f; run_q[i] = 0.f; }
         auto flush_stats = [&](int n_tile) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < CPW; ++i) {
+                t_buf[warp * BLOCK_N + i * 32 + lane] = run_s[i];
+                t_buf[warp * BLOCK_N + BLOCK_N / 2 + i * 32 + lane] = run_q[i];
+                run_s[i] = 0.f;
+                run_q[i] = 0.f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             for (int i = threadIdx.x; i < BLOCK_N; i += 256) {
-                atomicAdd(stats + n_tile * BLOCK_N + i, (double)s_stats[i]);
-                atomicAdd(stats + Cout + n_tile * BLOCK_N + i, (double)s_stats[BLOCK_N + i]);
-                s_stats[i] = 0.f;
-                s_stats[BLOCK_N + i] = 0.f;
+                const int ch = i / (BLOCK_N / 2), local = i % (BLOCK_N / 2);
+                double ds = 0.0, dq = 0.0;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    ds += t_buf[(ch * 4 + q4) * BLOCK_N + local];
+                    dq += t_buf[(ch * 4 + q4) * BLOCK_N + BLOCK_N / 2 + local];
+                }
+                atomicAdd(stats + n_tile * BLOCK_N + i, ds);
+                atomicAdd(stats + Cout + n_tile * BLOCK_N + i, dq);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
         };
@@ -188,33 +216,46 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             const int h = h0 + (row >> 3), w = w0 + (row & 7);
             const bool valid = h < H;
             TO* yrow = y + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N;
-#pragma unroll 1
-            for (int c = chalf * (BLOCK_N / 64); c < (chalf + 1) * (BLOCK_N / 64); ++c) {
+#pragma unroll
+            for (int cc = 0; cc < CPW; ++cc) {
+                const int c = chalf * CPW + cc;
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + acc * BLOCK_N + c * 32, r);
-                tmem_ld_wait();
-                float v[32], q[32];
+                if (!(dbg & 2)) {
+                    tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + acc * BLOCK_N + c * 32, r);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0;
+                }
+                if (cc == CPW - 1) {                     // accumulator drained: hand it back to the MMA warp now
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
+                }
+                float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float f = round_to<TO>(__uint_as_float(r[j]));
                     v[j] = valid ? f : 0.f;
                 }
-                if (valid) {
+                // pack the output first, reduce the statistics (in place on v), store last: the stores then
+                // never hold a read-dependency on registers the shuffle reduction wants to overwrite
+                uint4 packed[sizeof(TO) == 2 ? 4 : 8];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) store8<TO>(yrow + c * 32 + j, &v[j]);
-                }
+                for (int j = 0; j < 32; j += 4) pack4<TO>(packed[sizeof(TO) == 2 ? j / 8 : j / 4], (j / 4) & 1, &v[j]);
                 if (stats != nullptr) {
+                    float q[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] = v[j] * v[j];
-                    const float cs = warp_transpose_sum(v, lane);
-                    const float cq = warp_transpose_sum(q, lane);
-                    atomicAdd(&s_stats[c * 32 + lane], cs);
-                    atomicAdd(&s_stats[BLOCK_N + c * 32 + lane], cq);
+                    run_s[cc] += warp_transpose_sum(v, lane);
+                    run_q[cc] += warp_transpose_sum(q, lane);
+                }
+                if (valid && !(dbg & 1)) {
+#pragma unroll
+                    for (int j = 0; j < (sizeof(TO) == 2 ? 4 : 8); ++j)
+                        st16(reinterpret_cast<uint8_t*>(yrow + c * 32) + 16 * j, packed[j]);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
         }
         if (stats != nullptr && cur_n_tile >= 0) flush_stats(cur_n_tile);
     }
@@ -229,7 +270,7 @@ int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* s
                 int Cin, int Cout, cudaStream_t stream) {
     constexpr int TPS = BLOCK_N == 256 ? 1 : 3;
     constexpr int B_STAGES = WRES ? 3 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 3 : 5));
-    using L = HaloSmem<BLOCK_N, B_STAGES, TPS>;
+    using L = HaloSmem<BLOCK_N, B_STAGES, TPS, WRES>;
     auto kern = conv_tc_fwd_halo_kernel<BLOCK_N, TO, B_STAGES, TPS, WRES>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -239,7 +280,8 @@ int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* s
     }
     const int total_tiles = B * ((H + TILE_H - 1) / TILE_H) * (W / TILE_W) * (Cout / BLOCK_N);
     const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
-    kern<<<grid, 320, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout);
+    static int dbg = getenv("TAG_HALO_DBG") ? atoi(getenv("TAG_HALO_DBG")) : 0;
+    kern<<<grid, 320, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout, dbg);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }

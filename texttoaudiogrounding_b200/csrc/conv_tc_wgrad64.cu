@@ -56,7 +56,7 @@ conv_tc_wgrad64_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 4) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             for (int kt = kt_begin; kt < kt_end; ++kt) {
                 const int b = kt / tiles_img;
@@ -78,7 +78,7 @@ conv_tc_wgrad64_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         for (int kt = kt_begin; kt < kt_end; ++kt) {
             mbar_wait(full_bar + 8 * stage, phase);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one_sync()) {
                 const uint32_t sa = base + stage * STAGE;
                 const uint64_t bdesc = make_smem_desc(sa + 3 * XBOX, YBOX, 1024);
 #pragma unroll

@@ -32,6 +32,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > WAIT_SPIN_LIMIT) __trap();     // never hang the GPU on a pipeline bug
     }
 }
+// One elected lane of a fully converged warp (cute::elect_one_sync): lets ptxas keep the TMA / UMMA
+// operands in uniform registers instead of wrapping every instruction in a lane-uniformisation loop.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
