@@ -81,9 +81,14 @@ int tag_conv_tc_wgrad(const void* dy, const void* x, float* dw, int B, int H, in
 int tag_conv_tc_wgrad64(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout, int splits,
                         cudaStream_t stream);
 /* 3x3 only: same result as tag_conv_tc_fwd(taps=9, no bias/relu) with the input halo tile re-used
- * across the three vertical taps (16x8-pixel output tiles; W must be a multiple of 8). */
+ * across the three vertical taps (16x8-pixel output tiles; W must be a multiple of 8).
+ * Optional fused ReLU+BatchNorm backward (dgrad use): with bn_y (the BN input, bf16 NHWC [B,H,W,Cout]) and
+ * its per-channel scale/shift/mean/invstd, the output is gated by the ReLU mask and `stats` receives
+ * dbeta = sum g and dgamma = sum g*xhat (the reduce pass of tag_bn_relu_pool_bwd, mode 0, no pooling). */
 int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, double* stats, int B, int H,
-                         int W, int Cin, int Cout, cudaStream_t stream);
+                         int W, int Cin, int Cout, const void* bn_y, const float* bn_scale,
+                         const float* bn_shift, const float* bn_mean, const float* bn_invstd,
+                         cudaStream_t stream);
 /* its weight operand: bf16 tap-major [9][Cout][Cin] (flip_transpose=0) or, for dgrad,
  * [9][Cin][Cout] of the 180-degree rotated kernel (flip_transpose=1), from the fp32 master. */
 int tag_weight_prep_tapmajor_bf16(const float* w, void* out, int Co, int Ci, int flip_transpose,

@@ -160,3 +160,28 @@ def test_bigru_bf16_tensor_core_variant_close_to_oracle(B, T):
     # hprev is the state each step consumed: forward direction = out shifted by one step
     hp = hprev[0].reshape(B, T, 256)
     assert torch.equal(hp[:, 1:], out[:, :-1, :256]) and float(hp[:, 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 21, 16, 128), (3, 9, 64, 64), (2, 17, 8, 512)])
+def test_halo_dgrad_with_fused_bn_relu_backward_reduce(B, H, W, C):
+    """dgrad epilogue fusion: ReLU gate + (dbeta, dgamma) reduction == separate mode-0 pass."""
+    from texttoaudiogrounding_b200 import ops
+    dy = _bf(torch.randn(B, H, W, C, generator=g(30))).cuda().bfloat16()
+    w32 = (torch.randn(C, 3, 3, C, generator=g(31)) * (1.0 / (3 * C ** 0.5))).cuda()
+    y1 = _bf(torch.randn(B, H, W, C, generator=g(32))).cuda().bfloat16()
+    aux = [t.cuda() for t in (torch.rand(C, generator=g(33)) + 0.5, torch.randn(C, generator=g(34)) * 0.3,
+                              torch.randn(C, generator=g(35)) * 0.1, torch.rand(C, generator=g(36)) + 0.5)]
+    wt = ops.prep_weight_t(w32, C, C, 9, torch.bfloat16, W)
+    # reference: plain dgrad, then the stand-alone reduce pass
+    da = torch.empty(B, H, W, C, device="cuda", dtype=torch.bfloat16)
+    ops.conv_fwd(dy, wt, da, None, False, None, B, H, W, C, C, 9)
+    red_ref = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    ops.call("tag_bn_relu_pool_bwd", 0, y1, da, None, 1, *aux, red_ref, 1, B, H, W, C, 0, 0, 0.0, 0, None)
+    # fused
+    g_f = torch.empty_like(da)
+    red = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    ops.conv_fwd(dy, wt, g_f, None, False, red, B, H, W, C, C, 9, bn_fuse=(y1, *aux))
+    torch.cuda.synchronize()
+    mask = (y1.float() * aux[0] + aux[1]) > 0
+    assert torch.equal(g_f.float(), torch.where(mask, da.float(), torch.zeros_like(da.float())))
+    np.testing.assert_allclose(red.cpu().numpy(), red_ref.cpu().numpy(), rtol=2e-3, atol=2e-2)

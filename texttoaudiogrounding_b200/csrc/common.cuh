@@ -89,14 +89,13 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Counter-based dropout RNG: one 32-bit draw per (seed, element index).  The same
-// function regenerates the mask in the backward pass, so no mask is ever stored.
-__device__ __forceinline__ uint32_t tag_hash32(uint64_t seed, uint64_t idx) {
+// Counter-based dropout RNG: one 64-bit draw per (seed, group of 4 consecutive elements), 16 bits per
+// element.  The same function regenerates the mask in the backward pass, so no mask is ever stored.
+__device__ __forceinline__ uint64_t tag_hash64(uint64_t seed, uint64_t idx) {
     uint64_t z = idx * 0x9E3779B97F4A7C15ull + seed;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return (uint32_t)(z >> 32);
+    return z ^ (z >> 31);
 }
 // 16-byte raw vector access: 8 bf16 or 4 fp32 channels per load
 template <typename T> struct Raw16 { static constexpr int VEC = 16 / (int)sizeof(T); static constexpr int NSUB = VEC / 4; };
@@ -133,8 +132,18 @@ inline void tag_dropout_params(float p, uint32_t* thresh, float* keep_scale) {
     *keep_scale = 1.0f / (1.0f - p);
 }
 
-// keep-scale: 0 when dropped, 1/(1-p) when kept.  thresh = p * 2^32.
+// keep-scale: 0 when dropped, 1/(1-p) when kept.  thresh = p * 2^32 (its top 16 bits are compared).
 __device__ __forceinline__ float tag_dropout_scale(uint64_t seed, uint64_t idx, uint32_t thresh,
                                                    float keep_scale) {
-    return tag_hash32(seed, idx) >= thresh ? keep_scale : 0.0f;
+    const uint64_t z = tag_hash64(seed, idx >> 2);
+    const uint32_t u = (uint32_t)(z >> (16 * (idx & 3))) & 0xFFFFu;
+    return u >= (thresh >> 16) ? keep_scale : 0.0f;
+}
+// four consecutive elements starting at idx4 (a multiple of 4): one hash
+__device__ __forceinline__ void tag_dropout_scale4(uint64_t seed, uint64_t idx4, uint32_t thresh,
+                                                    float keep_scale, float* s4) {
+    const uint64_t z = tag_hash64(seed, idx4 >> 2);
+    const uint32_t t16 = thresh >> 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s4[k] = ((uint32_t)(z >> (16 * k)) & 0xFFFFu) >= t16 ? keep_scale : 0.0f;
 }

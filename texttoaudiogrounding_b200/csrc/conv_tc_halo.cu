@@ -31,8 +31,9 @@ struct HaloSmem {
     static constexpr int B_OFFSET = A_STAGES * A_SUB_BYTES;
     static constexpr int BAR_OFFSET = B_OFFSET + B_STAGES * B_TILE_BYTES;
     static constexpr int STATS_OFFSET = BAR_OFFSET + 512;
-    static constexpr int TBUF_OFFSET = STATS_OFFSET + 2 * BLOCK_N * 4;
-    static constexpr int TOTAL = TBUF_OFFSET + 8 * 32 * 17 * 4 + 1024;
+    static constexpr int TBUF_OFFSET = STATS_OFFSET + 2 * BLOCK_N * 4;       // 8 warps x BLOCK_N floats (flush)
+    static constexpr int BNP_OFFSET = TBUF_OFFSET + 8 * BLOCK_N * 4;         // fused BN-backward params [4][512]
+    static constexpr int TOTAL = BNP_OFFSET + 4 * 512 * 4 + 1024;
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
@@ -42,7 +43,9 @@ template <int BLOCK_N, typename TO, int B_STAGES, int TPS, bool WRES>
 __global__ void __launch_bounds__(320, 1)
 conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W, int Cin, int Cout,
-                        int dbg) {
+                        const bf16* __restrict__ bn_y, const float* __restrict__ bn_scale,
+                        const float* __restrict__ bn_shift, const float* __restrict__ bn_mean,
+                        const float* __restrict__ bn_invstd, int dbg) {
     using L = HaloSmem<BLOCK_N, B_STAGES, TPS, WRES>;
     constexpr int A_STAGES = L::A_STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -60,6 +63,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         reinterpret_cast<volatile uint32_t*>(base_ptr + L::BAR_OFFSET + 16 * A_STAGES + 16 * B_STAGES + 32);
     float* s_stats = reinterpret_cast<float*>(base_ptr + L::STATS_OFFSET);
     float* t_buf = reinterpret_cast<float*>(base_ptr + L::TBUF_OFFSET);
+    float* s_bnp = reinterpret_cast<float*>(base_ptr + L::BNP_OFFSET);     // [sc | sh | xs | xo] x Cout
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_w = W / TILE_W;
@@ -80,6 +84,15 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     if (warp == 9) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x < 256)
         for (int i = threadIdx.x; i < 2 * BLOCK_N; i += 256) s_stats[i] = 0.f;
+    if (bn_y != nullptr) {
+        for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
+            const float is = bn_invstd[c];
+            s_bnp[c] = bn_scale[c];
+            s_bnp[512 + c] = bn_shift[c];
+            s_bnp[1024 + c] = is;
+            s_bnp[1536 + c] = -bn_mean[c] * is;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -209,13 +222,23 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             cur_n_tile = n_tile;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(tmem_full + 8 * acc, acc_phase);
-            tc_fence_after();
             const int lq = warp & 3, chalf = warp >> 2;
             const int row = lq * 32 + lane;
             const int h = h0 + (row >> 3), w = w0 + (row & 7);
             const bool valid = h < H;
             TO* yrow = y + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N;
+            // fused BN backward: the BN input of this row is prefetched one chunk ahead (the first chunk
+            // before waiting for the accumulator)
+            const bf16* yin_row = bn_y != nullptr ? bn_y + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N : nullptr;
+            uint4 ynext[4];
+            auto fetch_y = [&](int cc_) {
+                const bf16* p = yin_row + (chalf * CPW + cc_) * 32;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ynext[j] = (valid && cc_ < CPW) ? ld16(p + 8 * j) : make_uint4(0u, 0u, 0u, 0u);
+            };
+            if (bn_y != nullptr) fetch_y(0);
+            mbar_wait(tmem_full + 8 * acc, acc_phase);
+            tc_fence_after();
 #pragma unroll
             for (int cc = 0; cc < CPW; ++cc) {
                 const int c = chalf * CPW + cc;
@@ -233,10 +256,42 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                     if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
                 }
                 float v[32];
+                float q[32];
+                if (bn_y != nullptr) {
+                    // fused "ReLU + BatchNorm backward, reduce pass": this kernel is the dgrad producing
+                    // d(relu(bn(y))); gate it with the ReLU mask recomputed from y and accumulate
+                    // dbeta = sum g and dgamma = sum g * xhat instead of the plain statistics
+                    const int cbase = n_tile * BLOCK_N + c * 32;
+                    uint4 yraw[4];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float f = round_to<TO>(__uint_as_float(r[j]));
-                    v[j] = valid ? f : 0.f;
+                    for (int j = 0; j < 4; ++j) yraw[j] = ynext[j];
+                    fetch_y(cc + 1);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float yv[4];
+                        unpack4<bf16>(yraw[j4 >> 1], j4 & 1, yv);
+                        const float4 sc = *reinterpret_cast<const float4*>(s_bnp + cbase + j4 * 4);
+                        const float4 sh = *reinterpret_cast<const float4*>(s_bnp + 512 + cbase + j4 * 4);
+                        const float4 xs = *reinterpret_cast<const float4*>(s_bnp + 1024 + cbase + j4 * 4);
+                        const float4 xo = *reinterpret_cast<const float4*>(s_bnp + 1536 + cbase + j4 * 4);
+                        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                        const float xsv[4] = {xs.x, xs.y, xs.z, xs.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = j4 * 4 + e;
+                            const bool on = valid && fmaf(yv[e], scv[e], shv[e]) > 0.f;
+                            const float g = on ? round_to<TO>(__uint_as_float(r[j])) : 0.f;
+                            v[j] = g;
+                            q[j] = g * fmaf(yv[e], xsv[e], xov[e]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float f = round_to<TO>(__uint_as_float(r[j]));
+                        v[j] = valid ? f : 0.f;
+                        q[j] = v[j] * v[j];
+                    }
                 }
                 // pack the output first, reduce the statistics (in place on v), store last: the stores then
                 // never hold a read-dependency on registers the shuffle reduction wants to overwrite
@@ -244,9 +299,6 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) pack4<TO>(packed[sizeof(TO) == 2 ? j / 8 : j / 4], (j / 4) & 1, &v[j]);
                 if (stats != nullptr) {
-                    float q[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) q[j] = v[j] * v[j];
                     run_s[cc] += warp_transpose_sum(v, lane);
                     run_q[cc] += warp_transpose_sum(q, lane);
                 }
@@ -267,7 +319,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 
 template <int BLOCK_N, typename TO, bool WRES>
 int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* stats, int B, int H, int W,
-                int Cin, int Cout, cudaStream_t stream) {
+                int Cin, int Cout, const void* bn_y, const float* const* bnp, cudaStream_t stream) {
     constexpr int TPS = BLOCK_N == 256 ? 1 : 3;
     constexpr int B_STAGES = WRES ? 3 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 3 : 5));
     using L = HaloSmem<BLOCK_N, B_STAGES, TPS, WRES>;
@@ -281,7 +333,8 @@ int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* s
     const int total_tiles = B * ((H + TILE_H - 1) / TILE_H) * (W / TILE_W) * (Cout / BLOCK_N);
     const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
     static int dbg = getenv("TAG_HALO_DBG") ? atoi(getenv("TAG_HALO_DBG")) : 0;
-    kern<<<grid, 320, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout, dbg);
+    kern<<<grid, 320, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout, (const bf16*)bn_y, bnp[0], bnp[1],
+                                          bnp[2], bnp[3], dbg);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }
@@ -339,8 +392,12 @@ extern "C" int tag_weight_prep_tapmajor_bf16(const float* w, void* out, int Co, 
 // 3x3 only, no bias / ReLU.  x: bf16 NHWC, W a multiple of 8; w: bf16 TAP-MAJOR [9][Cout][Cin]
 // (tag_weight_prep_tapmajor_bf16); y bf16 or fp32.
 extern "C" int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, double* stats, int B,
-                                    int H, int W, int Cin, int Cout, cudaStream_t stream) {
+                                    int H, int W, int Cin, int Cout, const void* bn_y, const float* bn_scale,
+                                    const float* bn_shift, const float* bn_mean, const float* bn_invstd,
+                                    cudaStream_t stream) {
     if (Cin % 64 != 0 || Cout % 64 != 0 || W % TILE_W != 0 || B <= 0 || H <= 0) return TAG_ERR_BAD_ARG;
+    if (bn_y != nullptr && (Cout > 512 || stats == nullptr)) return TAG_ERR_BAD_ARG;
+    const float* bnp[4] = {bn_scale, bn_shift, bn_mean, bn_invstd};
     const int block_n = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
     CUtensorMap tx, tw;
     int rc = make_act_tmap(&tx, x, B, H, W, Cin, TILE_W, TILE_H + 2);
@@ -348,8 +405,8 @@ extern "C" int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y
     rc = make_w3_tmap(&tw, w, Cout, Cin, block_n, block_n == 256 ? 1 : 3);
     if (rc != TAG_OK) return rc;
 #define TAG_HALO(BN_, WR_)                                                                               \
-    (y_dtype == TAG_DTYPE_BF16 ? launch_halo<BN_, bf16, WR_>(tx, tw, y, stats, B, H, W, Cin, Cout, stream)  \
-                               : launch_halo<BN_, float, WR_>(tx, tw, y, stats, B, H, W, Cin, Cout, stream))
+    (y_dtype == TAG_DTYPE_BF16 ? launch_halo<BN_, bf16, WR_>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, bnp, stream)  \
+                               : launch_halo<BN_, float, WR_>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, bnp, stream))
     const bool wres = Cin == 64 && Cout == block_n && block_n <= 128;
     if (block_n == 256) return TAG_HALO(256, false);
     if (block_n == 128) return wres ? TAG_HALO(128, true) : TAG_HALO(128, false);

@@ -146,10 +146,15 @@ __global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ y, T* __restrict__
             }
         float o[8];
         const long obase = (long)i * 8;
+        float ds[8];
+        if (thresh != 0u) {
+            tag_dropout_scale4(seed, (uint64_t)obase, thresh, keep_scale, ds);
+            tag_dropout_scale4(seed, (uint64_t)obase + 4, thresh, keep_scale, ds + 4);
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             float v = sum[k] * (1.0f / (PH * PW)) + mx[k];
-            if (thresh != 0u) v *= tag_dropout_scale(seed, (uint64_t)(obase + k), thresh, keep_scale);
+            if (thresh != 0u) v *= ds[k];
             o[k] = v;
         }
         store8<T>(out + obase, o);

@@ -94,9 +94,10 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dout, T* 
             float go[4];
             unpack4<T>(raw_g, sub, go);
             if (POOL && thresh != 0u && full) {
+                float ds[4];
+                tag_dropout_scale4(seed, (uint64_t)(oidx + sub * 4), thresh, keep_scale, ds);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    go[k] *= tag_dropout_scale(seed, (uint64_t)(oidx + sub * 4 + k), thresh, keep_scale);
+                for (int k = 0; k < 4; ++k) go[k] *= ds[k];
             }
             float v[NE][4], a[NE][4], m[4];
 #pragma unroll

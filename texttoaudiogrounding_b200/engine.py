@@ -265,12 +265,17 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
                        ops.wgrad_splits(P, cout, cout, 9))
         w2t = ops.prep_weight_t(Wt.conv[2 * blk + 1], cout, cout, 9, dtype, W)
         da1 = torch.empty_like(a1)
-        ops.conv_fwd(dy2, w2t, da1, None, False, None, B, H, W, cout, cout, 9)
+        red1 = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
+        if ops.can_fuse_bn_bwd(w2t, y1):
+            # dgrad with the ReLU gate and the BN-backward reductions of bn1 fused into its epilogue
+            ops.conv_fwd(dy2, w2t, da1, None, False, red1, B, H, W, cout, cout, 9,
+                         bn_fuse=(y1, aux1[0], aux1[1], aux1[2], aux1[3]))
+        else:
+            ops.conv_fwd(dy2, w2t, da1, None, False, None, B, H, W, cout, cout, 9)
+            call("tag_bn_relu_pool_bwd", 0, y1, da1, None, ops.dt(y1), aux1[0], aux1[1], aux1[2], aux1[3], red1,
+                 bn_tr, B, H, W, cout, 0, 0, 0.0, 0, None)
         del dy2
         # bn1 + relu
-        red1 = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
-        call("tag_bn_relu_pool_bwd", 0, y1, da1, None, ops.dt(y1), aux1[0], aux1[1], aux1[2], aux1[3], red1,
-             bn_tr, B, H, W, cout, 0, 0, 0.0, 0, None)
         dg, dbt = G.bn[1 + 2 * blk]
         call("tag_bn_param_grads", red1, cout, dg, dbt)
         dy1 = torch.empty_like(y1)

@@ -52,8 +52,9 @@ def tc_eligible(W: int, Cin: int, Cout: int) -> bool:
     return USE_TC and Cin % 64 == 0 and Cout % 64 == 0 and W in (1, 2, 4, 8, 16, 32, 64)
 
 
-def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps):
-    """Dispatch on the weight dtype: bf16 weights -> tcgen05 kernel, fp32 weights -> SIMT kernel."""
+def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps, bn_fuse=None):
+    """Dispatch on the weight dtype: bf16 weights -> tcgen05 kernel, fp32 weights -> SIMT kernel.
+    ``bn_fuse`` = (bn_y, scale, shift, mean, invstd): fused ReLU+BN backward reduce (halo kernel only)."""
     annotate(f"fwd M={B * H * W} N={Cout} K={taps * Cin}", 2.0 * B * H * W * Cout * taps * Cin)
     if w.dtype == torch.bfloat16:
         if x.dtype != torch.bfloat16 or not tc_eligible(W, Cin, Cout):
@@ -61,11 +62,20 @@ def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps):
         if getattr(w, "_tag_tapmajor", False):
             if taps != 9 or bias is not None or relu or W % 8 != 0:
                 raise _lib.TagError("tap-major weights are only valid for the 3x3 halo kernel")
-            call("tag_conv_tc_fwd_halo", x, w, y, dt(y), stats, B, H, W, Cin, Cout)
-        else:
-            call("tag_conv_tc_fwd", x, w, y, dt(y), bias, int(relu), stats, B, H, W, Cin, Cout, taps)
+            f = bn_fuse or (None, None, None, None, None)
+            call("tag_conv_tc_fwd_halo", x, w, y, dt(y), stats, B, H, W, Cin, Cout, *f)
+            return
+        if bn_fuse is not None:
+            raise _lib.TagError("bn_fuse needs the halo kernel")
+        call("tag_conv_tc_fwd", x, w, y, dt(y), bias, int(relu), stats, B, H, W, Cin, Cout, taps)
     else:
+        if bn_fuse is not None:
+            raise _lib.TagError("bn_fuse needs the halo kernel")
         call("tag_conv_fwd", x, dt(x), w, y, dt(y), bias, int(relu), stats, B, H, W, Cin, Cout, taps)
+
+
+def can_fuse_bn_bwd(w, y) -> bool:
+    return bool(getattr(w, "_tag_tapmajor", False)) and y.dtype == torch.bfloat16
 
 
 def conv_wgrad(dy, x, dw, B, H, W, Cin, Cout, taps, splits, tc=None):
