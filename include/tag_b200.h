@@ -129,7 +129,7 @@ int tag_gru_bwd(const float* d_out, const float* out, const float* gates, const 
 int tag_gru_fwd_bf16(const float* gi, const float* w_hh, const float* b_hh, float* out, float* gates,
                      int B, int T, cudaStream_t stream);
 int tag_gru_bwd_bf16(const float* d_out, const float* out, const float* gates, const float* w_hh,
-                     float* dgi, float* dgh, float* hprev, int B, int T, cudaStream_t stream);
+                     void* dgi, void* dgh, void* hprev, int B, int T, cudaStream_t stream);   /* bf16 outputs */
 
 /* ---- text encoder + match + loss — models/text_encoder.py:39-43,79-88; models/utils.py:33-58;
  * models/match.py:43-60; losses.py:12-24 (host pointers: none) */

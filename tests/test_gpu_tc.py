@@ -149,17 +149,18 @@ def test_bigru_bf16_tensor_core_variant_close_to_oracle(B, T):
     ops.call("tag_gru_fwd_bf16", gi, w_hh, b_hh, out, gates, B, T)
     torch.cuda.synchronize()
     assert (out.cpu() - ref.detach()).abs().max().item() < 1e-2
-    dgi = torch.empty(rows, 1536, device="cuda")
-    dgh = torch.empty(2, rows, 768, device="cuda")
-    hprev = torch.empty(2, rows, 256, device="cuda")
+    bf = dict(device="cuda", dtype=torch.bfloat16)
+    dgi = torch.empty(rows, 1536, **bf)
+    dgh = torch.empty(2, rows, 768, **bf)
+    hprev = torch.empty(2, rows, 256, **bf)
     ops.call("tag_gru_bwd_bf16", d_out.cuda(), out, gates, w_hh, dgi, dgh, hprev, B, T)
-    dx = (dgi @ w_ih).cpu().reshape(B, T, 512)
+    dx = (dgi.float() @ w_ih).cpu().reshape(B, T, 512)
     assert rel_err(dx, x.grad) < 3e-2, rel_err(dx, x.grad)
-    dw = dgh[0].t() @ hprev[0]
+    dw = dgh[0].float().t() @ hprev[0].float()
     assert rel_err(dw.cpu(), ws["weight_hh_l0"].grad) < 3e-2
     # hprev is the state each step consumed: forward direction = out shifted by one step
     hp = hprev[0].reshape(B, T, 256)
-    assert torch.equal(hp[:, 1:], out[:, :-1, :256]) and float(hp[:, 0].abs().max()) == 0.0
+    assert torch.equal(hp[:, 1:], out[:, :-1, :256].bfloat16()) and float(hp[:, 0].float().abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("B,H,W,C", [(2, 21, 16, 128), (3, 9, 64, 64), (2, 17, 8, 512)])

@@ -163,8 +163,8 @@ struct BwdSmem {
 
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(256, 1)
 gru_bwd_tc_kernel(const float* __restrict__ d_out, const float* __restrict__ out, const float* __restrict__ gates,
-                  const float* __restrict__ w_hh, float* __restrict__ dgi, float* __restrict__ dgh_out,
-                  float* __restrict__ hprev_out, int B, int T) {
+                  const float* __restrict__ w_hh, bf16* __restrict__ dgi, bf16* __restrict__ dgh_out,
+                  bf16* __restrict__ hprev_out, int B, int T) {
     __shared__ __align__(16) BwdSmem s;
     cg::cluster_group cluster = cg::this_cluster();
     const int cta = (int)cluster.block_rank();
@@ -228,9 +228,9 @@ gru_bwd_tc_kernel(const float* __restrict__ d_out, const float* __restrict__ out
             g_r = dr_pre; g_z = dz_pre; g_n = dn_pre * r;
             dh_direct = dht * z;
         }
+        const bf16 v_r = __float2bfloat16_rn(g_r), v_z = __float2bfloat16_rn(g_z), v_n = __float2bfloat16_rn(g_n);
         {
             const int o = (cur * BS + bl) * GPAD + jg;
-            const bf16 v_r = __float2bfloat16_rn(g_r), v_z = __float2bfloat16_rn(g_z), v_n = __float2bfloat16_rn(g_n);
 #pragma unroll
             for (int rnk = 0; rnk < NCTA; ++rnk) {
                 peer[rnk][o] = v_r; peer[rnk][o + HID] = v_z; peer[rnk][o + 2 * HID] = v_n;
@@ -239,11 +239,12 @@ gru_bwd_tc_kernel(const float* __restrict__ d_out, const float* __restrict__ out
         auto token = cluster.barrier_arrive();
         if (b_ok) {          // HBM stores after the arrive (see the forward kernel)
             const long bt = (long)bglob * T + t;
-            float* gi_p = dgi + bt * (2 * G3) + dir * G3;
-            gi_p[jg] = g_r; gi_p[HID + jg] = g_z; gi_p[2 * HID + jg] = s_dn;
-            float* gh_p = dgh_out + ((long)dir * B * T + bt) * G3;
-            gh_p[jg] = g_r; gh_p[HID + jg] = g_z; gh_p[2 * HID + jg] = g_n;
-            hprev_out[((long)dir * B * T + bt) * HID + jg] = s_hp;
+            // bf16 outputs: they are operands of the tensor-core weight-gradient / dgrad GEMMs
+            bf16* gi_p = dgi + bt * (2 * G3) + dir * G3;
+            gi_p[jg] = v_r; gi_p[HID + jg] = v_z; gi_p[2 * HID + jg] = __float2bfloat16_rn(s_dn);
+            bf16* gh_p = dgh_out + ((long)dir * B * T + bt) * G3;
+            gh_p[jg] = v_r; gh_p[HID + jg] = v_z; gh_p[2 * HID + jg] = v_n;
+            hprev_out[((long)dir * B * T + bt) * HID + jg] = __float2bfloat16_rn(s_hp);
         }
         fetch(step + 1);
         cluster.barrier_wait(std::move(token));
@@ -286,10 +287,10 @@ extern "C" int tag_gru_fwd_bf16(const float* gi, const float* w_hh, const float*
 }
 
 extern "C" int tag_gru_bwd_bf16(const float* d_out, const float* out, const float* gates, const float* w_hh,
-                                float* dgi, float* dgh, float* hprev, int B, int T, cudaStream_t stream) {
+                                void* dgi, void* dgh, void* hprev, int B, int T, cudaStream_t stream) {
     if (B <= 0 || T <= 0) return TAG_ERR_BAD_ARG;
     dim3 grid(NCTA, (B + BS - 1) / BS, 2);
-    gru_bwd_tc_kernel<<<grid, 256, 0, stream>>>(d_out, out, gates, w_hh, dgi, dgh, hprev, B, T);
+    gru_bwd_tc_kernel<<<grid, 256, 0, stream>>>(d_out, out, gates, w_hh, (bf16*)dgi, (bf16*)dgh, (bf16*)hprev, B, T);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }

@@ -208,18 +208,18 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
     p_fc = P_FC if ctx.dropout else 0.0
 
     # ---- GRU
-    dgi = torch.empty(rows, 1536, **f32)
-    dgh = torch.empty(2, rows, 768, **f32)
-    hprev = torch.empty(2, rows, 256, **f32)
-    gru_bwd = "tag_gru_bwd_bf16" if (dtype == torch.bfloat16 and ops.USE_TC) else "tag_gru_bwd"
-    call(gru_bwd, d_emb, ctx.out, ctx.gates, Wt.w_hh, dgi, dgh, hprev, B, Tp)
-    call("tag_colsum", dgi, ops.F32, rows, 1536, G.b_ih)
+    tc = dtype == torch.bfloat16 and ops.USE_TC
+    gdt = dict(device=dev, dtype=torch.bfloat16 if tc else torch.float32)   # the bf16 GRU emits GEMM operands
+    dgi = torch.empty(rows, 1536, **gdt)
+    dgh = torch.empty(2, rows, 768, **gdt)
+    hprev = torch.empty(2, rows, 256, **gdt)
+    call("tag_gru_bwd_bf16" if tc else "tag_gru_bwd", d_emb, ctx.out, ctx.gates, Wt.w_hh, dgi, dgh, hprev, B, Tp)
+    call("tag_colsum", dgi, ops.dt(dgi), rows, 1536, G.b_ih)
     for d in range(2):
-        call("tag_colsum", dgh[d], ops.F32, rows, 768, G.b_hh[d * 768:(d + 1) * 768])
+        call("tag_colsum", dgh[d], ops.dt(dgh), rows, 768, G.b_hh[d * 768:(d + 1) * 768])
         ops.conv_wgrad(dgh[d], hprev[d], G.w_hh[d], 1, rows, 1, 256, 768, 1,
                        ops.wgrad_splits(rows, 256, 768, 1))
-    tc = dtype == torch.bfloat16 and ops.USE_TC
-    dgi_op = ops.to_bf16(dgi) if tc else dgi
+    dgi_op = dgi
     ops.conv_wgrad(dgi_op, ctx.f, G.w_ih, 1, rows, 1, 512, 1536, 1, ops.wgrad_splits(rows, 512, 1536, 1))
     w_ih_t = ops.prep_weight_t(Wt.w_ih, 1536, 512, 1, dtype)
     df = torch.empty(rows, 512, **f32)
