@@ -153,6 +153,10 @@ int tag_clip_adam(float* p, const float* g, float* m, float* v, long n, const do
                   long long* step_ptr, float grad_mult, float max_norm, float lr, float beta1,
                   float beta2, float eps, float* norm_out, cudaStream_t stream);
 int tag_cast_f32_to_bf16(const float* x, void* y, long n, cudaStream_t stream);
+/* all bf16 GEMM operands of one step from the fp32 master weights in one launch; `table` (device) holds
+ * 5 int64 per entry: src, dst, rows<<32|cols, taps<<32|mode, first block (2048 elements per block);
+ * modes: 0 cast, 1 tap-major fwd, 2 tap-major dgrad (flip + transpose), 3 transpose. */
+int tag_weight_prep_batch(const long long* table, int n_entries, int total_blocks, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

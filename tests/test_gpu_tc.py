@@ -186,3 +186,23 @@ def test_halo_dgrad_with_fused_bn_relu_backward_reduce(B, H, W, C):
     mask = (y1.float() * aux[0] + aux[1]) > 0
     assert torch.equal(g_f.float(), torch.where(mask, da.float(), torch.zeros_like(da.float())))
     np.testing.assert_allclose(red.cpu().numpy(), red_ref.cpu().numpy(), rtol=2e-3, atol=2e-2)
+
+
+def test_batched_weight_prep_equals_single_kernels():
+    """tag_weight_prep_batch (one launch for all operands) == the per-weight prep kernels, bit for bit."""
+    from texttoaudiogrounding_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    wp = ops.WeightPrep("cuda")
+    cases = []
+    for co, ci in [(64, 64), (128, 64), (256, 128)]:
+        w = torch.randn(co, 3, 3, ci, generator=gen).cuda()
+        cases.append((wp.add(w, 1, co, ci, 9), ops.prep_weight(w, torch.bfloat16, 8)))
+        cases.append((wp.add(w, 2, co, ci, 9), ops.prep_weight_t(w, co, ci, 9, torch.bfloat16, 8)))
+    lin = torch.randn(192, 320, generator=gen).cuda()
+    cases.append((wp.add(lin, 0, 192, 320, 1), ops.to_bf16(lin).view(-1)))
+    cases.append((wp.add(lin, 3, 192, 320, 1), ops.prep_weight_t(lin, 192, 320, 1, torch.bfloat16)))
+    for got, _ in cases:
+        got.zero_()
+    wp.run()
+    for i, (got, ref) in enumerate(cases):
+        assert torch.equal(got.view(-1), ref.view(-1)), i

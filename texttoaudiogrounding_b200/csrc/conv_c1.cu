@@ -123,22 +123,32 @@ conv_c1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const floa
     // the wgrad-only instantiation skips the halo rows; loads are software-pipelined one pass ahead
     constexpr int IT0 = DGRAD ? 0 : TW / 32;
     constexpr int IT1 = DGRAD ? (TH + 2) * TW / 32 : (TH + 1) * TW / 32;
-    auto fetch = [&](int it, float* gg) {
+    // dy is prefetched PF passes ahead as raw 16-byte vectors: with one 16-byte load in flight per thread
+    // the kernel was latency-bound at ~1 TB/s
+    constexpr int PF = 4;
+    constexpr int RAWN = (int)sizeof(T) * 8 / 16;          // uint4 per 8 channels (1 for bf16, 2 for fp32)
+    uint4 ring[PF][RAWN];
+    auto fetch = [&](int it, uint4* raw) {
         const int pix = it * 32 + pl;
         const int r = pix / TW, c0 = pix - r * TW;
         const int h = h0 - 1 + r;
-        if (it < IT1 && h >= 0 && h < H) {
-            load8<T>(dy + (((long)b * H + h) * W + c0) * CO + cg * 8, gg);
-        } else {
+        const bool ok = it < IT1 && h >= 0 && h < H;
+        const T* src = dy + (((long)b * H + h) * W + c0) * CO + cg * 8;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) gg[c] = 0.f;
-        }
+        for (int j = 0; j < RAWN; ++j) raw[j] = ok ? ld16(reinterpret_cast<const uint8_t*>(src) + 16 * j) : make_uint4(0u, 0u, 0u, 0u);
     };
-    float g[8], gn[8];
-    fetch(IT0, g);
+#pragma unroll
+    for (int i = 0; i < PF; ++i) fetch(IT0 + i, ring[i]);
 #pragma unroll 1
-    for (int it = IT0; it < IT1; ++it) {
-        fetch(it + 1, gn);
+    for (int it0 = IT0; it0 < IT1; it0 += PF) {
+#pragma unroll
+    for (int ii = 0; ii < PF; ++ii) {
+        const int it = it0 + ii;
+        float g[8];
+        if (RAWN == 1) { unpack4<T>(ring[ii][0], 0, g); unpack4<T>(ring[ii][0], 1, g + 4); }
+        else { unpack4<T>(ring[ii][0], 0, g); unpack4<T>(ring[ii][RAWN - 1], 0, g + 4); }
+        fetch(it + PF, ring[ii]);
+        if (it >= IT1) continue;
         const int pix = it * 32 + pl;
         const int r = pix / TW, c0 = pix - r * TW;
         const int h = h0 - 1 + r;
@@ -174,8 +184,7 @@ conv_c1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const floa
 #pragma unroll
                 for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], xn[t], acc[c][t]);
         }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) g[c] = gn[c];
+    }
     }
     // ---- wgrad: reduce the per-thread accumulators (lanes with equal cg, then across warps)
     if (WGRAD) {

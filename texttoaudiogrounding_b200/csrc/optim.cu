@@ -94,3 +94,53 @@ extern "C" int tag_cast_f32_to_bf16(const float* x, void* y, long n, cudaStream_
 }
 
 extern "C" int tag_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------------------------
+// Batched weight preparation: every bf16 GEMM operand of a step (plain casts, tap-major conv
+// operands, flipped+transposed dgrad operands) from the fp32 master weights in ONE launch.
+// Table entry (5 x int64): src, dst, (rows << 32 | cols), (taps << 32 | mode), first block.
+//   mode 0: dst[i] = bf16(src[i])                                   (n = rows * cols * taps)
+//   mode 1: tap-major forward   dst[tp][co][ci] = src[co][tap][ci]  (rows = Co, cols = Ci)
+//   mode 2: tap-major dgrad     dst[tp][ci][co] = src[co][8-tap][ci]
+//   mode 3: transpose (taps=1)  dst[ci][co]     = src[co][ci]
+// with tap' = dwi*3 + dhi, tap = dhi*3 + dwi.
+namespace {
+constexpr int PREP_ELEMS_PER_BLOCK = 2048;
+
+__global__ void weight_prep_batch_kernel(const long long* __restrict__ table, int n_entries) {
+    int e = 0;
+    while (e + 1 < n_entries && (long long)blockIdx.x >= table[(e + 1) * 5 + 4]) ++e;
+    const float* src = reinterpret_cast<const float*>(table[e * 5 + 0]);
+    bf16* dst = reinterpret_cast<bf16*>(table[e * 5 + 1]);
+    const int Co = (int)(table[e * 5 + 2] >> 32), Ci = (int)(table[e * 5 + 2] & 0xFFFFFFFF);
+    const int taps = (int)(table[e * 5 + 3] >> 32), mode = (int)(table[e * 5 + 3] & 0xFFFFFFFF);
+    const long n = (long)Co * Ci * taps;
+    const long base = ((long)blockIdx.x - table[e * 5 + 4]) * PREP_ELEMS_PER_BLOCK;
+    for (long i = base + threadIdx.x; i < base + PREP_ELEMS_PER_BLOCK && i < n; i += blockDim.x) {
+        float v;
+        if (mode == 0) {
+            v = src[i];
+        } else if (mode == 1) {            // i -> [tp][co][ci]
+            const int ci = (int)(i % Ci); const long r = i / Ci;
+            const int co = (int)(r % Co); const int tp = (int)(r / Co);
+            v = src[((long)co * 9 + ((tp % 3) * 3 + tp / 3)) * Ci + ci];
+        } else if (mode == 2) {            // i -> [tp][ci][co]
+            const int co = (int)(i % Co); const long r = i / Co;
+            const int ci = (int)(r % Ci); const int tp = (int)(r / Ci);
+            v = src[((long)co * 9 + (8 - ((tp % 3) * 3 + tp / 3))) * Ci + ci];
+        } else {                           // i -> [ci][co]
+            const int co = (int)(i % Co); const int ci = (int)(i / Co);
+            v = src[(long)co * Ci + ci];
+        }
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+}  // namespace
+
+extern "C" int tag_weight_prep_batch(const long long* table, int n_entries, int total_blocks,
+                                     cudaStream_t stream) {
+    if (n_entries <= 0 || total_blocks <= 0) return TAG_ERR_BAD_ARG;
+    weight_prep_batch_kernel<<<total_blocks, 256, 0, stream>>>(table, n_entries);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}

@@ -43,6 +43,9 @@ class EncoderWeights:
     b_ih: torch.Tensor
     w_hh: torch.Tensor
     b_hh: torch.Tensor
+    # optional map of ready-made GEMM operands (FusedTrainStep refreshes them with ONE batched launch per
+    # step): ("f", i) / ("t", i) forward / dgrad operand of conv i, "fc", "ih", "fc_t", "ih_t"
+    prepared: Optional[dict] = None
 
 
 @dataclass
@@ -81,6 +84,12 @@ class EncoderCtx:
 
 def _seed_for(seed: int, layer: int) -> int:
     return (seed * 1000003 + layer * 7919 + 12345) & 0xFFFFFFFFFFFFFFFF
+
+
+def _operand(Wt: EncoderWeights, key, make):
+    if Wt.prepared is not None and key in Wt.prepared:
+        return Wt.prepared[key]
+    return make()
 
 
 def compute_mel_range(fb: torch.Tensor) -> torch.Tensor:
@@ -146,7 +155,7 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
         if cin == 1:
             call("tag_conv_c1_fwd", x, Wt.conv[0], y1, ops.dt(y1), st1, B, H, W)
         else:
-            ops.conv_fwd(x, ops.prep_weight(Wt.conv[2 * blk], dtype, W), y1, None, False, st1, B, H, W, cin, cout, 9)
+            ops.conv_fwd(x, _operand(Wt, ("f", 2 * blk), lambda: ops.prep_weight(Wt.conv[2 * blk], dtype, W)), y1, None, False, st1, B, H, W, cin, cout, 9)
         aux1 = bn_aux(cout)
         finalize(st1, count, cout, 1 + 2 * blk, aux1)
         a1 = torch.empty(B, H, W, cout, **act)
@@ -154,7 +163,7 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
         # conv2
         y2 = torch.empty(B, H, W, cout, **act)
         st2 = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if bn_training else None
-        ops.conv_fwd(a1, ops.prep_weight(Wt.conv[2 * blk + 1], dtype, W), y2, None, False, st2, B, H, W, cout, cout, 9)
+        ops.conv_fwd(a1, _operand(Wt, ("f", 2 * blk + 1), lambda: ops.prep_weight(Wt.conv[2 * blk + 1], dtype, W)), y2, None, False, st2, B, H, W, cout, cout, 9)
         aux2 = bn_aux(cout)
         finalize(st2, count, cout, 2 + 2 * blk, aux2)
         # bn2 + relu + pool + dropout
@@ -180,9 +189,9 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
     call("tag_freq_mean_fwd", x, m, ops.dt(m), rows, Wf, C, P_FC if use_dropout else 0.0,
          _seed_for(seed, 4), seed_dev)
     f = torch.empty(rows, 512, **act)
-    ops.conv_fwd(m, ops.prep_weight(Wt.fc_w, dtype), f, Wt.fc_b, True, None, 1, rows, 1, C, 512, 1)
+    ops.conv_fwd(m, _operand(Wt, "fc", lambda: ops.prep_weight(Wt.fc_w, dtype)), f, Wt.fc_b, True, None, 1, rows, 1, C, 512, 1)
     gi = torch.empty(rows, 1536, **f32)
-    ops.conv_fwd(f, ops.prep_weight(Wt.w_ih, dtype), gi, Wt.b_ih, False, None, 1, rows, 1, 512, 1536, 1)
+    ops.conv_fwd(f, _operand(Wt, "ih", lambda: ops.prep_weight(Wt.w_ih, dtype)), gi, Wt.b_ih, False, None, 1, rows, 1, 512, 1536, 1)
     out = torch.empty(B, Tp, 512, **f32)
     gates = torch.empty(B, Tp, 2, 4, 256, **f32) if save else None
     gru_fwd = "tag_gru_fwd_bf16" if (dtype == torch.bfloat16 and ops.USE_TC) else "tag_gru_fwd"
@@ -221,7 +230,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
                        ops.wgrad_splits(rows, 256, 768, 1))
     dgi_op = dgi
     ops.conv_wgrad(dgi_op, ctx.f, G.w_ih, 1, rows, 1, 512, 1536, 1, ops.wgrad_splits(rows, 512, 1536, 1))
-    w_ih_t = ops.prep_weight_t(Wt.w_ih, 1536, 512, 1, dtype)
+    w_ih_t = _operand(Wt, "ih_t", lambda: ops.prep_weight_t(Wt.w_ih, 1536, 512, 1, dtype))
     df = torch.empty(rows, 512, **f32)
     ops.conv_fwd(dgi_op, w_ih_t, df, None, False, None, 1, rows, 1, 1536, 512, 1)
 
@@ -230,7 +239,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
     call("tag_relu_bwd", df, ops.F32, ctx.f, ops.dt(ctx.f), dpre, ops.dt(dpre), df.numel())
     call("tag_colsum", dpre, ops.dt(dpre), rows, 512, G.fc_b)
     ops.conv_wgrad(dpre, ctx.m, G.fc_w, 1, rows, 1, 512, 512, 1, ops.wgrad_splits(rows, 512, 512, 1))
-    fc_t = ops.prep_weight_t(Wt.fc_w, 512, 512, 1, dtype)
+    fc_t = _operand(Wt, "fc_t", lambda: ops.prep_weight_t(Wt.fc_w, 512, 512, 1, dtype))
     dm = torch.empty(rows, 512, **act)
     ops.conv_fwd(dpre, fc_t, dm, None, False, None, 1, rows, 1, 512, 512, 1)
 
@@ -263,7 +272,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         # conv2
         ops.conv_wgrad(dy2, a1, G.conv[2 * blk + 1], B, H, W, cout, cout, 9,
                        ops.wgrad_splits(P, cout, cout, 9))
-        w2t = ops.prep_weight_t(Wt.conv[2 * blk + 1], cout, cout, 9, dtype, W)
+        w2t = _operand(Wt, ("t", 2 * blk + 1), lambda: ops.prep_weight_t(Wt.conv[2 * blk + 1], cout, cout, 9, dtype, W))
         da1 = torch.empty_like(a1)
         red1 = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
         if ops.can_fuse_bn_bwd(w2t, y1):
@@ -295,7 +304,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
             x_in = ctx.p[blk - 1]
             ops.conv_wgrad(dy1, x_in, G.conv[2 * blk], B, H, W, cin, cout, 9,
                            ops.wgrad_splits(P, cin, cout, 9))
-            w1t = ops.prep_weight_t(Wt.conv[2 * blk], cout, cin, 9, dtype, W)
+            w1t = _operand(Wt, ("t", 2 * blk), lambda: ops.prep_weight_t(Wt.conv[2 * blk], cout, cin, 9, dtype, W))
             dp = torch.empty_like(x_in)
             ops.conv_fwd(dy1, w1t, dp, None, False, None, B, H, W, cout, cin, 9)
         del dy1

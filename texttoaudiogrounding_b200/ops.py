@@ -136,6 +136,40 @@ def prep_weight_t(w: torch.Tensor, Co: int, Ci: int, taps: int, dtype: torch.dty
     return wt
 
 
+class WeightPrep:
+    """Persistent bf16 operand buffers for a fixed set of fp32 master weights + one batched prep launch.
+    ``add(src, mode, rows, cols, taps)`` registers an operand and returns its bf16 tensor;
+    ``run()`` refreshes all of them (modes: 0 cast, 1 tap-major fwd, 2 tap-major dgrad, 3 transpose)."""
+    ELEMS = 2048
+
+    def __init__(self, device):
+        self.device = device
+        self.entries = []
+        self.table = None
+        self.blocks = 0
+
+    def add(self, src: torch.Tensor, mode: int, rows: int, cols: int, taps: int) -> torch.Tensor:
+        dst = torch.empty(src.numel(), device=self.device, dtype=torch.bfloat16)
+        if mode in (1, 2):
+            dst._tag_tapmajor = True
+        self.entries.append((src, dst, mode, rows, cols, taps))
+        self.table = None
+        return dst
+
+    def key(self):
+        return tuple(e[0].data_ptr() for e in self.entries)
+
+    def run(self):
+        if self.table is None:
+            rows, blk = [], 0
+            for src, dst, mode, r, c, t in self.entries:
+                rows.append([src.data_ptr(), dst.data_ptr(), (r << 32) | c, (t << 32) | mode, blk])
+                blk += (src.numel() + self.ELEMS - 1) // self.ELEMS
+            self.table = torch.tensor(rows, dtype=torch.int64).to(self.device)
+            self.blocks = blk
+        call("tag_weight_prep_batch", self.table, len(self.entries), self.blocks)
+
+
 def to_bf16(x: torch.Tensor) -> torch.Tensor:
     y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     call("tag_cast_f32_to_bf16", x, y, x.numel())

@@ -121,6 +121,21 @@ class FusedTrainStep:
         self.Wt = self.enc._weights()
         assert self.Wt.w_ih.data_ptr() == self.enc.rnn.weight_ih_l0.data_ptr()
         self.G = self._grad_bundle()
+        self.prep = None
+        if self.enc.compute_dtype == torch.bfloat16 and ops.USE_TC and ops.USE_HALO:
+            # every bf16 GEMM operand of the step is regenerated from the fp32 masters by one launch
+            wp = ops.WeightPrep(dev)
+            prepared = {}
+            for i in range(1, 8):
+                co, ci = engine.CHANNELS[i // 2][1], (engine.CHANNELS[i // 2][0] if i % 2 == 0 else engine.CHANNELS[i // 2][1])
+                prepared[("f", i)] = wp.add(self.Wt.conv[i], 1, co, ci, 9)
+                prepared[("t", i)] = wp.add(self.Wt.conv[i], 2, co, ci, 9)
+            prepared["fc"] = wp.add(self.Wt.fc_w, 0, 512, 512, 1).view(512, 512)
+            prepared["ih"] = wp.add(self.Wt.w_ih, 0, 1536, 512, 1).view(1536, 512)
+            prepared["fc_t"] = wp.add(self.Wt.fc_w, 3, 512, 512, 1)
+            prepared["ih_t"] = wp.add(self.Wt.w_ih, 3, 1536, 512, 1)
+            self.Wt.prepared = prepared
+            self.prep = wp
 
     def _grad_bundle(self) -> engine.EncoderGrads:
         enc = self.enc
@@ -140,6 +155,8 @@ class FusedTrainStep:
         """Forward + backward into flat_g; returns nothing (loss in self.loss_out)."""
         enc = self.enc
         self.flat_g.zero_()
+        if self.prep is not None:
+            self.prep.run()
         emb, ectx = engine.encoder_forward(
             self.Wt, wav, training=True, bn_training=enc.bn0.training, dropout=enc.dropout_enabled,
             seed=self.base_seed, dtype=enc.compute_dtype, save=True, seed_dev=self.step_dev)
