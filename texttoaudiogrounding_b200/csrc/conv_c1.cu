@@ -12,6 +12,8 @@
 
 namespace {
 
+__device__ __forceinline__ uint32_t smem_u32_c1(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 constexpr int CO = 64;
 constexpr int TH = 8;            // tile rows
 constexpr int TW = 64;           // tile width == W
@@ -219,6 +221,194 @@ conv_c1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const floa
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// bf16 backward on mma.sync (m16n8k16): both halves of the Cin = 1 backward are thin GEMMs over dy,
+//   S[p][tap]    = sum_co dy[p][co] * w[co][tap]        (M = 16 pixels, N = 9 -> 16 taps, K = 64 channels)
+//   dw^T[tap][co] = sum_p xcol[p][tap] * dy[p][co]       (M = 9 -> 16 taps, N = 64 channels, K = 16 pixels)
+// which the CUDA-core version above spends ~200 instructions per 4 pixels on.  Here a warp streams units of
+// 16 consecutive pixels x 64 channels (2 KB) through a private cp.async ring in shared memory (XOR-swizzled
+// 16-byte chunks); `ldmatrix` of a unit yields the A fragments of the first product and `ldmatrix.trans` of the
+// SAME addresses the B fragments of the second, so dy is read from HBM once and never touches the register
+// file as scalars.  dx[p] = sum_tap S[p - d(tap)][tap] is then assembled from the S tile (halo rows recomputed).
+constexpr int MTH = 16;                       // tile rows
+constexpr int MROWS = MTH + 2;
+constexpr int MNST = 3;                       // cp.async stages per warp
+constexpr int MXS_W = 68;                     // bf16 halo row: 66 used
+constexpr int MMA_SMEM = 8 * MNST * 2048 + MROWS * 64 * 9 * 4 + MROWS * MXS_W * 2 + CO * 9 * 4;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(256, 2)
+conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ w,
+                       float* __restrict__ dw, float* __restrict__ dx, int B, int H) {
+    extern __shared__ __align__(128) uint8_t msm[];
+    uint8_t* stage = msm;                                                     // [8 warps][MNST][2048]
+    float* S = reinterpret_cast<float*>(msm + 8 * MNST * 2048);               // [MROWS][64][9]
+    uint16_t* xs = reinterpret_cast<uint16_t*>(S + MROWS * 64 * 9);           // [MROWS][MXS_W] bf16 bits
+    float* s_dw = reinterpret_cast<float*>(xs + MROWS * MXS_W);               // [64][9]
+    const int tiles_h = (H + MTH - 1) / MTH;
+    const int b = blockIdx.x / tiles_h, h0 = (blockIdx.x % tiles_h) * MTH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int W = TW;
+
+    for (int i = threadIdx.x; i < CO * 9; i += 256) s_dw[i] = 0.f;
+    for (int i = threadIdx.x; i < MROWS * MXS_W; i += 256) {
+        const int r = i / MXS_W, c = i - r * MXS_W;
+        const int h = h0 - 1 + r, wc = c - 1;
+        uint16_t v = 0;
+        if (c < 66 && h >= 0 && h < H && wc >= 0 && wc < W)
+            v = reinterpret_cast<const uint16_t*>(x)[((long)b * H + h) * W + wc];
+        xs[i] = v;
+    }
+    // B fragments of the dgrad product: w[co][tap] as bf16, k = co, n = tap (second n-tile: tap 8 only)
+    uint32_t wb[4][2][2];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int co = ks * 16 + hf * 8 + 2 * t;
+            wb[ks][0][hf] = pack2(w[co * 9 + g], w[(co + 1) * 9 + g]);
+            wb[ks][1][hf] = g == 0 ? pack2(w[co * 9 + 8], w[(co + 1) * 9 + 8]) : 0u;
+        }
+    float acc[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[n][k] = 0.f;
+    __syncthreads();
+
+    const uint32_t my_stage = smem_u32_c1(stage + warp * MNST * 2048);
+    constexpr int NUNITS = MROWS * 4;                     // units of 16 pixels
+    constexpr int PER_WARP = (NUNITS + 7) / 8;
+    auto unit_row_ok = [&](int u, int& r, int& c0) {
+        r = u >> 2; c0 = (u & 3) * 16;
+        const int h = h0 - 1 + r;
+        return u < NUNITS && h >= 0 && h < H;
+    };
+    auto issue = [&](int i) {
+        int r, c0;
+        const int u = warp + 8 * i;
+        if (i < PER_WARP && unit_row_ok(u, r, c0)) {
+            const bf16* src = dy + (((long)b * H + (h0 - 1 + r)) * W + c0) * CO;
+            const uint32_t dst = my_stage + (i % MNST) * 2048;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = j * 32 + lane;
+                const int px = idx >> 3, ch = idx & 7;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + px * 128 + ((ch ^ (px & 7)) << 4)),
+                             "l"(src + px * CO + ch * 8) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int i = 0; i < MNST - 1; ++i) issue(i);
+    // ldmatrix lane address inside a unit: row = (lane & 7) + 8 * ((lane >> 3) & 1), 16-byte chunk = 2 * q + (lane >> 4)
+    const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int lchk = lane >> 4;
+#pragma unroll 1
+    for (int i = 0; i < PER_WARP; ++i) {
+        issue(i + MNST - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(MNST - 1) : "memory");
+        __syncwarp();
+        int r, c0;
+        const int u = warp + 8 * i;
+        if (u >= NUNITS) break;
+        const bool ok = unit_row_ok(u, r, c0);
+        float* Srow = S + ((r * 64) + c0) * 9;
+        if (!ok) {
+            for (int k = lane; k < 16 * 9; k += 32) Srow[k] = 0.f;
+            continue;
+        }
+        const uint32_t sbase = my_stage + (i % MNST) * 2048 + lrow * 128;
+        uint32_t a[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ldsm_x4(a[q], sbase + (((2 * q + lchk) ^ (lrow & 7)) << 4));
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            mma16816(s0, a[q], wb[q][0][0], wb[q][0][1]);
+            mma16816(s1, a[q], wb[q][1][0], wb[q][1][1]);
+        }
+        Srow[g * 9 + 2 * t] = s0[0];
+        Srow[g * 9 + 2 * t + 1] = s0[1];
+        Srow[(g + 8) * 9 + 2 * t] = s0[2];
+        Srow[(g + 8) * 9 + 2 * t + 1] = s0[3];
+        if (t == 0) { Srow[g * 9 + 8] = s1[0]; Srow[(g + 8) * 9 + 8] = s1[2]; }
+        if (r >= 1 && r <= MTH) {
+            // A fragments of the wgrad product: rows = taps, k = the unit's 16 pixels; x[h + dh][c + dw] from the halo tile
+            uint32_t ax[4];
+            {
+                const int dh = g / 3, dwv = g - dh * 3;                       // tap g (g <= 7): xs row r - 1 + dh, col c + dwv
+                const uint16_t* xr = xs + (r - 1 + dh) * MXS_W + c0 + dwv + 2 * t;
+                ax[0] = (uint32_t)xr[0] | ((uint32_t)xr[1] << 16);
+                ax[2] = (uint32_t)xr[8] | ((uint32_t)xr[9] << 16);
+                const uint16_t* x8 = xs + (r + 1) * MXS_W + c0 + 2 + 2 * t;  // tap 8 = (dh, dw) = (+1, +1)
+                ax[1] = g == 0 ? ((uint32_t)x8[0] | ((uint32_t)x8[1] << 16)) : 0u;
+                ax[3] = g == 0 ? ((uint32_t)x8[8] | ((uint32_t)x8[9] << 16)) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t bt[4];
+                ldsm_x4_trans(bt, sbase + (((2 * q + lchk) ^ (lrow & 7)) << 4));
+                mma16816(acc[2 * q], ax, bt[0], bt[1]);
+                mma16816(acc[2 * q + 1], ax, bt[2], bt[3]);
+            }
+        }
+        __syncwarp();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // ---- wgrad: acc[n][0..1] = (tap g, co 8n + 2t, +1), acc[n][2..3] = (tap 8 when g == 0)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        const int co = n * 8 + 2 * t;
+        atomicAdd(&s_dw[co * 9 + g], acc[n][0]);
+        atomicAdd(&s_dw[(co + 1) * 9 + g], acc[n][1]);
+        if (g == 0) {
+            atomicAdd(&s_dw[co * 9 + 8], acc[n][2]);
+            atomicAdd(&s_dw[(co + 1) * 9 + 8], acc[n][3]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CO * 9; i += 256) atomicAdd(dw + i, s_dw[i]);
+    // ---- dx[p] = sum_tap S[p - d(tap)][tap]
+    if (dx != nullptr) {
+        for (int pix = threadIdx.x; pix < MTH * W; pix += 256) {
+            const int r = pix / W, c = pix - r * W;
+            const int h = h0 + r;
+            if (h >= H) break;
+            float v = 0.f;
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp) {
+                const int dh = tp / 3 - 1, dwv = tp % 3 - 1;
+                const int cc = c - dwv;
+                if (cc >= 0 && cc < W) v += S[(((r + 1 - dh) * 64) + cc) * 9 + tp];
+            }
+            dx[((long)b * H + h) * W + c] = v;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int tag_conv_c1_fwd(const void* x, const float* w, void* y, int dtype, double* stats, int B,
@@ -242,9 +432,14 @@ extern "C" int tag_conv_c1_bwd(const void* dy, const void* x, const float* w, in
         if (dx != nullptr)
             conv_c1_bwd_kernel<float, false, true><<<blocks, 256, 0, stream>>>((const float*)dy, (const float*)x, w, dw, dx, B, H, W);
     } else {
-        conv_c1_bwd_kernel<bf16, true, false><<<blocks, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, w, dw, dx, B, H, W);
-        if (dx != nullptr)
-            conv_c1_bwd_kernel<bf16, false, true><<<blocks, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, w, dw, dx, B, H, W);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(conv_c1_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MMA_SMEM);
+            if (e != cudaSuccess) return (int)e;
+            attr_set = true;
+        }
+        const int mblocks = B * ((H + MTH - 1) / MTH);
+        conv_c1_bwd_mma_kernel<<<mblocks, 256, MMA_SMEM, stream>>>((const bf16*)dy, (const bf16*)x, w, dw, dx, B, H);
     }
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;

@@ -40,7 +40,7 @@ struct HaloSmem {
 // WRES (Cin == 64, Cout == BLOCK_N <= 128): the whole 9-tap weight tensor (<= 144 KB) is loaded ONCE
 // per CTA into the three weight stages and stays resident; only the input boxes stream.
 template <int BLOCK_N, typename TO, int B_STAGES, int TPS, bool WRES>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W, int Cin, int Cout,
                         const bf16* __restrict__ bn_y, const float* __restrict__ bn_scale,
@@ -48,6 +48,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                         const float* __restrict__ bn_invstd, int dbg) {
     using L = HaloSmem<BLOCK_N, B_STAGES, TPS, WRES>;
     constexpr int A_STAGES = L::A_STAGES;
+    constexpr bool TWO_ISSUERS = WRES && BLOCK_N == 64 && A_STAGES == 6;      // see the MMA issuer section
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -97,6 +98,8 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // 12 warps = 3 warpgroups: the two epilogue warpgroups take the registers the producer / MMA / idle warps
+    // (warpgroup 2) do not need — the epilogue keeps 64 running statistics per thread on top of a 32-column chunk
 
     auto decode = [&](int tile, int& n_tile, int& b, int& h0, int& w0) {
         n_tile = tile / m_tiles;
@@ -108,6 +111,8 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         w0 = (m_tile - th * tiles_w) * TILE_W;
     };
 
+    if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 8) {
         // ===================== TMA producer =====================
         if (elect_one_sync()) {
@@ -139,14 +144,26 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                 }
             }
         }
-    } else if (warp == 9) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 9 || (TWO_ISSUERS && warp == 10)) {
+        // ===================== MMA issuer(s) =====================
+        // At BLOCK_N = 64 an MMA occupies the tensor pipe for 32 cycles, less than one warp needs to build the
+        // descriptors and issue it (~65 cycles measured): a single issuer left the pipe 60 % idle.  The weights-resident
+        // BLOCK_N = 64 variant therefore runs TWO issuing warps, one per TMEM accumulator: warp 9 takes the even tiles
+        // of this CTA, warp 10 the odd ones.  This is only sound because there A_STAGES == 2 * (boxes per tile): each
+        // warp owns a fixed half of the input ring, so it never waits on a barrier whose previous phase belongs to
+        // the other warp (mbarrier parity waits cannot tell phases two apart).
         constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 0, 0);
-        int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        constexpr int NI = TWO_ISSUERS ? 2 : 1;
+        const int mw = warp - 9;
+        const uint32_t a_per_tile = (uint32_t)KC * 3u;
+        const uint32_t b_per_tile = a_per_tile * (3 / TPS);
+        int it = mw;
+        for (int tile = blockIdx.x + mw * gridDim.x; tile < total_tiles; tile += NI * gridDim.x, it += NI) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
+            const uint32_t na = (uint32_t)it * a_per_tile, nb = (uint32_t)it * b_per_tile;
+            int as = (int)(na % A_STAGES), bs = (int)(nb % B_STAGES);
+            uint32_t aph = (na / A_STAGES) & 1u, bph = (nb / B_STAGES) & 1u;
             mbar_wait(tmem_empty + 8 * acc, acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -182,24 +199,39 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                 }
             }
         }
+    }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         // ===================== epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., column half w/4
         int it = 0;
         int cur_n_tile = -1;
         constexpr int CPW = BLOCK_N / 64;            // 32-column chunks per warp
-        // running per-channel sums live in registers (lane l owns column l of each of the warp's chunks); shared-memory
-        // float atomics are CAS loops and were the epilogue bottleneck of the small-K layers
-        float run_s[CPW], run_q[CPW];
+        // Per-channel statistics: a thread owns one pixel row of the tile (its TMEM lane) and 32 columns per chunk.
+        // Reducing over the 32 rows of every tile costs a 31-shuffle butterfly per chunk and quantity — that, not the
+        // MMAs, paced the narrow layers.  Instead the butterfly is cut after STAGES stages (none for BLOCK_N = 64) and
+        // the partial sums (64 registers in total) keep accumulating across tiles; the remaining stages run once per
+        // flush.  The lane -> column mapping of a butterfly stage is fixed, so accumulating in between is exact.
+        constexpr int STAGES = CPW == 1 ? 0 : (CPW == 2 ? 1 : 2);
+        constexpr int KEEP = 32 >> STAGES;
+        float run_s[CPW][KEEP], run_q[CPW][KEEP];
 #pragma unroll
-        for (int i = 0; i < CPW; ++i) { run_s[i] = 0.f; run_q[i] = 0.f; }
+        for (int i = 0; i < CPW; ++i)
+#pragma unroll
+            for (int k = 0; k < KEEP; ++k) { run_s[i][k] = 0.f; run_q[i][k] = 0.f; }
         auto flush_stats = [&](int n_tile) {
+            float fs[CPW], fq[CPW];
+#pragma unroll
+            for (int i = 0; i < CPW; ++i) {
+                fs[i] = warp_transpose_tail<KEEP>(run_s[i], lane);
+                fq[i] = warp_transpose_tail<KEEP>(run_q[i], lane);
+#pragma unroll
+                for (int k = 0; k < KEEP; ++k) { run_s[i][k] = 0.f; run_q[i][k] = 0.f; }
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
             for (int i = 0; i < CPW; ++i) {
-                t_buf[warp * BLOCK_N + i * 32 + lane] = run_s[i];
-                t_buf[warp * BLOCK_N + BLOCK_N / 2 + i * 32 + lane] = run_q[i];
-                run_s[i] = 0.f;
-                run_q[i] = 0.f;
+                t_buf[warp * BLOCK_N + i * 32 + lane] = fs[i];
+                t_buf[warp * BLOCK_N + BLOCK_N / 2 + i * 32 + lane] = fq[i];
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             for (int i = threadIdx.x; i < BLOCK_N; i += 256) {
@@ -226,6 +258,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             const int row = lq * 32 + lane;
             const int h = h0 + (row >> 3), w = w0 + (row & 7);
             const bool valid = h < H;
+            const bool edge_tile = h0 + TILE_H > H;          // tile-uniform: some rows fall off the image
             TO* yrow = y + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N;
             // fused BN backward: the BN input of this row is prefetched one chunk ahead (the first chunk
             // before waiting for the accumulator)
@@ -255,9 +288,10 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
                 }
-                float v[32];
-                float q[32];
-                if (bn_y != nullptr) {
+                float v[32];                             // the values as stored (rounded to TO, gated)
+                float q[32];                             // second statistic's factor: v (plain) or xhat (fused BN bwd)
+                const bool fused = bn_y != nullptr;
+                if (fused) {
                     // fused "ReLU + BatchNorm backward, reduce pass": this kernel is the dgrad producing
                     // d(relu(bn(y))); gate it with the ReLU mask recomputed from y and accumulate
                     // dbeta = sum g and dgamma = sum g * xhat instead of the plain statistics
@@ -279,28 +313,50 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int j = j4 * 4 + e;
-                            const bool on = valid && fmaf(yv[e], scv[e], shv[e]) > 0.f;
-                            const float g = on ? round_to<TO>(__uint_as_float(r[j])) : 0.f;
-                            v[j] = g;
-                            q[j] = g * fmaf(yv[e], xsv[e], xov[e]);
+                            const bool on = fmaf(yv[e], scv[e], shv[e]) > 0.f;
+                            r[j] = on ? r[j] : 0u;
+                            q[j] = fmaf(yv[e], xsv[e], xov[e]);
                         }
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float f = round_to<TO>(__uint_as_float(r[j]));
-                        v[j] = valid ? f : 0.f;
-                        q[j] = v[j] * v[j];
-                    }
                 }
-                // pack the output first, reduce the statistics (in place on v), store last: the stores then
-                // never hold a read-dependency on registers the shuffle reduction wants to overwrite
+                // round + pack first (one F2FP per pair), recover the rounded floats from the packed words
                 uint4 packed[sizeof(TO) == 2 ? 4 : 8];
+                if (sizeof(TO) == 2) {
+                    uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) pack4<TO>(packed[sizeof(TO) == 2 ? j / 8 : j / 4], (j / 4) & 1, &v[j]);
+                    for (int j = 0; j < 32; j += 2) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+                        const uint32_t u = *reinterpret_cast<const uint32_t*>(&h2);
+                        pw[j >> 1] = u;
+                        v[j] = __uint_as_float(u << 16);
+                        v[j + 1] = __uint_as_float(u & 0xFFFF0000u);
+                    }
+                } else {
+                    uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { pw[j] = r[j]; v[j] = __uint_as_float(r[j]); }
+                }
                 if (stats != nullptr) {
-                    run_s[cc] += warp_transpose_sum(v, lane);
-                    run_q[cc] += warp_transpose_sum(q, lane);
+                    if (STAGES == 0) {
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                run_s[cc][j] += v[j];
+                                run_q[cc][j] = fmaf(v[j], fused ? q[j] : v[j], run_q[cc][j]);
+                            }
+                        }
+                    } else {
+                        if (edge_tile) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] : 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) q[j] = v[j] * (fused ? q[j] : v[j]);
+                        warp_transpose_head<STAGES>(v, lane);
+                        warp_transpose_head<STAGES>(q, lane);
+#pragma unroll
+                        for (int k = 0; k < KEEP; ++k) { run_s[cc][k] += v[k]; run_q[cc][k] += q[k]; }
+                    }
                 }
                 if (valid && !(dbg & 1)) {
 #pragma unroll
@@ -333,7 +389,7 @@ int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* s
     const int total_tiles = B * ((H + TILE_H - 1) / TILE_H) * (W / TILE_W) * (Cout / BLOCK_N);
     const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
     static int dbg = getenv("TAG_HALO_DBG") ? atoi(getenv("TAG_HALO_DBG")) : 0;
-    kern<<<grid, 320, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout, (const bf16*)bn_y, bnp[0], bnp[1],
+    kern<<<grid, 384, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout, (const bf16*)bn_y, bnp[0], bnp[1],
                                           bnp[2], bnp[3], dbg);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;

@@ -38,7 +38,15 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dout, T* 
         const float sc = scale[c], mu = mean[c], is = invstd[c];
         s_sc[c] = sc;
         s_sh[c] = shift[c];
-        if (MODE == 0) {
+        if (MODE == 0 && POOL) {
+            // pooled reduce pass works on u = sign(gamma) * xhat: a = |gamma| * u + beta is monotone in u, so the
+            // window maximum of a is attained at the maximum of u (sc = gamma * invstd carries gamma's sign)
+            const float sg = sc < 0.f ? -1.f : 1.f;
+            s_pa[c] = sg * is;
+            s_pb[c] = -sg * mu * is;
+            s_sc[c] = sg * sc / is;          // |gamma|  (invstd > 0)
+            s_sh[c] = shift[c] + sc * mu;    // beta = shift + gamma * invstd * mean
+        } else if (MODE == 0) {
             s_pa[c] = is;
             s_pb[c] = -mu * is;
         } else {
@@ -71,6 +79,7 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dout, T* 
         const int hs = (int)(r - (unsigned)b * Hs);
         const bool full = POOL ? (hs < Ho && ws_ < Wo) : true;
         const long oidx = ((((long)b * Ho + hs) * Wo + ws_) * CV + cv) * VEC;
+        if (POOL && MODE == 0 && !full) continue;
         uint4 raw_g = make_uint4(0u, 0u, 0u, 0u);
         if (full) raw_g = ld16(dout + oidx);
         uint4 raw_y[NE];
@@ -99,43 +108,72 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dout, T* 
 #pragma unroll
                 for (int k = 0; k < 4; ++k) go[k] *= ds[k];
             }
-            float v[NE][4], a[NE][4], m[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) m[k] = -INFINITY;
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                unpack4<T>(raw_y[e], sub, v[e]);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    a[e][k] = fmaf(v[e][k], sc[k], sh[k]);
-                    if (inb[e]) m[k] = fmaxf(m[k], a[e][k]);
-                }
-            }
-            bool taken[4] = {false, false, false, false};
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                float o[4];
+            if (POOL && MODE == 0) {
+                // ---- reduce pass, pooled: per window and channel
+                //   sum_e g_e        = G * (cnt/NE + [cnt > 0])
+                //   sum_e g_e * u_e  = G * (S/NE   + [cnt > 0] * max_e u_e),   S = sum of u_e over a_e > 0
+                // (the max-pool gradient lands on a maximal element; tied elements have equal u).  Windows that
+                // hang over the edge carry no gradient (floor-mode pooling) and were skipped above.
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    float g = 0.f;
-                    if (POOL) {
-                        // the first maximum in scan order takes the max-pool gradient (torch semantics)
-                        const bool is_max = !taken[k] && a[e][k] == m[k];
-                        taken[k] = taken[k] || is_max;
-                        if (full && a[e][k] > 0.f) g = go[k] * ((1.0f / NE) + (is_max ? 1.f : 0.f));
-                    } else {
-                        if (a[e][k] > 0.f) g = go[k];
+                    float S = 0.f, cnt = 0.f, m = -INFINITY;
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        float ve[4];
+                        unpack4<T>(raw_y[e], sub, ve);
+                        const float u = fmaf(ve[k], pa[k], pb[k]);
+                        const bool pos = fmaf(u, sc[k], sh[k]) > 0.f;
+                        S += pos ? u : 0.f;
+                        cnt += pos ? 1.f : 0.f;
+                        m = fmaxf(m, u);
                     }
+                    const bool any = cnt > 0.f;
+                    rs[sub * 4 + k] = fmaf(go[k], fmaf(cnt, 1.0f / NE, any ? 1.f : 0.f), rs[sub * 4 + k]);
+                    rq[sub * 4 + k] = fmaf(go[k], fmaf(S, 1.0f / NE, any ? m : 0.f), rq[sub * 4 + k]);
+                }
+            } else if (POOL) {
+                // ---- apply pass, pooled: first maximum in scan order takes the max-pool gradient (torch semantics)
+                float o[NE][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float ve[NE], ae[NE];
+                    float m = -INFINITY;
+                    int idx = 0;
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        float t4[4];
+                        unpack4<T>(raw_y[e], sub, t4);
+                        ve[e] = t4[k];
+                        ae[e] = fmaf(ve[e], sc[k], sh[k]);
+                        const bool better = inb[e] && ae[e] > m;
+                        m = better ? ae[e] : m;
+                        idx = better ? e : idx;
+                    }
+                    const float g1 = full ? go[k] * (1.0f / NE) : 0.f;
+                    const float g2 = g1 + (full ? go[k] : 0.f);
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        const float g = ae[e] > 0.f ? (idx == e ? g2 : g1) : 0.f;
+                        o[e][k] = fmaf(sc[k], g, fmaf(ve[e], pa[k], pb[k]));
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NE; ++e) pack4<T>(raw_o[e], sub, o[e]);
+            } else {
+                // ---- no pooling (NE == 1)
+                float v0[4], o[4];
+                unpack4<T>(raw_y[0], sub, v0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float g = fmaf(v0[k], sc[k], sh[k]) > 0.f ? go[k] : 0.f;
                     if (MODE == 0) {
-                        if (inb[e]) {
-                            rs[sub * 4 + k] += g;
-                            rq[sub * 4 + k] += g * fmaf(v[e][k], pa[k], pb[k]);
-                        }
+                        rs[sub * 4 + k] += g;
+                        rq[sub * 4 + k] = fmaf(g, fmaf(v0[k], pa[k], pb[k]), rq[sub * 4 + k]);
                     } else {
-                        o[k] = fmaf(sc[k], g, fmaf(v[e][k], pa[k], pb[k]));
+                        o[k] = fmaf(sc[k], g, fmaf(v0[k], pa[k], pb[k]));
                     }
                 }
-                if (MODE == 1) pack4<T>(raw_o[e], sub, o);
+                if (MODE == 1) pack4<T>(raw_o[0], sub, o);
             }
         }
         if (MODE == 1) {
@@ -162,6 +200,7 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dout, T* 
                 ds += sm[0][l * CV + cvi][k];
                 dq += sm[1][l * CV + cvi][k];
             }
+            if (POOL && scale[i] < 0.f) dq = -dq;           // the pooled pass accumulated sum g * sign(gamma) * xhat
             atomicAdd(red + i, ds);
             atomicAdd(red + C + i, dq);
         }

@@ -134,6 +134,38 @@ __device__ __forceinline__ float warp_transpose_sum(float (&a)[32], int lane) {
     return a[0];
 }
 
+// The same butterfly split in two: `head` runs the first STAGES stages (offsets 16, 8, ...) and leaves 32 >> STAGES
+// partial sums in a[0 .. (32 >> STAGES) - 1]; `tail` finishes from N = 32 >> STAGES values.  The stages are linear,
+// so partial sums of many calls can be added element-wise between head and tail.
+template <int STAGES>
+__device__ __forceinline__ void warp_transpose_head(float (&a)[32], int lane) {
+#pragma unroll
+    for (int st = 0; st < STAGES; ++st) {
+        const int off = 16 >> st;
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? a[i] : a[i + off];
+            const float keep = upper ? a[i + off] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+template <int N>
+__device__ __forceinline__ float warp_transpose_tail(float (&a)[N], int lane) {
+#pragma unroll
+    for (int off = N / 2; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? a[i] : a[i + off];
+            const float keep = upper ? a[i + off] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return a[0];
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
