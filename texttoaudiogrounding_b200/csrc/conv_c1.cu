@@ -37,19 +37,23 @@ conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __re
     __shared__ float xs[TH + 2][XS_W];
     __shared__ float s_sum[CO], s_sq[CO];
     const int tiles_h = (H + TH - 1) / TH;
-    const int b = blockIdx.x / tiles_h, h0 = (blockIdx.x % tiles_h) * TH;
     const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;        // 8 channel groups x 32 pixels
     if (threadIdx.x < CO) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-    load_x_tile<T>(xs, x, b, h0, H, W);
     float wr[8][9];
 #pragma unroll
     for (int c = 0; c < 8; ++c)
 #pragma unroll
         for (int t = 0; t < 9; ++t) wr[c][t] = __ldg(w + (cg * 8 + c) * 9 + t);
-    __syncthreads();
     float cs[8], cq[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) { cs[c] = 0.f; cq[c] = 0.f; }
+    // persistent over tiles: the per-channel statistics stay in registers and are flushed ONCE per CTA (one
+    // flush per tile meant ~1 M double atomics on 8 cache lines, which serialise in L2)
+    for (int tile = blockIdx.x; tile < B * tiles_h; tile += gridDim.x) {
+    const int b = tile / tiles_h, h0 = (tile % tiles_h) * TH;
+    __syncthreads();
+    load_x_tile<T>(xs, x, b, h0, H, W);
+    __syncthreads();
 #pragma unroll 2
     for (int it = 0; it < TH * TW / 32; ++it) {
         const int pix = it * 32 + pl;
@@ -71,6 +75,7 @@ conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __re
             cq[c] += a * a;
         }
         store8<T>(y + (((long)b * H + h) * W + c0) * CO + cg * 8, o);
+    }
     }
     if (stats != nullptr) {
         // lanes with equal (lane & 7) share the channel group: reduce over lane bits 3,4
@@ -266,20 +271,11 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
     uint16_t* xs = reinterpret_cast<uint16_t*>(S + MROWS * 64 * 9);           // [MROWS][MXS_W] bf16 bits
     float* s_dw = reinterpret_cast<float*>(xs + MROWS * MXS_W);               // [64][9]
     const int tiles_h = (H + MTH - 1) / MTH;
-    const int b = blockIdx.x / tiles_h, h0 = (blockIdx.x % tiles_h) * MTH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     constexpr int W = TW;
 
     for (int i = threadIdx.x; i < CO * 9; i += 256) s_dw[i] = 0.f;
-    for (int i = threadIdx.x; i < MROWS * MXS_W; i += 256) {
-        const int r = i / MXS_W, c = i - r * MXS_W;
-        const int h = h0 - 1 + r, wc = c - 1;
-        uint16_t v = 0;
-        if (c < 66 && h >= 0 && h < H && wc >= 0 && wc < W)
-            v = reinterpret_cast<const uint16_t*>(x)[((long)b * H + h) * W + wc];
-        xs[i] = v;
-    }
     // B fragments of the dgrad product: w[co][tap] as bf16, k = co, n = tap (second n-tile: tap 8 only)
     uint32_t wb[4][2][2];
 #pragma unroll
@@ -295,9 +291,22 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
     for (int n = 0; n < 8; ++n)
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[n][k] = 0.f;
+    const uint32_t my_stage = smem_u32_c1(stage + warp * MNST * 2048);
+    // persistent over tiles: the weight-gradient accumulators stay in registers and are flushed once per CTA
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < B * tiles_h; tile += gridDim.x) {
+    const int b = tile / tiles_h, h0 = (tile % tiles_h) * MTH;
+    __syncthreads();                                      // previous tile's dx phase is done with S / xs
+    for (int i = threadIdx.x; i < MROWS * MXS_W; i += 256) {
+        const int r = i / MXS_W, c = i - r * MXS_W;
+        const int h = h0 - 1 + r, wc = c - 1;
+        uint16_t v = 0;
+        if (c < 66 && h >= 0 && h < H && wc >= 0 && wc < W)
+            v = reinterpret_cast<const uint16_t*>(x)[((long)b * H + h) * W + wc];
+        xs[i] = v;
+    }
     __syncthreads();
 
-    const uint32_t my_stage = smem_u32_c1(stage + warp * MNST * 2048);
     constexpr int NUNITS = MROWS * 4;                     // units of 16 pixels
     constexpr int PER_WARP = (NUNITS + 7) / 8;
     auto unit_row_ok = [&](int u, int& r, int& c0) {
@@ -378,19 +387,7 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
         __syncwarp();
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    // ---- wgrad: acc[n][0..1] = (tap g, co 8n + 2t, +1), acc[n][2..3] = (tap 8 when g == 0)
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-        const int co = n * 8 + 2 * t;
-        atomicAdd(&s_dw[co * 9 + g], acc[n][0]);
-        atomicAdd(&s_dw[(co + 1) * 9 + g], acc[n][1]);
-        if (g == 0) {
-            atomicAdd(&s_dw[co * 9 + 8], acc[n][2]);
-            atomicAdd(&s_dw[(co + 1) * 9 + 8], acc[n][3]);
-        }
-    }
     __syncthreads();
-    for (int i = threadIdx.x; i < CO * 9; i += 256) atomicAdd(dw + i, s_dw[i]);
     // ---- dx[p] = sum_tap S[p - d(tap)][tap]
     if (dx != nullptr) {
         for (int pix = threadIdx.x; pix < MTH * W; pix += 256) {
@@ -407,6 +404,20 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
             dx[((long)b * H + h) * W + c] = v;
         }
     }
+    }
+    // ---- wgrad: acc[n][0..1] = (tap g, co 8n + 2t, +1), acc[n][2..3] = (tap 8 when g == 0)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        const int co = n * 8 + 2 * t;
+        atomicAdd(&s_dw[co * 9 + g], acc[n][0]);
+        atomicAdd(&s_dw[(co + 1) * 9 + g], acc[n][1]);
+        if (g == 0) {
+            atomicAdd(&s_dw[co * 9 + 8], acc[n][2]);
+            atomicAdd(&s_dw[(co + 1) * 9 + 8], acc[n][3]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CO * 9; i += 256) atomicAdd(dw + i, s_dw[i]);
 }
 
 }  // namespace
@@ -414,7 +425,8 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
 extern "C" int tag_conv_c1_fwd(const void* x, const float* w, void* y, int dtype, double* stats, int B,
                                int H, int W, cudaStream_t stream) {
     if (W != TW || B <= 0 || H <= 0) return TAG_ERR_BAD_ARG;
-    const int blocks = B * ((H + TH - 1) / TH);
+    int blocks = B * ((H + TH - 1) / TH);
+    if (blocks > 148 * 8) blocks = 148 * 8;
     if (dtype == TAG_DTYPE_F32)
         conv_c1_fwd_kernel<float><<<blocks, 256, 0, stream>>>((const float*)x, w, (float*)y, stats, B, H, W);
     else
@@ -438,7 +450,8 @@ extern "C" int tag_conv_c1_bwd(const void* dy, const void* x, const float* w, in
             if (e != cudaSuccess) return (int)e;
             attr_set = true;
         }
-        const int mblocks = B * ((H + MTH - 1) / MTH);
+        int mblocks = B * ((H + MTH - 1) / MTH);
+        if (mblocks > 148 * 2) mblocks = 148 * 2;
         conv_c1_bwd_mma_kernel<<<mblocks, 256, MMA_SMEM, stream>>>((const bf16*)dy, (const bf16*)x, w, dw, dx, B, H);
     }
     TAG_RETURN_IF_LAUNCH_FAILED();

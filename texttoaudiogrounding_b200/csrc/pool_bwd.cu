@@ -18,7 +18,7 @@
 namespace {
 
 template <typename T, int PH, int PW, bool POOL, int MODE>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 bn_relu_pool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dout, T* __restrict__ dy,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -71,25 +71,46 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dout, T* 
 #pragma unroll
     for (int k = 0; k < VEC; ++k) { rs[k] = 0.f; rq[k] = 0.f; }
 
-    for (unsigned s = blockIdx.x * slots_per_block + slot_lane; s < n_slots;
-         s += gridDim.x * slots_per_block) {
+    // Slot coordinates and raw loads are one slot AHEAD of the arithmetic (software prefetch): with ~500 instructions
+    // of math per slot and only 16 warps per SM the loads of the next window must already be in flight.
+    // Element offsets are 32-bit (host-checked: the tensors have fewer than 2^31 elements).
+    struct Slot { int b, hs, ws; bool full; unsigned oidx; };
+    auto coord = [&](unsigned s) {
+        Slot c;
         const unsigned r = s / (unsigned)Ws;
-        const int ws_ = (int)(s - r * Ws);
-        const int b = (int)(r / (unsigned)Hs);
-        const int hs = (int)(r - (unsigned)b * Hs);
-        const bool full = POOL ? (hs < Ho && ws_ < Wo) : true;
-        const long oidx = ((((long)b * Ho + hs) * Wo + ws_) * CV + cv) * VEC;
-        if (POOL && MODE == 0 && !full) continue;
-        uint4 raw_g = make_uint4(0u, 0u, 0u, 0u);
-        if (full) raw_g = ld16(dout + oidx);
-        uint4 raw_y[NE];
-        bool inb[NE];
+        c.ws = (int)(s - r * Ws);
+        c.b = (int)(r / (unsigned)Hs);
+        c.hs = (int)(r - (unsigned)c.b * Hs);
+        c.full = POOL ? (c.hs < Ho && c.ws < Wo) : true;
+        c.oidx = ((((unsigned)c.b * Ho + c.hs) * Wo + c.ws) * CV + cv) * VEC;
+        return c;
+    };
+    auto fetch = [&](const Slot& c, uint4& gq, uint4 (&yq)[NE]) {
+        const bool want = !(POOL && MODE == 0 && !c.full);          // the pooled reduce pass skips edge windows
+        gq = (c.full && want) ? ld16(dout + c.oidx) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
-            const int h = hs * PH + e / PW, w = ws_ * PW + e % PW;
-            inb[e] = (h < H && w < W);
-            raw_y[e] = inb[e] ? ld16(y + (((long)b * H + h) * W + w) * C + c_base) : make_uint4(0u, 0u, 0u, 0u);
+            const int h = c.hs * PH + e / PW, w = c.ws * PW + e % PW;
+            yq[e] = (want && h < H && w < W) ? ld16(y + ((((unsigned)c.b * H + h) * W + w) * (unsigned)C + c_base))
+                                             : make_uint4(0u, 0u, 0u, 0u);
         }
+    };
+    const unsigned s_stride = gridDim.x * slots_per_block;
+    unsigned s = blockIdx.x * slots_per_block + slot_lane;
+    Slot cur = coord(s < n_slots ? s : 0u);
+    uint4 raw_g, raw_y[NE];
+    if (s < n_slots) fetch(cur, raw_g, raw_y);
+    Slot nxt = cur;
+    uint4 nxt_g = make_uint4(0u, 0u, 0u, 0u), nxt_y[NE];
+    for (; s < n_slots; s += s_stride, cur = nxt, raw_g = nxt_g) {
+        if (s + s_stride < n_slots) { nxt = coord(s + s_stride); fetch(nxt, nxt_g, nxt_y); }
+        const int b = cur.b, hs = cur.hs, ws_ = cur.ws;
+        const bool full = cur.full;
+        const unsigned oidx = cur.oidx;
+        bool inb[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) inb[e] = (hs * PH + e / PW < H) && (ws_ * PW + e % PW < W);
+        if (!(POOL && MODE == 0 && !full)) {
         uint4 raw_o[NE];
 #pragma unroll
         for (int sub = 0; sub < NSUB; ++sub) {
@@ -181,10 +202,13 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dout, T* 
             for (int e = 0; e < NE; ++e) {
                 if (inb[e]) {
                     const int h = hs * PH + e / PW, w = ws_ * PW + e % PW;
-                    st16(dy + (((long)b * H + h) * W + w) * C + c_base, raw_o[e]);
+                    st16(dy + ((((unsigned)b * H + h) * W + w) * (unsigned)C + c_base), raw_o[e]);
                 }
             }
         }
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) raw_y[e] = nxt_y[e];
     }
     if (MODE == 0) {
         __syncthreads();
@@ -219,9 +243,11 @@ int pool_bwd_dispatch(const void* y, const void* dout, void* dy, const float* sc
     const int spb = 256 / CV;
     const int ph_e = ph > 0 ? ph : 1, pw_e = pw > 0 ? pw : 1;
     const long n_slots = (long)B * ((H + ph_e - 1) / ph_e) * ((W + pw_e - 1) / pw_e);
-    if (n_slots >= (1L << 31)) return TAG_ERR_BAD_ARG;
+    if (n_slots >= (1L << 31) || (long)B * H * W * C >= (1L << 31)) return TAG_ERR_BAD_ARG;
     long blocks = (n_slots + spb - 1) / spb;
-    if (blocks > 148 * 12) blocks = 148 * 12;
+    // two CTAs are resident per SM; the reduce pass ends in 2C double atomics per CTA on a handful of cache lines
+    // (they serialise in L2), so it runs exactly one resident wave
+    if (blocks > 148 * (MODE == 0 ? 2 : 12)) blocks = 148 * (MODE == 0 ? 2 : 12);
     if (blocks < 1) blocks = 1;
     const size_t smem = (size_t)4 * C * sizeof(float);
 #define TAG_LAUNCH_POOL_BWD(PH_, PW_, POOL_)                                                              \

@@ -204,8 +204,40 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
     return out, ctx
 
 
-def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G: EncoderGrads) -> None:
+class _SideStream:
+    """Weight-gradient GEMMs are off the critical path of the backward pass (nothing but the optimizer reads them),
+    so they can run on a second stream next to the HBM-bound elementwise passes of the main stream.  ``run(fn, *t)``
+    forks after the work already queued on the main stream, runs ``fn`` on the side stream and keeps the tensors
+    it reads alive until ``join()`` (the caching allocator must not hand their memory to a later main-stream
+    allocation while the side stream still reads it)."""
+
+    def __init__(self, stream: Optional[torch.cuda.Stream]):
+        self.stream = stream
+        self.keep = []
+
+    def run(self, fn, *tensors):
+        if self.stream is None:
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.stream.wait_event(ev)
+        self.keep.extend(tensors)
+        with torch.cuda.stream(self.stream):
+            fn()
+
+    def join(self):
+        if self.stream is not None:
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            torch.cuda.current_stream().wait_event(ev)
+        self.keep.clear()
+
+
+def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G: EncoderGrads,
+                     side_stream: Optional[torch.cuda.Stream] = None) -> None:
     """Backward of encoder_forward: accumulates parameter gradients into ``G``."""
+    side = _SideStream(side_stream)
     dev = d_emb.device
     B, dtype = ctx.B, ctx.dtype
     f32 = dict(device=dev, dtype=torch.float32)
@@ -270,8 +302,8 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         call("tag_bn_relu_pool_bwd", 1, y2, dp, dy2, ops.dt(y2), aux2[0], aux2[1], aux2[2], aux2[3], red,
              bn_tr, B, H, W, cout, ph, pw, p_blk, seed, ctx.seed_dev)
         # conv2
-        ops.conv_wgrad(dy2, a1, G.conv[2 * blk + 1], B, H, W, cout, cout, 9,
-                       ops.wgrad_splits(P, cout, cout, 9))
+        side.run(lambda: ops.conv_wgrad(dy2, a1, G.conv[2 * blk + 1], B, H, W, cout, cout, 9,
+                                        ops.wgrad_splits(P, cout, cout, 9)), dy2, a1)
         w2t = _operand(Wt, ("t", 2 * blk + 1), lambda: ops.prep_weight_t(Wt.conv[2 * blk + 1], cout, cout, 9, dtype, W))
         da1 = torch.empty_like(a1)
         red1 = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
@@ -302,9 +334,10 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
             call("tag_bn_param_grads", red0, N_MELS, dg, dbt)
         else:
             x_in = ctx.p[blk - 1]
-            ops.conv_wgrad(dy1, x_in, G.conv[2 * blk], B, H, W, cin, cout, 9,
-                           ops.wgrad_splits(P, cin, cout, 9))
+            side.run(lambda: ops.conv_wgrad(dy1, x_in, G.conv[2 * blk], B, H, W, cin, cout, 9,
+                                            ops.wgrad_splits(P, cin, cout, 9)), dy1, x_in)
             w1t = _operand(Wt, ("t", 2 * blk), lambda: ops.prep_weight_t(Wt.conv[2 * blk], cout, cin, 9, dtype, W))
             dp = torch.empty_like(x_in)
             ops.conv_fwd(dy1, w1t, dp, None, False, None, B, H, W, cout, cin, 9)
         del dy1
+    side.join()

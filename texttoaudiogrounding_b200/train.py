@@ -11,6 +11,7 @@
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -80,6 +81,8 @@ class FusedTrainStep:
         self._graphs = {}
         self._static = None
         self._calls = 0
+        # weight-gradient GEMMs on a second stream (TAG_B200_OVERLAP=1)
+        self.side_stream = torch.cuda.Stream(self.device) if os.environ.get("TAG_B200_OVERLAP", "0") == "1" else None
 
     # ------------------------------------------------------------------ flat buffers
     def _flatten(self):
@@ -176,7 +179,7 @@ class FusedTrainStep:
         ws = torch.empty(B, Tp, device=emb.device, dtype=torch.float32)
         call("tag_dot_sigmoid_bwd", d_sim, sim, emb, seq, d_emb, d_seq, ws, B, Tp, D, self.scale)
         call("tag_embed_mean_bwd", text, text_len, d_seq, ew.grad, B, N, D, V)
-        engine.encoder_backward(self.Wt, ectx, d_emb, self.G)
+        engine.encoder_backward(self.Wt, ectx, d_emb, self.G, side_stream=self.side_stream)
         self.sim = sim
 
     def _optim(self):
