@@ -153,6 +153,38 @@ def test_fused_graph_replay_equals_eager():
     assert rel_err(params[True], params[False]) < 1e-2
 
 
+def test_prefetched_inputs_and_side_stream_give_the_same_steps():
+    """step(batch) after prefetch(batch) (copy stream + staging buffers, two alternating pinned host batches) and
+    the side-stream weight-gradient schedule produce the same losses / parameters as the plain path."""
+    from texttoaudiogrounding_b200.train import FusedTrainStep
+    sd = O.synth_state_dict(seed=1, sharpen=1.0, perturb_bn=True)
+    batches = [O.synth_batch(4, 64000, seed=s) for s in (0, 1)]
+    pinned = [{k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in b.items()} for b in batches]
+    res = {}
+    for mode in ("plain", "prefetch", "side"):
+        model = build_model(sd, "fp32")
+        model.train()
+        model.audio_encoder.dropout_enabled = False
+        ts = FusedTrainStep(model, use_graph=True)
+        if mode == "side":
+            ts.side_stream = torch.cuda.Stream()
+        ls = []
+        if mode == "prefetch":
+            ts.prefetch(pinned[0])
+        for i in range(6):
+            b = pinned[i % 2] if mode == "prefetch" else batches[i % 2]
+            loss = ts.step(b)
+            if mode == "prefetch" and i + 1 < 6:
+                ts.prefetch(pinned[(i + 1) % 2])
+            ls.append(loss.item())
+        torch.cuda.synchronize()
+        res[mode] = (ls, ts.flat_p.clone())
+    for mode in ("prefetch", "side"):
+        np.testing.assert_allclose(res[mode][0], res["plain"][0], rtol=5e-3)
+        assert rel_err(res[mode][1], res["plain"][1]) < 1e-2
+    assert abs(res["plain"][0][0] - res["plain"][0][1]) > 1e-6          # the two batches differ
+
+
 def test_train_step_bf16_close_to_reference():
     from texttoaudiogrounding_b200.train import FusedTrainStep
     g, sd, batch = load_case("cfg1_b4_2s")
