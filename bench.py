@@ -251,8 +251,13 @@ def main():
         if dom["flops"] > 0:
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
             ach = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
+            traffic = None
+            try:          # DRAM bytes per launch of the dominant kernel from the committed ncu capture
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[dom_name]["traffic_bytes_per_launch"]
+            except Exception:
+                pass
             roofline = {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None,
+                        "frac": ach / peak, "traffic": traffic,
                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                         if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
                         "flops_per_launch": dom["flops"] / dom["launches"],

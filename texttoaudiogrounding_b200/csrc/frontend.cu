@@ -31,19 +31,32 @@ struct FrontendSmem {
 };
 
 __global__ void __launch_bounds__(THREADS)
-logmel_kernel(const float* __restrict__ wav, int L, long wav_stride, int T0,
+logmel_kernel(const float* __restrict__ wav, int n_clips, int L, long wav_stride, int T0,
               const float* __restrict__ window, const float* __restrict__ fb,
               const int* __restrict__ mel_range, float* __restrict__ db_out,
               double* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrontendSmem& s = *reinterpret_cast<FrontendSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int b = blockIdx.y;
-    const int t0 = blockIdx.x * FRAMES_PER_CTA;
+    // persistent over 8-frame groups: twiddles / window are staged once per CTA and the bn0 statistics are
+    // flushed once per CTA (one flush per group meant 1 M double atomics on 8 cache lines)
+    for (int i = tid; i < 3 * N_FFT / 4; i += THREADS) {
+        float sn, cs;
+        sincospif(2.0f * (float)i / (float)N_FFT, &sn, &cs);
+        s.tw[i] = make_float2(cs, -sn);
+    }
+    for (int i = tid; i < N_FFT; i += THREADS) s.win[i] = __ldg(window + i);
+    float st_sum = 0.f, st_sq = 0.f;
+    const int groups_per_clip = (T0 + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA;
+#pragma unroll 1
+    for (int grp = blockIdx.x; grp < n_clips * groups_per_clip; grp += gridDim.x) {
+    const int b = grp / groups_per_clip;
+    const int t0 = (grp - b * groups_per_clip) * FRAMES_PER_CTA;
     const float* w = wav + (long)b * wav_stride;
 
     // ---- stage samples (reflect padding of 512 on both sides, torch.stft center=True)
     const int start = t0 * HOP - N_FFT / 2;
+    __syncthreads();                       // previous group's readers of samples / db are done
     for (int i = tid; i < SPAN; i += THREADS) {
         int src = start + i;
         if (src < 0) src = -src;
@@ -52,12 +65,6 @@ logmel_kernel(const float* __restrict__ wav, int L, long wav_stride, int T0,
         if (src >= 0 && src < L) v = __ldg(w + src);
         s.samples[i] = v;
     }
-    for (int i = tid; i < 3 * N_FFT / 4; i += THREADS) {
-        float sn, cs;
-        sincospif(2.0f * (float)i / (float)N_FFT, &sn, &cs);
-        s.tw[i] = make_float2(cs, -sn);
-    }
-    for (int i = tid; i < N_FFT; i += THREADS) s.win[i] = __ldg(window + i);
     __syncthreads();
 
     // ---- windowed load (natural order); frame 2p -> real part, 2p+1 -> imaginary part
@@ -138,13 +145,15 @@ logmel_kernel(const float* __restrict__ wav, int L, long wav_stride, int T0,
     if (stats != nullptr) {
         __syncthreads();
         if (tid < N_MELS) {
-            float sm = 0.f, sq = 0.f;
             for (int f = 0; f < FRAMES_PER_CTA; ++f) {
-                if (t0 + f < T0) { float v = s.db[f][tid]; sm += v; sq += v * v; }
+                if (t0 + f < T0) { float v = s.db[f][tid]; st_sum += v; st_sq += v * v; }
             }
-            atomicAdd(stats + tid, (double)sm);
-            atomicAdd(stats + N_MELS + tid, (double)sq);
         }
+    }
+    }
+    if (stats != nullptr && tid < N_MELS) {
+        atomicAdd(stats + tid, (double)st_sum);
+        atomicAdd(stats + N_MELS + tid, (double)st_sq);
     }
 }
 
@@ -162,9 +171,10 @@ extern "C" int tag_logmel_fwd(const float* wav, int batch, int n_samples, long w
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    dim3 grid((T0 + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA, batch);
+    long groups = (long)((T0 + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA) * batch;
+    const int grid = (int)(groups < 148 * 3 ? groups : 148 * 3);          // 3 CTAs (74 KB each) per SM
     logmel_kernel<<<grid, THREADS, sizeof(FrontendSmem), stream>>>(
-        wav, n_samples, wav_stride, T0, window, fb, mel_range, db_out, stats);
+        wav, batch, n_samples, wav_stride, T0, window, fb, mel_range, db_out, stats);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }
