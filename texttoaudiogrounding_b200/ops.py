@@ -98,7 +98,9 @@ def tc_wgrad_splits(B, H, W, Cin, Cout, taps) -> int:
     k_tiles = B * ((H + thk - 1) // thk)
     m_blocks = taps * (Cin // 128) if Cin >= 128 else (taps + 1) // 2
     base = m_blocks * (Cout // bn)
-    s = max(1, (148 * 2 + base - 1) // base)
+    # one CTA (198 KB of smem) is resident per SM, so the grid runs in waves of 148: pick the split count that
+    # fills two waves from BELOW (297 CTAs would run three waves for the work of two)
+    s = max(1, (148 * 2) // base)
     return max(1, min(s, k_tiles // 8 if k_tiles >= 8 else 1))
 
 
