@@ -147,6 +147,23 @@ int tag_frame_bce(const float* sim, long sim_stride, const float* label, long la
                   const long long* length, int B, int Tt, float* loss_out, float* d_sim,
                   long dsim_stride, float grad_scale, cudaStream_t stream);
 
+/* ---- multi-phrase (weakly supervised) head — SURVEY.md §8f rank 1.  MultiTextBiEncoder.forward
+ * (models/audio_text_model.py:147-229) matches every clip against n phrases; the reference expands the audio
+ * embedding to [B*n,T,D] and calls DotProduct (models/match.py:43-60) — here audio [B,T,D] is read in place:
+ * sim[b,t,j] = clamp(sigmoid(scale * <audio[b,t,:], seq[b,j,:]>), 1e-7, 1).  D = 512, n <= 64. */
+int tag_multi_dot_sigmoid_fwd(const float* audio, const float* seq, float* sim, int B, int T, int n, int D,
+                              float scale, cudaStream_t stream);
+/* d_logit_ws: workspace [B,T,n]; d_audio [B,T,D] and d_seq [B,n,D] are overwritten */
+int tag_multi_dot_sigmoid_bwd(const float* d_sim, const float* sim, const float* audio, const float* seq,
+                              float* d_audio, float* d_seq, float* d_logit_ws, int B, int T, int n, int D,
+                              float scale, cudaStream_t stream);
+/* clip[b,j] = pooling over t < length[b] of sim[b,t,j] — models/utils.py:33-95; mode 0 linear_softmax
+ * (sum f^2 / sum f), 1 max, 2 mean, 3 exp_softmax (shifted by the max over ALL frames, as the reference) */
+int tag_pool_with_lens_fwd(const float* sim, const long long* length, int mode, float* clip, int B, int T, int n,
+                           cudaStream_t stream);
+int tag_pool_with_lens_bwd(const float* d_clip, const float* sim, const float* clip, const long long* length,
+                           int mode, float* d_sim, int B, int T, int n, cudaStream_t stream);
+
 /* ---- optimizer step — clip_grad_norm_ + Adam, python_scripts/training/run_strong.py:143-145 */
 int tag_sumsq(const float* g, long n, double* out, cudaStream_t stream);
 int tag_clip_adam(float* p, const float* g, float* m, float* v, long n, const double* sumsq,

@@ -454,3 +454,98 @@ def train_step(sd, batch, opt: AdamState, lr: float = 1e-3, max_grad_norm: float
             denom = (opt.v[k].sqrt() / math.sqrt(bc2)).add_(eps)
             sd[k] = (p - (lr / bc1) * opt.m[k] / denom).detach()
     return loss.detach(), dict(zip(keys, grads)), total_norm
+
+
+# --------------------------------------------------------------------------- weak (multi-phrase) path
+# SURVEY.md §8f rank 1.  Reference sites restated here:
+#   * MultiTextBiEncoder.forward ...... models/audio_text_model.py:147-229
+#   * *_with_lens pooling ............. models/utils.py:33-95
+#   * ClipBceLoss / ClipFrameBceLoss .. losses.py:38-43,186-210
+#   * Runner.forward (weak) ........... python_scripts/training/run_weak_phrase.py:39-60
+def sum_with_lens(features, lens):
+    """models/utils.py:33-48."""
+    mask = generate_length_mask(torch.as_tensor(lens), features.size(1))
+    while mask.ndim < features.ndim:
+        mask = mask.unsqueeze(-1)
+    return (features * mask).sum(1)
+
+
+def pool_with_lens(frame_sim, lens, pooling: str):
+    """clip-level pooling of frame probabilities [B,T,n] over the valid frames (models/utils.py:51-95)."""
+    lens = torch.as_tensor(lens)
+    if pooling == "linear_softmax":
+        return sum_with_lens(frame_sim ** 2, lens) / sum_with_lens(frame_sim, lens)
+    if pooling == "mean":
+        l = lens
+        s = sum_with_lens(frame_sim, lens)
+        while l.ndim < s.ndim:
+            l = l.unsqueeze(1)
+        return s / l
+    if pooling == "max":
+        mask = generate_length_mask(lens, frame_sim.size(1))
+        f = frame_sim.clone()
+        f[~mask] = float("-inf")
+        return f.max(1)[0]
+    if pooling == "exp_softmax":
+        normed = frame_sim - frame_sim.max(1, keepdim=True)[0]
+        e = torch.exp(normed)
+        w = e / sum_with_lens(e, lens).unsqueeze(1)
+        return sum_with_lens(w * frame_sim, lens)
+    raise Exception(f"Unsupported pooling {pooling}")
+
+
+def synth_weak_batch(batch: int, n_samples: int, n_phrases: int = 5, n_tokens: int = 6, seed: int = 0,
+                     vocab: int = VOCAB, ragged: bool = True):
+    """Seeded batch in the schema of the weak-phrase runner: text [B,n,N], text_len [B,n], weak label [B,n],
+    strong label [B,T',n]."""
+    base = synth_batch(batch, n_samples, n_tokens, seed, vocab, ragged)
+    g = torch.Generator().manual_seed(seed + 1000)
+    text = torch.randint(2, vocab, (batch, n_phrases, n_tokens), generator=g)
+    text_len = torch.randint(1, n_tokens + 1, (batch, n_phrases), generator=g)
+    for b in range(batch):
+        for j in range(n_phrases):
+            text[b, j, text_len[b, j]:] = 0
+    t_out = (n_samples // HOP + 1) // 4
+    base.update({
+        "text": text, "text_len": text_len,
+        "label": (torch.rand(batch, n_phrases, generator=g) > 0.5).float(),
+        "strong_label": (torch.rand(batch, t_out, n_phrases, generator=g) > 0.5).float(),
+    })
+    base["weak_label"] = base["label"]
+    return base
+
+
+def multitext_forward(sd, input_dict, pooling: str = "linear_softmax", training=False, dropout=True,
+                      dropout_masks=None, fast_gru=False):
+    """models/audio_text_model.py:147-229 (no cross encoder / projections / upsample / safe_size)."""
+    a = cnn8rnn_forward(sd, input_dict["waveform"], input_dict["waveform_len"], training,
+                        dropout_masks, dropout, None, fast_gru)
+    audio_emb = a["embedding"]
+    text = input_dict["text"]
+    B, n = text.shape[0], text.shape[1]
+    t = embedding_mean(sd, text.reshape(B * n, -1), torch.as_tensor(input_dict["text_len"]).reshape(B * n))
+    audio_rep = audio_emb.unsqueeze(1).expand(-1, n, -1, -1).reshape(B * n, *audio_emb.shape[1:])
+    frame_sim, _ = dot_product_match(audio_rep, t["seq_emb"])
+    frame_sim = frame_sim.reshape(B, n, -1).transpose(1, 2)          # [B,T,n]
+    clip_sim = pool_with_lens(frame_sim, a["length"], pooling)
+    return {"frame_sim": frame_sim, "clip_sim": clip_sim, "length": a["length"]}
+
+
+def clip_bce_loss(clip_sim, label):
+    """losses.py:38-43."""
+    return F.binary_cross_entropy(clip_sim, label)
+
+
+def frame_bce_tensor(frame_sim, label, length):
+    """losses.py:26-35 (FrameBceLoss.forward_tensor, 2-D or 3-D)."""
+    loss = F.binary_cross_entropy(frame_sim, label, reduction="none")
+    mask = generate_length_mask(length, loss.size(1)).to(loss.dtype)
+    if loss.ndim == 3:
+        mask = mask.unsqueeze(-1).expand(*loss.size())
+    return (loss * mask).sum() / mask.sum()
+
+
+def clip_frame_bce_loss(output, frame_weight: float):
+    """losses.py:186-210 with the default keys."""
+    return (1 - frame_weight) * clip_bce_loss(output["clip_sim"], output["weak_label"]) + \
+        frame_weight * frame_bce_tensor(output["frame_sim"], output["strong_label"], output["length"])

@@ -112,3 +112,27 @@ def test_freeze_and_train_mode_semantics():
     length = torch.div(torch.div(torch.as_tensor([64000, 32000]), 320, rounding_mode="floor") + 1, 4,
                        rounding_mode="floor")
     assert length.tolist() == [50, 25]
+
+
+def test_dict_tokenizer_matches_reference_behaviour():
+    """reference datasets/text_tokenizer.py:9-58: whitespace tokens, <unk> for unknown words, zero padding,
+    List[List[str]] -> [B, text_num, N]."""
+    from texttoaudiogrounding_b200.datasets.text_tokenizer import DictTokenizer
+    vocab = {"<pad>": 0, "<unk>": 1, "a": 2, "dog": 3, "barks": 4, "rain": 5}
+    tok = DictTokenizer(vocab)
+    out = tok(["a dog barks", "rain", "a cat"])
+    assert out["text"].tolist() == [[2, 3, 4], [5, 0, 0], [2, 1, 0]]
+    assert out["text_len"].tolist() == [3, 1, 2]
+    out = tok([["a dog", "rain"], ["barks", "a dog barks"]])
+    assert tuple(out["text"].shape) == (2, 2, 3) and out["text_len"].tolist() == [[2, 1], [1, 3]]
+    assert tok.inverse_transform(out["text"][1].tolist()) == ["barks", "a dog barks"]
+
+
+def test_hf_style_facade_builds_and_refuses_cpu():
+    from texttoaudiogrounding_b200.models.hf_modeling_grounding import (
+        Cnn8RnnW2vMeanGroundingConfig, Cnn8RnnW2vMeanGroundingModel)
+    cfg = Cnn8RnnW2vMeanGroundingConfig(vocabulary={"<pad>": 0, "<unk>": 1, "dog": 2})
+    model = Cnn8RnnW2vMeanGroundingModel(cfg)
+    assert model.model.text_encoder.embedding.core.weight.shape == (3, 512)
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 32000), [32000], ["dog"])          # CPU tensors: no fallback

@@ -1,5 +1,6 @@
-"""FrameBceLoss — host-side mirror of reference losses.py:11-35.  Masked mean BCE over the
-frames t < length[b]; forward and d(loss)/d(frame_sim) in one kernel (csrc/head.cu)."""
+"""FrameBceLoss / ClipBceLoss / ClipFrameBceLoss — host-side mirrors of reference losses.py:11-43 and :186-210.
+Masked mean BCE over the frames t < length[b] (or over all clip-level probabilities); forward and
+d(loss)/d(prob) in one kernel (csrc/head.cu)."""
 from __future__ import annotations
 
 from typing import Dict
@@ -30,6 +31,14 @@ class _FrameBceFunction(torch.autograd.Function):
 def frame_bce(frame_sim: torch.Tensor, label: torch.Tensor, length) -> torch.Tensor:
     if frame_sim.ndim == 3 and frame_sim.size(2) == 1:
         frame_sim = frame_sim.squeeze(2)
+    if frame_sim.ndim == 3:
+        # [B, T, n] with the mask expanded over n (losses.py:26-35): element (b, t, j) is valid iff t < length[b],
+        # i.e. iff its flat index t*n + j < length[b]*n
+        n = frame_sim.size(2)
+        B = frame_sim.size(0)
+        length3 = torch.as_tensor(length).to(torch.long) * n
+        label = label.to(device=frame_sim.device, dtype=torch.float32)
+        return frame_bce(frame_sim.contiguous().view(B, -1), label.contiguous().view(B, -1), length3)
     if not frame_sim.is_cuda:
         raise RuntimeError("FrameBceLoss (B200) needs CUDA tensors: there is no CPU fallback")
     length_host = torch.as_tensor(length)
@@ -54,3 +63,40 @@ class FrameBceLoss(nn.Module):
 
     def forward_tensor(self, frame_sim, label, length):
         return frame_bce(frame_sim, label, length)
+
+
+def clip_bce(prob: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+    """F.binary_cross_entropy(prob, label) (mean over all elements) of clip-level probabilities [B, n]."""
+    if not prob.is_cuda:
+        raise RuntimeError("ClipBceLoss (B200) needs CUDA tensors: there is no CPU fallback")
+    p2 = prob.float().contiguous().view(prob.shape[0], -1)
+    l2 = label.to(device=prob.device, dtype=torch.float32).contiguous().view(prob.shape[0], -1)
+    full = torch.full((p2.shape[0],), p2.shape[1], device=prob.device, dtype=torch.long)
+    return _FrameBceFunction.apply(p2, l2, full)
+
+
+class ClipBceLoss(nn.Module):
+    def forward(self, output: Dict):
+        return clip_bce(output["clip_sim"], output["label"])
+
+    def forward_tensor(self, prob, label):
+        return clip_bce(prob, label)
+
+
+class ClipFrameBceLoss(nn.Module):
+    def __init__(self, frame_weight, clip_label_key="weak_label", clip_prob_key="clip_sim",
+                 frame_label_key="strong_label", frame_prob_key="frame_sim"):
+        super().__init__()
+        self.clip_loss_fn = ClipBceLoss()
+        self.frame_loss_fn = FrameBceLoss()
+        self.frame_weight = frame_weight
+        self.clip_label_key = clip_label_key
+        self.clip_prob_key = clip_prob_key
+        self.frame_label_key = frame_label_key
+        self.frame_prob_key = frame_prob_key
+
+    def forward(self, output: Dict):
+        return (1 - self.frame_weight) * self.clip_loss_fn.forward_tensor(
+            output[self.clip_prob_key], output[self.clip_label_key]) + \
+            self.frame_weight * self.frame_loss_fn.forward_tensor(
+                output[self.frame_prob_key], output[self.frame_label_key], output["length"])

@@ -15,7 +15,7 @@ from . import _lib
 F32, BF16 = 0, 1
 LAUNCHES = 0
 # kernels per C-ABI call (default 1)
-_KERNELS_PER_CALL = {"tag_clip_adam": 2, "tag_dot_sigmoid_bwd": 2, "tag_conv_c1_bwd": 2}
+_KERNELS_PER_CALL = {"tag_clip_adam": 2, "tag_dot_sigmoid_bwd": 2, "tag_multi_dot_sigmoid_bwd": 2}
 
 
 def dt(t: torch.Tensor) -> int:
