@@ -164,6 +164,32 @@ int tag_pool_with_lens_fwd(const float* sim, const long long* length, int mode, 
 int tag_pool_with_lens_bwd(const float* d_clip, const float* sim, const float* clip, const long long* length,
                            int mode, float* d_sim, int B, int T, int n, cudaStream_t stream);
 
+/* ---- sentence-level alignment — SURVEY.md §8f rank 3.  align.DotProduct (models/align.py:7-31) forms
+ * sim[i,j,t,n] = clamp(sigmoid(scale * <audio[i,t,:], text[j,n,:]>), 1e-7, 1) for ALL (clip i, text j) pairs and
+ * the sim_pooling classes (models/sim_pooling.py:6-204) reduce it over frames t < audio_len[i] and tokens
+ * n < text_len[j].  The frame pooling is fused into the kernel that forms the dot products; the 4-D matrix is only
+ * written when sim_matrix != NULL.  text is [Cpad, D] (the Bt*N token rows, zero padded to a multiple of 64 rows),
+ * colpool / aux are [Ba, Cpad] (frame-pooled value per (clip, text row) and the term backward needs).
+ * a_mode: 0 mean, 1 max, 2 linear_softmax, 3 exp_softmax;  t_mode: 0 mean, 1 sum, 2 max, 3 mean+sum.  D = 512. */
+int tag_align_pool_fwd(const float* audio, const float* text, const long long* audio_len, int a_mode,
+                       float* sim_matrix, float* colpool, float* aux, int Ba, int T, int Bt, int N, int Cpad,
+                       int D, float scale, cudaStream_t stream);
+/* G [Ba*T, Cpad] = scale * d(loss)/d(logit); d_audio = G x text and d_text = G^T x audio are then plain GEMMs
+ * (tag_conv_fwd / tag_conv_wgrad with taps = 1) */
+int tag_align_pool_bwd(const float* audio, const float* text, const long long* audio_len, int a_mode,
+                       const float* d_colpool, const float* colpool, const float* aux, float* G, int Ba, int T,
+                       int Cpad, int D, float scale, cudaStream_t stream);
+int tag_align_text_pool_fwd(const float* colpool, const long long* text_len, int t_mode, float* out, int Ba, int Bt,
+                            int N, int Cpad, cudaStream_t stream);
+int tag_align_text_pool_bwd(const float* d_out, const float* colpool, const long long* text_len, int t_mode,
+                            float* d_colpool, int Ba, int Bt, int N, int Cpad, cudaStream_t stream);
+/* MaxMarginRankingLoss (losses.py:226-264) on sim [n, n]: loss (scalar) and d(loss)/d(sim) in one launch */
+int tag_max_margin_rank(const float* sim, int n, float margin, float lamda1, int fix_norm, float* loss,
+                        float* d_sim, cudaStream_t stream);
+/* gradient of the token embeddings (EmbeddingLayer.forward, models/text_encoder.py:39-43): d_emb[text[b,n]] += d_token[b,n,:] */
+int tag_embed_token_bwd(const long long* text, const float* d_token, float* d_emb, int B, int N, int D, int vocab,
+                        cudaStream_t stream);
+
 /* ---- optimizer step — clip_grad_norm_ + Adam, python_scripts/training/run_strong.py:143-145 */
 int tag_sumsq(const float* g, long n, double* out, cudaStream_t stream);
 int tag_clip_adam(float* p, const float* g, float* m, float* v, long n, const double* sumsq,

@@ -549,3 +549,95 @@ def clip_frame_bce_loss(output, frame_weight: float):
     """losses.py:186-210 with the default keys."""
     return (1 - frame_weight) * clip_bce_loss(output["clip_sim"], output["weak_label"]) + \
         frame_weight * frame_bce_tensor(output["frame_sim"], output["strong_label"], output["length"])
+
+
+# =====================================================================================================
+# SURVEY.md §8f rank 3 — sentence-level alignment.  Reference sites restated here:
+#   * align.DotProduct ................ models/align.py:7-31
+#   * sim_pooling.Audio*Text* ......... models/sim_pooling.py:6-190
+#   * AudioTextAlignByWord/ByPhrase ... models/audio_text_model.py:843-976
+#   * MaxMarginRankingLoss ............ losses.py:226-264
+def align_dot_product(audio, text, scaled: bool = False):
+    """sim[i, j, t, n] for all (clip i, text j) pairs (models/align.py:14-31, l2norm=False)."""
+    bs, n_seg, dim = audio.shape
+    n_txt = text.shape[1]
+    score = audio.reshape(-1, dim) @ text.reshape(-1, dim).t()
+    if scaled:
+        score = score / math.sqrt(dim)
+    score = torch.sigmoid(score).clamp(1e-7, 1.0)
+    return score.reshape(bs, n_seg, bs, n_txt).transpose(1, 2)
+
+
+def _tokens_pool(x, lens, mode: str):
+    """second reduction of sim_pooling: x [bs*bs, t_len] over n < lens."""
+    lens = torch.as_tensor(lens)
+    if mode == "mean":
+        return sum_with_lens(x, lens) / lens
+    if mode == "sum":
+        return sum_with_lens(x, lens)
+    if mode == "max":
+        return pool_with_lens(x, lens, "max")
+    if mode == "meansum":
+        return sum_with_lens(x, lens) + sum_with_lens(x, lens) / lens
+    raise Exception(mode)
+
+
+def sim_pooling(sim, audio_len, text_len, audio_pool: str, text_pool: str):
+    """models/sim_pooling.py: frames pooled with audio_len[i] (expanded over j), tokens with text_len[j]
+    (repeated over i); returns [bs, bs]."""
+    bs, a_len, t_len = sim.size(0), sim.size(2), sim.size(3)
+    s = sim.reshape(bs * bs, a_len, t_len)
+    al = torch.as_tensor(audio_len).unsqueeze(1).expand(bs, bs).reshape(-1)
+    s = pool_with_lens(s, al, audio_pool)
+    tl = torch.as_tensor(text_len).repeat(bs)
+    return _tokens_pool(s, tl, text_pool).reshape(bs, bs)
+
+
+def max_margin_ranking_loss(x, margin: float = 1.0, fix_norm: bool = True, lamda1: float = 1.0):
+    """losses.py:235-264, written per element: both halves compare the positive x[i,i] with x[i,j] and with
+    lamda1 * x[j,i]; fix_norm drops the i == j terms."""
+    n = x.size(0)
+    d = torch.diag(x).unsqueeze(1).expand(n, n)
+    m1 = F.relu(margin - (d - x))
+    m2 = F.relu(margin - (d - lamda1 * x.t()))
+    if fix_norm:
+        keep = 1.0 - torch.eye(n)
+        return ((m1 * keep).sum() + (m2 * keep).sum()) / (2.0 * n * (n - 1))
+    return (m1.sum() + m2.sum()) / (2.0 * n * n)
+
+
+def synth_align_batch(batch: int, n_samples: int, max_phrases: int = 3, n_tokens: int = 6, seed: int = 0,
+                      vocab: int = VOCAB):
+    """Seeded batch in the schema of the sentence-level runners: word-level ``text`` [B, N] / ``text_len`` and
+    phrase-level ``phrases`` [txt_num, N] / ``phrases_len`` / ``phrases_num`` (list, sums to txt_num)."""
+    base = synth_batch(batch, n_samples, n_tokens, seed, vocab, True)
+    g = torch.Generator().manual_seed(seed + 2000)
+    num = torch.randint(1, max_phrases + 1, (batch,), generator=g)
+    num[0] = max_phrases
+    total = int(num.sum())
+    phrases = torch.randint(2, vocab, (total, n_tokens), generator=g)
+    plen = torch.randint(1, n_tokens + 1, (total,), generator=g)
+    for r in range(total):
+        phrases[r, plen[r]:] = 0
+    base.update({"phrases": phrases, "phrases_len": plen, "phrases_num": num.tolist(), "text_key": "phrases"})
+    return base
+
+
+def align_forward(sd, input_dict, level: str = "phrase", audio_pool: str = "mean", text_pool: str = "mean",
+                  scaled: bool = False, training=False, dropout=True, dropout_masks=None, fast_gru=False):
+    """AudioTextAlignByWord.forward (models/audio_text_model.py:871-904) / AudioTextAlignByPhrase.forward
+    (:937-976) without projections / cross encoder."""
+    a = cnn8rnn_forward(sd, input_dict["waveform"], input_dict["waveform_len"], training,
+                        dropout_masks, dropout, None, fast_gru)
+    if level == "word":
+        t = embedding_mean(sd, input_dict["text"], torch.as_tensor(input_dict["text_len"]))
+        text_emb, text_len = t["token_emb"], input_dict["text_len"]
+    else:
+        key = input_dict["text_key"]
+        t = embedding_mean(sd, input_dict[key], torch.as_tensor(input_dict[f"{key}_len"]))
+        num = [int(n) for n in input_dict[f"{key}_num"]]
+        text_emb = torch.nn.utils.rnn.pad_sequence(torch.split(t["seq_emb"], num, dim=0), batch_first=True)
+        text_len = num
+    sim_matrix = align_dot_product(a["embedding"], text_emb, scaled)
+    sim = sim_pooling(sim_matrix, a["length"], text_len, audio_pool, text_pool)
+    return {"sim": sim, "sim_matrix": sim_matrix, "length": a["length"]}

@@ -42,6 +42,16 @@ __global__ void embed_mean_bwd_kernel(const long long* __restrict__ text, const 
     }
 }
 
+// d_emb[text[b,n], :] += d_token[b,n,:] for every position (nn.Embedding backward; pads included)
+__global__ void embed_token_bwd_kernel(const long long* __restrict__ text, const float* __restrict__ d_token,
+                                       float* __restrict__ d_emb, int D, int vocab) {
+    const long row = blockIdx.x;
+    long long id = text[row];
+    if (id < 0) id = 0;
+    if (id >= vocab) id = vocab - 1;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) atomicAdd(d_emb + id * D + d, d_token[row * D + d]);
+}
+
 // one warp per (b, t): sim = clamp(sigmoid(scale * <a[b,t,:], s[b,:]>), 1e-7, 1)
 __global__ void dot_sigmoid_fwd_kernel(const float* __restrict__ audio, const float* __restrict__ seq,
                                        float* __restrict__ sim, float* __restrict__ logits,
@@ -169,6 +179,14 @@ extern "C" int tag_embed_mean_bwd(const long long* text, const long long* text_l
                                   float* d_emb, int B, int N, int D, int vocab, cudaStream_t stream) {
     if (B <= 0) return TAG_ERR_BAD_ARG;
     embed_mean_bwd_kernel<<<B, 128, 0, stream>>>(text, text_len, d_seq, d_emb, N, D, vocab);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_embed_token_bwd(const long long* text, const float* d_token, float* d_emb, int B, int N, int D,
+                                   int vocab, cudaStream_t stream) {
+    if (B <= 0 || N <= 0) return TAG_ERR_BAD_ARG;
+    embed_token_bwd_kernel<<<B * N, 128, 0, stream>>>(text, d_token, d_emb, D, vocab);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }

@@ -100,3 +100,39 @@ class ClipFrameBceLoss(nn.Module):
             output[self.clip_prob_key], output[self.clip_label_key]) + \
             self.frame_weight * self.frame_loss_fn.forward_tensor(
                 output[self.frame_prob_key], output[self.frame_label_key], output["length"])
+
+
+class _MaxMarginRankFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sim, margin, lamda1, fix_norm):
+        n = sim.shape[0]
+        loss = torch.empty((), device=sim.device, dtype=torch.float32)
+        d_sim = torch.empty(n, n, device=sim.device, dtype=torch.float32)
+        call("tag_max_margin_rank", sim, n, float(margin), float(lamda1), int(bool(fix_norm)), loss, d_sim)
+        ctx.save_for_backward(d_sim)
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        (d_sim,) = ctx.saved_tensors
+        return d_sim * d_loss, None, None, None
+
+
+class MaxMarginRankingLoss(nn.Module):
+    """Bidirectional max-margin ranking over the clip x caption similarity matrix — mirror of reference
+    losses.py:226-264 (same constructor; loss and its gradient from one kernel, csrc/align.cu)."""
+
+    def __init__(self, margin=1, fix_norm=True, lamda1=1, sim_key="sim"):
+        super().__init__()
+        self.fix_norm = fix_norm
+        self.margin = margin
+        self.lamda1 = lamda1
+        self.sim_key = sim_key
+
+    def forward(self, x):
+        x = x[self.sim_key]
+        if not x.is_cuda:
+            raise RuntimeError("MaxMarginRankingLoss (B200) needs CUDA tensors: there is no CPU fallback")
+        if x.ndim != 2 or x.shape[0] != x.shape[1]:
+            raise RuntimeError(f"expected a square similarity matrix, got {tuple(x.shape)}")
+        return _MaxMarginRankFunction.apply(x.float().contiguous(), self.margin, self.lamda1, self.fix_norm)

@@ -101,3 +101,72 @@ class MultiTextBiEncoder(BiEncoder):
         length = audio_output["length"]
         clip_sim = pool_with_lens(frame_sim, length, self.pooling)
         return {"frame_sim": frame_sim, "clip_sim": clip_sim, "length": length}
+
+
+class _AudioTextAlign(nn.Module):
+    """Shared constructor of the sentence-level alignment models (reference models/audio_text_model.py:843-869,
+    907-935): all-pairs similarity ``match_fn`` (models.align.DotProduct) + a ``sim_pooling`` module."""
+
+    def __init__(self, audio_encoder: nn.Module, text_encoder: nn.Module, match_fn: nn.Module, sim_pooling: nn.Module,
+                 shared_dim: int, cross_encoder: Optional[nn.Module] = None, add_proj: bool = False,
+                 freeze_audio_encoder: bool = False, freeze_text_encoder: bool = False):
+        super().__init__()
+        self.audio_encoder = audio_encoder
+        self.text_encoder = text_encoder
+        self.match_fn = match_fn
+        self.sim_pooling = sim_pooling
+        self.shared_dim = shared_dim
+        if cross_encoder is not None:
+            raise NotImplementedError("cross_encoder is not on the B200 path (SURVEY.md §8f rank 2)")
+        if audio_encoder.embed_dim != text_encoder.embed_dim or add_proj:
+            raise NotImplementedError("audio_proj/text_proj (add_proj or mismatched embed dims) are not on the "
+                                      "B200 path (SURVEY.md §8f rank 2)")
+        if freeze_audio_encoder:
+            for param in self.audio_encoder.parameters():
+                param.requires_grad = False
+        if freeze_text_encoder:
+            for param in self.text_encoder.parameters():
+                param.requires_grad = False
+
+    def _finish(self, input_dict, sim_matrix, audio_len, text_len):
+        sim = self.sim_pooling({"sim": sim_matrix, "audio_len": audio_len, "text_len": text_len})
+        output = {"sim": sim}
+        if input_dict.get("output_matrix", False):
+            output["sim_matrix"] = sim_matrix.materialize() if hasattr(sim_matrix, "materialize") else sim_matrix
+        return output
+
+
+class AudioTextAlignByWord(_AudioTextAlign):
+    """Every clip against every caption, word by word (reference models/audio_text_model.py:843-904)."""
+
+    def __init__(self, audio_encoder, text_encoder, match_fn, sim_pooling, shared_dim, add_proj=False,
+                 freeze_audio_encoder=False, freeze_text_encoder=False):
+        super().__init__(audio_encoder, text_encoder, match_fn, sim_pooling, shared_dim, None, add_proj,
+                         freeze_audio_encoder, freeze_text_encoder)
+
+    def forward(self, input_dict):
+        audio_output = self.audio_encoder(input_dict)
+        audio_emb = audio_output["embedding"]                     # [bs, n_seg, emb_dim]
+        word_emb = self.text_encoder(input_dict)["token_emb"]     # [bs, n_word, emb_dim]
+        sim_matrix = self.match_fn(audio_emb, word_emb)           # [bs, bs, n_seg, n_word] (deferred)
+        return self._finish(input_dict, sim_matrix, audio_output["length"], input_dict["text_len"])
+
+
+class AudioTextAlignByPhrase(_AudioTextAlign):
+    """Every clip against the phrases of every caption (reference models/audio_text_model.py:907-976):
+    ``input_dict[text_key]`` holds all phrases of the batch [txt_num, max_txt_len], ``{text_key}_num`` how many
+    belong to each clip; the phrase embeddings are regrouped to [bs, max_txt_num, emb_dim] (zero padded)."""
+
+    def forward(self, input_dict):
+        import torch
+        audio_output = self.audio_encoder(input_dict)
+        audio_emb = audio_output["embedding"]
+        text_key = input_dict["text_key"]
+        phrases_emb = self.text_encoder({"text": input_dict[text_key], "text_len": input_dict[f"{text_key}_len"]})
+        phrases_num = input_dict[f"{text_key}_num"]
+        if isinstance(phrases_num, torch.Tensor):
+            phrases_num = phrases_num.tolist()
+        seq_emb = torch.split(phrases_emb["seq_emb"], [int(n) for n in phrases_num], dim=0)
+        seq_emb = nn.utils.rnn.pad_sequence(seq_emb, batch_first=True)      # [bs, max_txt_num, emb_dim]
+        sim_matrix = self.match_fn(audio_emb, seq_emb)
+        return self._finish(input_dict, sim_matrix, audio_output["length"], phrases_num)

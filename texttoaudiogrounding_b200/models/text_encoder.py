@@ -23,16 +23,19 @@ class _EmbedMeanFunction(torch.autograd.Function):
         call("tag_embed_mean_fwd", tokens, lens, weight, token_emb, seq_emb, B, N, D, V)
         ctx.save_for_backward(tokens, lens)
         ctx.shape = (V, D)
-        ctx.mark_non_differentiable(token_emb)
+        ctx.set_materialize_grads(False)        # an unused output arrives as None, not as a zero tensor
         return token_emb, seq_emb
 
     @staticmethod
-    def backward(ctx, _d_token, d_seq):
+    def backward(ctx, d_token, d_seq):
         tokens, lens = ctx.saved_tensors
         V, D = ctx.shape
         B, N = tokens.shape
-        d_w = torch.zeros(V, D, device=d_seq.device, dtype=torch.float32)
-        call("tag_embed_mean_bwd", tokens, lens, d_seq.contiguous(), d_w, B, N, D, V)
+        d_w = torch.zeros(V, D, device=tokens.device, dtype=torch.float32)
+        if d_seq is not None:
+            call("tag_embed_mean_bwd", tokens, lens, d_seq.contiguous(), d_w, B, N, D, V)
+        if d_token is not None:          # word-level consumers (AudioTextAlignByWord): nn.Embedding backward
+            call("tag_embed_token_bwd", tokens, d_token.contiguous(), d_w, B, N, D, V)
         return d_w, None, None
 
 
