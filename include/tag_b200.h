@@ -43,6 +43,13 @@ int tag_version(void);
 int tag_logmel_fwd(const float* wav, int batch, int n_samples, long wav_stride, const float* window,
                    const float* fb, const int* mel_range, float* db_out, double* stats,
                    cudaStream_t stream);
+/* Same contract for a COMPACT filterbank (mel_range required; fb_nnz = sum over mels of hi - lo, <= 2048 — the
+ * slaney triangles need ~1030): one warp per pair of frames, 1024-point FFT as two register-resident 32-point passes.
+ * wav_dtype: 0 = float32, 2 = float16 (the reference stores waveforms as float16, utils/data/pack_waveform.py:46-52;
+ * they are widened on load, as `.float()` does in datasets/single_phrase_dataset.py). */
+int tag_logmel_fwd_v2(const void* wav, int wav_dtype, int batch, int n_samples, long wav_stride,
+                      const float* window, const float* fb, const int* mel_range, int fb_nnz, float* db_out,
+                      double* stats, cudaStream_t stream);
 
 /* ---- BatchNorm2d pieces — models/audio_encoder.py:133,188-190; models/panns.py:35-36,49-50 */
 int tag_channel_stats_f32(const float* x, long rows, int C, double* stats, cudaStream_t stream);

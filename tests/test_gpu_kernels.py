@@ -45,6 +45,40 @@ def test_logmel_matches_oracle_incl_short_and_tonal():
         assert (out2 - out).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("L,B", [(64000, 3), (32000, 2), (6401, 1), (640, 2), (320000, 1), (319999, 2)])
+def test_logmel_warp_kernel_matches_oracle(L, B):
+    """tag_logmel_fwd_v2 (one warp per frame pair, register FFT): even / odd frame counts, clips shorter than two
+    windows (every frame reflected), fp32 and fp16 waveforms, bn0 statistics."""
+    ops = _ops()
+    from texttoaudiogrounding_b200 import engine
+    batch = O.synth_batch(B, L, seed=L % 7)
+    wav = batch["waveform"]
+    window, fb = O.hann_window(), O.melscale_fbanks()
+    ref = O.logmel_db(wav, window, fb).transpose(1, 2)          # [B,T0,64]
+    T0 = L // 320 + 1
+    fbc = fb.cuda()
+    mr = engine.compute_mel_range(fbc)
+    nnz = engine.mel_nnz(mr)
+    assert 0 < nnz <= engine.LOGMEL_FB_CAP
+    out = torch.full((B, T0, 64), float("nan"), device="cuda")
+    stats = torch.zeros(128, device="cuda", dtype=torch.float64)
+    ops.call("tag_logmel_fwd_v2", wav.cuda(), 0, B, L, L, window.cuda(), fbc, mr, nnz, out, stats)
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < 5e-3, (L, err)
+    np.testing.assert_allclose(stats[:64].cpu().numpy(), ref.double().sum((0, 1)).numpy(), rtol=1e-4)
+    np.testing.assert_allclose(stats[64:].cpu().numpy(), ref.double().pow(2).sum((0, 1)).numpy(), rtol=1e-4)
+    # agrees with the shared-memory Stockham kernel far below the oracle tolerance
+    out1 = torch.empty_like(out)
+    ops.call("tag_logmel_fwd", wav.cuda(), B, L, L, window.cuda(), fbc, mr, out1, None)
+    assert (out1 - out).abs().max().item() < 2e-3
+    # float16 waveform (the reference's h5 storage type): identical to widening on the host first
+    wav16 = wav.half()
+    ref16 = O.logmel_db(wav16.float(), window, fb).transpose(1, 2)
+    out16 = torch.empty_like(out)
+    ops.call("tag_logmel_fwd_v2", wav16.cuda(), 2, B, L, L, window.cuda(), fbc, mr, nnz, out16, None)
+    assert (out16.cpu() - ref16).abs().max().item() < 5e-3
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 13, 8, 64, 64), (1, 7, 16, 64, 128), (3, 5, 4, 128, 256)])
 def test_conv3x3_fwd_dgrad_wgrad_fp32(B, H, W, Cin, Cout):
     ops = _ops()

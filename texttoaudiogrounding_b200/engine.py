@@ -46,6 +46,8 @@ class EncoderWeights:
     # optional map of ready-made GEMM operands (FusedTrainStep refreshes them with ONE batched launch per
     # step): ("f", i) / ("t", i) forward / dgrad operand of conv i, "fc", "ih", "fc_t", "ih_t"
     prepared: Optional[dict] = None
+    # number of non-zero-support filterbank entries, sum(hi - lo) of mel_range (host int; 0 = unknown)
+    mel_nnz: int = 0
 
 
 @dataclass
@@ -92,6 +94,14 @@ def _operand(Wt: EncoderWeights, key, make):
     return make()
 
 
+LOGMEL_FB_CAP = 2048      # FB_CAP of csrc/frontend.cu
+
+
+def mel_nnz(mel_range: torch.Tensor) -> int:
+    """sum of the filter supports (one host read, done once per model/device)."""
+    return int((mel_range[:, 1] - mel_range[:, 0]).clamp_min(0).sum().item())
+
+
 def compute_mel_range(fb: torch.Tensor) -> torch.Tensor:
     """[64,2] int32 (lo, hi) support of each mel filter, derived from the fb buffer."""
     nz = fb != 0
@@ -109,7 +119,7 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
                     seed_dev: Optional[torch.Tensor] = None,
                     stages: Optional[dict] = None) -> Tuple[torch.Tensor, Optional[EncoderCtx]]:
     """wav [B, L] fp32 (cuda) -> embedding [B, T', 512] fp32.  ``save`` keeps what backward needs."""
-    assert wav.is_cuda and wav.dtype == torch.float32 and wav.dim() == 2
+    assert wav.is_cuda and wav.dtype in (torch.float32, torch.float16) and wav.dim() == 2
     if wav.stride(1) != 1:
         wav = wav.contiguous()
     dev = wav.device
@@ -132,7 +142,16 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
     # ---- log-mel + bn0
     db = torch.empty(B, T0, N_MELS, **f32)
     st = torch.zeros(2 * N_MELS, device=dev, dtype=torch.float64) if bn_training else None
-    call("tag_logmel_fwd", wav, B, L, wav.stride(0), Wt.window, Wt.fb, Wt.mel_range, db, st)
+    ops.annotate(f"logmel B={B} L={L}", 0.0, wav.numel() * wav.element_size() + db.numel() * 4.0)
+    if 0 < Wt.mel_nnz <= LOGMEL_FB_CAP:
+        # compact (triangular) filterbank: warp-per-frame-pair kernel; fp32 or fp16 waveform (the reference stores
+        # waveforms as float16 in its h5 files, utils/data/pack_waveform.py:46-52)
+        call("tag_logmel_fwd_v2", wav, 0 if wav.dtype == torch.float32 else 2, B, L, wav.stride(0), Wt.window, Wt.fb,
+             Wt.mel_range, Wt.mel_nnz, db, st)
+    else:
+        if wav.dtype != torch.float32:
+            raise ops._lib.TagError("the dense-filterbank log-mel kernel takes fp32 waveforms")
+        call("tag_logmel_fwd", wav, B, L, wav.stride(0), Wt.window, Wt.fb, Wt.mel_range, db, st)
     aux0 = bn_aux(N_MELS)
     finalize(st, B * T0, N_MELS, 0, aux0)
     x0 = torch.empty(B, T0, N_MELS, **act)

@@ -149,6 +149,7 @@ class Cnn8Rnn(nn.Module, LoadPretrainedMixin):
         self._stages = None               # set to a dict to capture stage tensors (tests)
         self._call_count = 0
         self._mel_range = None
+        self._mel_nnz = 0
 
         if pretrained is not None:
             self.load_pretrained(pretrained, output_fn)
@@ -177,6 +178,7 @@ class Cnn8Rnn(nn.Module, LoadPretrainedMixin):
 
     def _load_from_state_dict(self, *args, **kwargs):
         self._mel_range = None
+        self._mel_nnz = 0
         return super()._load_from_state_dict(*args, **kwargs)
 
     # ------------------------------------------------------------------ kernel plumbing
@@ -208,9 +210,10 @@ class Cnn8Rnn(nn.Module, LoadPretrainedMixin):
         fb = self.melspec_extractor.mel_scale.fb
         if self._mel_range is None or self._mel_range.device != fb.device:
             self._mel_range = engine.compute_mel_range(fb)
+            self._mel_nnz = engine.mel_nnz(self._mel_range)
         r = self.rnn
         return engine.EncoderWeights(
-            window=self.melspec_extractor.spectrogram.window, fb=fb, mel_range=self._mel_range,
+            window=self.melspec_extractor.spectrogram.window, fb=fb, mel_range=self._mel_range, mel_nnz=self._mel_nnz,
             bn=[(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var) for bn in self._bns()],
             conv=[_packed_conv(c.weight.data) for c in self._convs()],
             fc_w=self.fc1.weight.data, fc_b=self.fc1.bias.data,
