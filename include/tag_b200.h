@@ -197,6 +197,54 @@ int tag_max_margin_rank(const float* sim, int n, float margin, float lamda1, int
 int tag_embed_token_bwd(const long long* text, const float* d_token, float* d_emb, int B, int N, int D, int vocab,
                         cudaStream_t stream);
 
+/* ---- attention-type heads of the later configurations — SURVEY.md §8f rank 2 (BASELINE.json configs[3]).  All fp32,
+ * E = 512; the dense projections around them are tag_conv_fwd / tag_conv_wgrad with taps = 1.
+ * text_encoder.SelfAttention (models/text_encoder.py:240-268): out[b,0] = cls + pe[0], out[b,1+n] = emb[text[b,n]] +
+ * pe[1+n], then dropout (PositionalEncoding, :128-146).  bwd accumulates into d_emb [vocab,E] and d_cls [E]. */
+int tag_text_assemble_fwd(const long long* text, const float* emb, const float* cls, const float* pe, float* out,
+                          int B, int N, int E, int vocab, float dropout_p, uint64_t seed, const uint64_t* seed_dev,
+                          cudaStream_t stream);
+int tag_text_assemble_bwd(const long long* text, const float* d_out, float* d_emb, float* d_cls, int B, int N, int E,
+                          int vocab, float dropout_p, uint64_t seed, const uint64_t* seed_dev, cudaStream_t stream);
+/* scaled-dot-product core of nn.MultiheadAttention (text_encoder.py:266, match.py:66-73,82): q [B,Lq,E], k/v [B,Lk,E]
+ * already projected; keys n >= key_len[b] are masked (key_padding_mask; NULL = none); softmax; dropout on the
+ * probabilities; out [B,Lq,E] (heads concatenated).  probs [B,heads,Lq,Lk] is kept for backward.  Lk <= 128,
+ * E / heads in {32, 64, 128}. */
+int tag_mha_core_fwd(const float* q, const float* k, const float* v, const long long* key_len, float* out,
+                     float* probs, int B, int Lq, int Lk, int E, int heads, float dropout_p, uint64_t seed,
+                     const uint64_t* seed_dev, cudaStream_t stream);
+int tag_mha_core_bwd(const float* d_out, const float* q, const float* k, const float* v, const float* probs,
+                     const long long* key_len, float* dq, float* dk, float* dv, int B, int Lq, int Lk, int E,
+                     int heads, float dropout_p, uint64_t seed, const uint64_t* seed_dev, cudaStream_t stream);
+/* cross_encoder.Seq2SeqAttention (models/cross_encoder.py:12-42) with h2attn split into its query / key halves:
+ * hq = query W_q^T [B,T,E], hk = kv W_k^T + b [B,N,E]; score = sum_a v[a] tanh(hq + hk), -1e10 where t >= q_len[b] or
+ * n >= kv_len[b], softmax over n, out = attn x kv.  N <= 32 (backward: N <= 24).  bwd: d_hq overwritten; d_hk, d_kv,
+ * d_v accumulated (pre-zeroed). */
+int tag_additive_attn_fwd(const float* hq, const float* hk, const float* v, const float* kv, const long long* q_len,
+                          const long long* kv_len, float* attn, float* out, int B, int T, int N, int E,
+                          cudaStream_t stream);
+int tag_additive_attn_bwd(const float* d_out, const float* hq, const float* hk, const float* v, const float* kv,
+                          const float* attn, const long long* q_len, const long long* kv_len, float* d_hq, float* d_hk,
+                          float* d_v, float* d_kv, int B, int T, int N, int E, cudaStream_t stream);
+/* cross_encoder.CrossGating (models/cross_encoder.py:45-57): out = x * sigmoid(z) */
+int tag_sigmoid_gate_fwd(const float* x, const float* z, float* out, long n, cudaStream_t stream);
+int tag_sigmoid_gate_bwd(const float* d_out, const float* x, const float* z, float* dx, float* dz, long n,
+                         cudaStream_t stream);
+/* match.DotProduct(text_level="token") on per-frame text embeddings (models/match.py:43-60): a, x [R,E] -> sim [R] */
+int tag_rowdot_sigmoid_fwd(const float* a, const float* x, float* sim, long R, int E, float scale, cudaStream_t stream);
+int tag_rowdot_sigmoid_bwd(const float* d_sim, const float* sim, const float* a, const float* x, float* da, float* dx,
+                           long R, int E, float scale, cudaStream_t stream);
+/* tail of match.CrossAttention.forward (models/match.py:84-88): sigmoid(Linear_{E->1}(LayerNorm(audio +
+ * dropout(attn_out)))).  stat [R,2] keeps (mean, rstd).  bwd: d_audio, d_attn overwritten; d_gamma, d_beta, d_w [E],
+ * d_bias [1] accumulated (pre-zeroed). */
+int tag_ln_linear_sigmoid_fwd(const float* audio, const float* attn_out, const float* gamma, const float* beta,
+                              const float* w, const float* bias, float* prob, float* stat, long R, int E, float eps,
+                              float dropout_p, uint64_t seed, const uint64_t* seed_dev, cudaStream_t stream);
+int tag_ln_linear_sigmoid_bwd(const float* d_prob, const float* prob, const float* audio, const float* attn_out,
+                              const float* gamma, const float* beta, const float* w, const float* stat, float* d_audio,
+                              float* d_attn, float* d_gamma, float* d_beta, float* d_w, float* d_bias, long R, int E,
+                              float dropout_p, uint64_t seed, const uint64_t* seed_dev, cudaStream_t stream);
+
 /* ---- optimizer step — clip_grad_norm_ + Adam, python_scripts/training/run_strong.py:143-145 */
 int tag_sumsq(const float* g, long n, double* out, cudaStream_t stream);
 int tag_clip_adam(float* p, const float* g, float* m, float* v, long n, const double* sumsq,

@@ -641,3 +641,163 @@ def align_forward(sd, input_dict, level: str = "phrase", audio_pool: str = "mean
     sim_matrix = align_dot_product(a["embedding"], text_emb, scaled)
     sim = sim_pooling(sim_matrix, a["length"], text_len, audio_pool, text_pool)
     return {"sim": sim, "sim_matrix": sim_matrix, "length": a["length"]}
+
+
+# =====================================================================================================
+# SURVEY.md §8f rank 2 — attention-type heads (BASELINE.json configs[3]).  Reference sites restated here:
+#   * PositionalEncoding / SelfAttention ... models/text_encoder.py:128-146, 240-268
+#   * nn.MultiheadAttention ................ torch 2.11 (packed in_proj, batch_first, key_padding_mask), used at
+#                                            text_encoder.py:258-266 and match.py:66-73,82
+#   * match.CrossAttention ................. models/match.py:63-88
+#   * DotProduct(text_level="token") ....... models/match.py:43-60
+#   * Seq2SeqAttention / CrossGating / CrossAttentionGating ... models/cross_encoder.py:5-79
+#   * BiEncoder.forward with a cross encoder ... models/audio_text_model.py:58-98
+HEADS = 8
+
+
+def positional_table(max_len: int = 100, d_model: int = EMBED) -> torch.Tensor:
+    """models/text_encoder.py:132-140 -> [1, max_len, d_model]."""
+    pe = torch.zeros(max_len, d_model)
+    position = torch.arange(0, max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * -(math.log(10000.0) / d_model))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe.unsqueeze(0)
+
+
+def attn_state_spec(E: int = EMBED):
+    te, mf, ce = "text_encoder.", "match_fn.", "cross_encoder."
+    return {
+        "selfattn": [(te + "cls_token", (1, 1, E), 0.5), (te + "mha.in_proj_weight", (3 * E, E), None),
+                     (te + "mha.in_proj_bias", (3 * E,), 0.1), (te + "mha.out_proj.weight", (E, E), None),
+                     (te + "mha.out_proj.bias", (E,), 0.1)],
+        "crossattn": [(mf + "attn.in_proj_weight", (3 * E, E), None), (mf + "attn.in_proj_bias", (3 * E,), 0.1),
+                      (mf + "attn.out_proj.weight", (E, E), None), (mf + "attn.out_proj.bias", (E,), 0.1),
+                      (mf + "norm.weight", (E,), "ln_w"), (mf + "norm.bias", (E,), 0.2),
+                      (mf + "linear.weight", (1, E), 0.3), (mf + "linear.bias", (1,), 0.1)],
+        "gating": [(ce + "attn.h2attn.weight", (E, 2 * E), None), (ce + "attn.h2attn.bias", (E,), 0.1),
+                   (ce + "attn.v", (E,), "randn"), (ce + "gating.fc_u.weight", (E, E), None),
+                   (ce + "gating.fc_u.bias", (E,), 0.1), (ce + "gating.fc_s.weight", (E, E), None),
+                   (ce + "gating.fc_s.bias", (E,), 0.1)],
+    }
+
+
+def synth_attn_state(seed: int, parts=("selfattn", "crossattn", "gating"), gain: float = 1.0):
+    """Deterministic weights for the attention-type heads (Xavier-uniform matrices scaled by ``gain``, small
+    non-zero biases so no term is vacuous).  ``text_encoder.pe.pe`` is the sinusoidal buffer."""
+    sd = {}
+    spec = attn_state_spec()
+    idx = 0
+    for part in ("selfattn", "crossattn", "gating"):
+        for key, shape, kind in spec[part]:
+            idx += 1
+            if part not in parts:
+                continue
+            g = torch.Generator().manual_seed(seed * 7919 + idx)
+            if kind is None:
+                a = gain * math.sqrt(6.0 / (shape[0] + shape[1]))
+                t = (torch.rand(shape, generator=g) * 2 - 1) * a
+            elif kind == "ln_w":
+                t = 0.75 + 0.5 * torch.rand(shape, generator=g)
+            elif kind == "randn":
+                t = torch.randn(shape, generator=g)
+            else:
+                t = (torch.rand(shape, generator=g) * 2 - 1) * kind
+            sd[key] = t
+    if "selfattn" in parts:
+        sd["text_encoder.pe.pe"] = positional_table()
+    return sd
+
+
+def attn_case_state(variant: str, seed: int, attn_seed: int, sharpen: float = 20.0):
+    """Weights of one parity case: audio encoder + embedding from synth_state_dict, heads from synth_attn_state.
+    For the "gating" variant the text encoder's out_proj is scaled by 25 so that the scaled dot-product logits
+    span about +-3 instead of +-0.08 (a vacuous comparison on frame_sim otherwise)."""
+    sd = synth_state_dict(seed=seed, sharpen=sharpen, perturb_bn=True)
+    parts = ("selfattn", "crossattn") if variant == "crossattn" else ("selfattn", "gating")
+    sd.update(synth_attn_state(attn_seed, parts))
+    if variant == "gating":
+        sd["text_encoder.mha.out_proj.weight"] = sd["text_encoder.mha.out_proj.weight"] * 25.0
+        sd["text_encoder.mha.out_proj.bias"] = sd["text_encoder.mha.out_proj.bias"] * 25.0
+    return sd
+
+
+def multi_head_attention(xq, xkv, in_w, in_b, out_w, out_b, heads: int, key_len):
+    """nn.MultiheadAttention forward (eval / dropout off): packed in_proj, q scaled by 1/sqrt(dh), keys
+    n >= key_len[b] masked to -inf, softmax, heads concatenated, out_proj."""
+    B, Lq, E = xq.shape
+    Lk = xkv.shape[1]
+    dh = E // heads
+    q = xq @ in_w[:E].t() + in_b[:E]
+    k = xkv @ in_w[E:2 * E].t() + in_b[E:2 * E]
+    v = xkv @ in_w[2 * E:].t() + in_b[2 * E:]
+    q = q.view(B, Lq, heads, dh).transpose(1, 2) / math.sqrt(dh)
+    k = k.view(B, Lk, heads, dh).transpose(1, 2)
+    v = v.view(B, Lk, heads, dh).transpose(1, 2)
+    score = q @ k.transpose(-1, -2)                                    # [B,h,Lq,Lk]
+    mask = ~generate_length_mask(torch.as_tensor(key_len), Lk)         # True = padded
+    score = score.masked_fill(mask[:, None, None, :], float("-inf"))
+    ctx = torch.softmax(score, dim=-1) @ v
+    ctx = ctx.transpose(1, 2).reshape(B, Lq, E)
+    return ctx @ out_w.t() + out_b
+
+
+def self_attention_text_encoder(sd, text, text_len, heads: int = HEADS):
+    """models/text_encoder.py:260-268 (dropout off)."""
+    p = "text_encoder."
+    x = F.embedding(text.long(), sd[p + "embedding.core.weight"])
+    x = torch.cat((sd[p + "cls_token"].expand(x.shape[0], -1, -1), x), dim=1)
+    x = x + sd[p + "pe.pe"][:, :x.size(1)]
+    lens = torch.as_tensor(text_len) + 1
+    x = multi_head_attention(x, x, sd[p + "mha.in_proj_weight"], sd[p + "mha.in_proj_bias"],
+                             sd[p + "mha.out_proj.weight"], sd[p + "mha.out_proj.bias"], heads, lens)
+    return {"token_emb": x[:, 1:], "seq_emb": x[:, 0]}
+
+
+def cross_attention_match(sd, audio, token_emb, text_len, heads: int = HEADS):
+    """models/match.py:76-88 (dropout off)."""
+    p = "match_fn."
+    out = multi_head_attention(audio, token_emb, sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"],
+                               sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"], heads, text_len)
+    out = F.layer_norm(audio + out, (audio.size(-1),), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-5)
+    out = out @ sd[p + "linear.weight"].t() + sd[p + "linear.bias"]
+    return torch.sigmoid(out).squeeze(-1)
+
+
+def cross_attention_gating(sd, audio, token_emb, audio_len, text_len):
+    """models/cross_encoder.py:12-42 (additive attention, written without the [B, T*N, 2E] expansion: h2attn is
+    linear in cat(q, kv)), :52-57 (gating), :67-79."""
+    p = "cross_encoder."
+    B, T, E = audio.shape
+    N = token_emb.shape[1]
+    W, b, v = sd[p + "attn.h2attn.weight"], sd[p + "attn.h2attn.bias"], sd[p + "attn.v"]
+    hq = audio @ W[:, :E].t()
+    hk = token_emb @ W[:, E:].t() + b
+    score = (torch.tanh(hq.unsqueeze(2) + hk.unsqueeze(1)) * v).sum(-1)            # [B,T,N]
+    m1 = generate_length_mask(torch.as_tensor(audio_len), T).unsqueeze(-1)
+    m2 = generate_length_mask(torch.as_tensor(text_len), N).unsqueeze(1)
+    score = score.masked_fill(~m1, -1e10).masked_fill(~m2, -1e10)
+    text_att = torch.softmax(score, dim=-1) @ token_emb                            # [B,T,E]
+    g_u = torch.sigmoid(audio @ sd[p + "gating.fc_u.weight"].t() + sd[p + "gating.fc_u.bias"])
+    s_out = text_att * g_u
+    g_s = torch.sigmoid(text_att @ sd[p + "gating.fc_s.weight"].t() + sd[p + "gating.fc_s.bias"])
+    u_out = audio * g_s
+    return u_out, s_out
+
+
+def attn_biencoder_forward(sd, input_dict, variant: str, training=False, dropout=True, dropout_masks=None,
+                           fast_gru=False):
+    """BiEncoder.forward (models/audio_text_model.py:58-98) for the attention configurations:
+    variant "crossattn": SelfAttention text encoder + match.CrossAttention;
+    variant "gating":    SelfAttention text encoder + CrossAttentionGating + DotProduct(text_level="token").
+    Dropout inside the attention heads is off (parity runs patch F.dropout / use eval for those modules)."""
+    a = cnn8rnn_forward(sd, input_dict["waveform"], input_dict["waveform_len"], training,
+                        dropout_masks, dropout, None, fast_gru)
+    t = self_attention_text_encoder(sd, input_dict["text"], input_dict["text_len"])
+    audio = a["embedding"]
+    if variant == "crossattn":
+        sim = cross_attention_match(sd, audio, t["token_emb"], input_dict["text_len"])
+    else:
+        u, s = cross_attention_gating(sd, audio, t["token_emb"], a["length"], input_dict["text_len"])
+        sim = torch.sigmoid((u * s).sum(-1) / math.sqrt(u.size(-1))).clamp(1e-7, 1.0)     # match.py:43-60, "token"
+    return {"frame_sim": sim, "length": a["length"], "token_emb": t["token_emb"], "seq_emb": t["seq_emb"]}

@@ -21,8 +21,6 @@ class BiEncoder(nn.Module, LoadPretrainedMixin):
         self.text_encoder = text_encoder
         self.match_fn = match_fn
         self.cross_encoder = cross_encoder
-        if cross_encoder is not None:
-            raise NotImplementedError("cross_encoder is outside the cnn8rnn-w2vmean hot path (SURVEY.md §8f)")
         if audio_encoder.embed_dim != text_encoder.embed_dim or add_proj:
             raise NotImplementedError("audio_proj/text_proj (add_proj or mismatched embed dims) are "
                                       "outside the cnn8rnn-w2vmean hot path (SURVEY.md §8f)")
@@ -49,6 +47,8 @@ class BiEncoder(nn.Module, LoadPretrainedMixin):
                         "audio_len": audio_output["length"]}
         if "text_len" in input_dict:
             forward_dict["text_len"] = input_dict["text_len"]
+        if self.cross_encoder is not None:
+            forward_dict.update(self.cross_encoder(forward_dict))     # audio_emb, text_emb (per-frame tokens)
         frame_sim = self.match_fn(forward_dict)      # [batch_size, max_len]
         length = audio_output["length"]
         return {"frame_sim": frame_sim, "length": length}

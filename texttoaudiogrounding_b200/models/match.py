@@ -9,6 +9,8 @@ import torch
 import torch.nn as nn
 
 from ..ops import call
+from . import nn_ops
+from .utils import lens_to_device
 
 
 class _DotSigmoidFunction(torch.autograd.Function):
@@ -73,15 +75,22 @@ class DotProduct(nn.Module):
     def forward(self, input_dict):
         audio = input_dict["audio_emb"]  # [bs, n_seg, dim]
         text = input_dict["text_emb"]
-        if self.text_level == "seq":
-            text = text["seq_emb"]      # [bs, dim]
-        else:
-            raise NotImplementedError("text_level='token' is outside the cnn8rnn-w2vmean hot path")
         if self.l2norm:
             raise NotImplementedError("l2norm=True is outside the cnn8rnn-w2vmean hot path")
         if not audio.is_cuda:
             raise RuntimeError("DotProduct (B200) needs CUDA tensors: there is no CPU fallback")
         scale = 1.0 / math.sqrt(audio.size(-1)) if self.scale else 1.0
+        if self.text_level == "seq":
+            text = text["seq_emb"]      # [bs, dim]
+        elif self.text_level == "token":
+            # per-frame text embeddings from a cross encoder: [bs, n_seg, dim] against [bs, n_seg, dim]
+            text = text["token_emb"]
+            if text.shape != audio.shape:
+                raise RuntimeError(f"The size of tensor a {tuple(audio.shape)} must match the size of tensor b "
+                                   f"{tuple(text.shape)}")
+            return nn_ops.rowdot_sigmoid(audio, text, scale)
+        else:
+            raise KeyError(self.text_level)
         return _DotSigmoidFunction.apply(audio.float().contiguous(), text.float().contiguous(), scale)
 
     def forward_multi(self, audio: torch.Tensor, seq: torch.Tensor) -> torch.Tensor:
@@ -96,3 +105,30 @@ class DotProduct(nn.Module):
         chunks = [_MultiDotSigmoidFunction.apply(audio, seq[:, i:i + MULTI_MAX_PHRASES].contiguous(), scale)
                   for i in range(0, seq.shape[1], MULTI_MAX_PHRASES)]
         return chunks[0] if len(chunks) == 1 else torch.cat(chunks, dim=2)
+
+
+class CrossAttention(nn.Module):
+    """Cross-attention match head — mirror of reference models/match.py:63-88: every audio frame attends over the
+    text tokens (nn.MultiheadAttention with key padding mask), then residual + dropout -> LayerNorm -> Linear(E, 1)
+    -> sigmoid.  Same constructor and state-dict keys; the modules hold the parameters only."""
+
+    def __init__(self, embed_dim, num_heads, dropout, kvdim=None) -> None:
+        super().__init__()
+        if kvdim is not None and kvdim != embed_dim:
+            raise NotImplementedError("CrossAttention (B200): kvdim must equal embed_dim (packed in_proj)")
+        self.attn = nn.MultiheadAttention(embed_dim, num_heads, dropout, batch_first=True, kdim=kvdim, vdim=kvdim)
+        self.dropout = nn.Dropout(dropout)
+        self.norm = nn.LayerNorm(embed_dim)
+        self.linear = nn.Linear(embed_dim, 1)
+
+    def forward(self, input_dict):
+        audio = input_dict["audio_emb"]  # [bs, n_seg, dim]
+        text = input_dict["text_emb"]["token_emb"]
+        if not audio.is_cuda:
+            raise RuntimeError("CrossAttention (B200) needs CUDA tensors: there is no CPU fallback")
+        text_len = lens_to_device(input_dict["text_len"], audio.device).contiguous()
+        audio = audio.float().contiguous()
+        out = nn_ops.multi_head_attention(self.attn, audio, text.float().contiguous(), text.float().contiguous(),
+                                          text_len, self.training)
+        p = self.dropout.p if self.training else 0.0
+        return nn_ops.ln_linear_sigmoid(audio, out, self.norm, self.linear, p)

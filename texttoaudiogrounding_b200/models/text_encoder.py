@@ -9,7 +9,10 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+import math
+
 from ..ops import call
+from . import nn_ops
 from .utils import init_weights, lens_to_device
 
 
@@ -83,3 +86,71 @@ class EmbeddingAgg(nn.Module):
         lens = lens_to_device(input_dict["text_len"], weight.device).contiguous()
         token_emb, seq_emb = _EmbedMeanFunction.apply(weight, tokens, lens)
         return {"token_emb": token_emb, "seq_emb": seq_emb}
+
+
+class PositionalEncoding(nn.Module):
+    """Sinusoidal table of reference models/text_encoder.py:128-146 (buffer ``pe`` [1, max_len, d_model]); the
+    addition and its dropout are fused into the text-assemble kernel of SelfAttention."""
+
+    def __init__(self, d_model, dropout, max_len=100):
+        super().__init__()
+        self.dropout = nn.Dropout(p=dropout)
+        pe = torch.zeros(max_len, d_model)
+        position = torch.arange(0, max_len).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2) * -(math.log(10000.0) / d_model))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe.unsqueeze(0))
+
+
+class _TextAssembleFunction(torch.autograd.Function):
+    """x[b] = dropout([cls; emb[text[b]]] + pe[:N+1])"""
+
+    @staticmethod
+    def forward(ctx, emb, cls, pe, tokens, dropout_p, seed):
+        B, N = tokens.shape
+        V, E = emb.shape
+        out = torch.empty(B, N + 1, E, device=emb.device, dtype=torch.float32)
+        call("tag_text_assemble_fwd", tokens, emb, cls, pe, out, B, N, E, V, float(dropout_p), seed, None)
+        ctx.save_for_backward(tokens)
+        ctx.cfg = (V, E, float(dropout_p), seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (tokens,) = ctx.saved_tensors
+        V, E, p, seed = ctx.cfg
+        B, N = tokens.shape
+        d_emb = torch.zeros(V, E, device=d_out.device, dtype=torch.float32)
+        d_cls = torch.zeros(1, 1, E, device=d_out.device, dtype=torch.float32)
+        call("tag_text_assemble_bwd", tokens, d_out.contiguous(), d_emb, d_cls, B, N, E, V, p, seed, None)
+        return d_emb, d_cls, None, None, None, None
+
+
+class SelfAttention(nn.Module):
+    """Transformer text encoder — mirror of reference models/text_encoder.py:240-268: word embedding with a [CLS]
+    token and sinusoidal positions, one nn.MultiheadAttention layer with the padding mask; ``seq_emb`` is the [CLS]
+    output, ``token_emb`` the rest.  Same constructor, parameters and state-dict keys (the nn.MultiheadAttention
+    module holds the weights; its forward is replaced by csrc/attn.cu + the fp32 GEMMs)."""
+
+    def __init__(self, vocab_size, embed_dim, num_heads, dropout=0.2, pretrained_embedding=None,
+                 freeze_embedding=False) -> None:
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.embedding = EmbeddingLayer(vocab_size, embed_dim, pretrained_embedding, freeze_embedding)
+        self.pe = PositionalEncoding(embed_dim, dropout)
+        self.mha = nn.MultiheadAttention(embed_dim, num_heads, dropout, batch_first=True)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+
+    def forward(self, input_dict):
+        weight = self.embedding.core.weight
+        if not weight.is_cuda:
+            raise RuntimeError("SelfAttention (B200) needs CUDA tensors: there is no CPU fallback")
+        tokens = input_dict["text"].long().to(weight.device).contiguous()
+        if tokens.shape[1] + 1 > self.pe.pe.shape[1]:
+            raise RuntimeError(f"text longer than the positional table ({self.pe.pe.shape[1] - 1} tokens)")
+        p = self.pe.dropout.p if self.training else 0.0
+        x = _TextAssembleFunction.apply(weight, self.cls_token, self.pe.pe, tokens, p, nn_ops.next_seed())
+        lens = (lens_to_device(input_dict["text_len"], weight.device) + 1).contiguous()
+        x = nn_ops.multi_head_attention(self.mha, x, x, x, lens, self.training)
+        return {"token_emb": x[:, 1:], "seq_emb": x[:, 0]}
