@@ -97,9 +97,22 @@ def test_run_strong_dialect_config_instantiates_b200_classes(tmp_path):
     loss = train_util.init_obj_from_str(config["loss"])
     opt = train_util.init_obj_from_str(config["optimizer"], params=model.parameters())
     assert type(loss).__name__ == "FrameBceLoss" and opt.defaults["lr"] == 0.01
-    with pytest.raises(NotImplementedError):
+    # no CPU fallback: the mirrored modules refuse host tensors instead of computing with torch ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         train_util.init_obj_from_str({"type": "models.match.DotProduct", "args": {"text_level": "token"}})(
             {"audio_emb": torch.zeros(1, 2, 4), "text_emb": {"token_emb": torch.zeros(1, 2, 4)}})
+    with pytest.raises(NotImplementedError):
+        train_util.init_obj_from_str({"type": "models.match.DotProduct", "args": {"l2norm": True}})(
+            {"audio_emb": torch.zeros(1, 2, 4), "text_emb": {"seq_emb": torch.zeros(1, 4)}})
+    # the later-config components resolve through the same registry
+    for typ, args in (("models.text_encoder.SelfAttention", {"vocab_size": 50, "embed_dim": 512, "num_heads": 8}),
+                      ("models.match.CrossAttention", {"embed_dim": 512, "num_heads": 8, "dropout": 0.2}),
+                      ("models.cross_encoder.CrossAttentionGating", {"embed_dim": 512}),
+                      ("models.align.DotProduct", {"l2norm": False, "scaled": False}),
+                      ("models.sim_pooling.AudioMeanTextMean", {}),
+                      ("losses.MaxMarginRankingLoss", {"margin": 1})):
+        obj = train_util.init_obj_from_str({"type": typ, "args": args})
+        assert type(obj).__module__.startswith("texttoaudiogrounding_b200."), typ
 
 
 def test_freeze_and_train_mode_semantics():

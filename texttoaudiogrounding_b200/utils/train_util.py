@@ -97,6 +97,10 @@ _ALIASES = {
     "models.audio_text_model": "texttoaudiogrounding_b200.models.audio_text_model",
     "models.utils": "texttoaudiogrounding_b200.models.utils",
     "models.base": "texttoaudiogrounding_b200.models.base",
+    "models.align": "texttoaudiogrounding_b200.models.align",
+    "models.sim_pooling": "texttoaudiogrounding_b200.models.sim_pooling",
+    "models.cross_encoder": "texttoaudiogrounding_b200.models.cross_encoder",
+    "models.hf_modeling_grounding": "texttoaudiogrounding_b200.models.hf_modeling_grounding",
     "losses": "texttoaudiogrounding_b200.losses",
 }
 
