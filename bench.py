@@ -27,6 +27,8 @@ N_SAMPLES = 320000
 N_TOKENS = 8
 FWD_GFLOP_PER_CLIP = 33.83          # conv 33.11 + fc1 0.131 + GRU 0.590
 TRAIN_GFLOP_PER_CLIP = 3 * FWD_GFLOP_PER_CLIP
+WORKLOAD = ("cnn8rnn-w2vmean full train step (fwd+bwd+clip+Adam), bs={B}/GPU, 10 s @32 kHz clips, 8-token phrases "
+            "(BASELINE.json configs[2])")
 
 
 def cpu_reference_step_time(batch_size: int, n_samples: int, steps: int, warmup: int):
@@ -60,7 +62,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cnn8rnn-w2vmean train step, bs=64/GPU, 10 s @32 kHz clips, 8-token phrases"},
+        "config": {"workload": WORKLOAD.format(B=BATCH), "global_batch": BATCH * args.gpus,
+                   "parallelism": f"dp{args.gpus}"},
         "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -68,56 +71,101 @@ def run_reference(args):
 
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed regions.  NVML from a thread of this process (20 Hz): an
+    `nvidia-smi -lms` child polling at that rate slowed the host-side API calls of the end-to-end loop by 5-20 %;
+    nvidia-smi remains the fallback when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.rows = []          # (sm_mhz, max_mhz, set of reasons)
         self.proc = None
+        self.thread = None
+        self._stop = threading.Event()
+        self.source = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if visible:
+                ids = [v for v in visible.split(",") if v.strip() != ""]
+                if idx < len(ids) and ids[idx].strip().isdigit():
+                    idx = int(ids[idx])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = (("hw_slowdown", pynvml.nvmlClocksEventReasonHwSlowdown),
+                     ("hw_thermal_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwThermalSlowdown),
+                     ("sw_power_cap", pynvml.nvmlClocksEventReasonSwPowerCap))
+
+            def run():
+                while not self._stop.is_set():
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        self.rows.append((float(sm), float(mx), {n for n, bit in names if mask & bit}))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.05)
+
+            self.thread = threading.Thread(target=run, daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            self.source = "nvidia-smi"
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+            r = [c.strip() for c in line.split(",")]
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                reasons = {name for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6),
+                                                  ("sw_thermal_slowdown", 7), ("sw_power_cap", 8))
+                           if len(r) > col and r[col].lower().startswith("active")}
+                self.rows.append((float(r[1]), float(r[2]), reasons))
             except Exception:
                 continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
-                              ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
+
+    def stop(self):
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(r[0] for r in self.rows)
+        mx = [r[1] for r in self.rows]
+        reasons = set()
+        for r in self.rows:
+            reasons |= r[2]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--wav-fp16", action="store_true",
+                    help="host waveforms in float16 (the reference's h5 storage type): halves the H2D bytes")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -149,7 +197,8 @@ def main():
 
     g = torch.Generator().manual_seed(100 + rank)
     host = {
-        "waveform": (0.1 * torch.randn(B, N_SAMPLES, generator=g)).pin_memory(),
+        "waveform": (0.1 * torch.randn(B, N_SAMPLES, generator=g)).to(
+            torch.float16 if args.wav_fp16 else torch.float32).pin_memory(),
         "waveform_len": torch.full((B,), N_SAMPLES, dtype=torch.long).pin_memory(),
         "text": torch.randint(2, 5221, (B, N_TOKENS), generator=g).pin_memory(),
         "text_len": torch.full((B,), N_TOKENS, dtype=torch.long).pin_memory(),
@@ -192,13 +241,19 @@ def main():
     f0.record()
     last = 0.0
     # two pinned host batches alternate; the copy of step i+1's inputs is started (prefetch) right after step i
-    # is queued, so it overlaps step i's kernels; every step still uploads its own inputs and reads its own loss
+    # is queued, so it overlaps step i's kernels; every step uploads its own inputs and its own loss is copied to
+    # the host and read there — one step late, so the host never stalls the queue (software pipelining of the
+    # reference's synchronous loss.item())
     ts.prefetch(hosts[0])
+    pending = None
     for i in range(args.steps):
-        loss = ts.step(hosts[i % 2])
+        handle = ts.step_async(hosts[i % 2])      # queues the step and the D2H copy of ITS loss (pinned slot)
         if i + 1 < args.steps:
             ts.prefetch(hosts[(i + 1) % 2])
-        last = loss.item()                    # D2H read of the step's loss
+        if pending is not None:
+            last = pending.result()               # host read of step i-1's loss while step i runs
+        pending = handle
+    last = pending.result()                       # every step's loss has been read on the host by here
     f1.record()
     barrier()
     ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3 * 0.0)
@@ -283,11 +338,11 @@ def main():
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"cnn8rnn-w2vmean full train step (fwd+bwd+clip+Adam), bs={B}/GPU, "
-                                   "10 s @32 kHz clips, 8-token phrases (BASELINE.json configs[2])",
+            "config": {"workload": WORKLOAD.format(B=B),
                        "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set (>5 GB of activations) is far larger than the 126 MB L2",
-                       "cuda_graph": ts.use_graph, "dropout": True},
+                       "cuda_graph": ts.use_graph, "dropout": True,
+                       "waveform_dtype": "f16" if args.wav_fp16 else "f32"},
             "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,

@@ -59,6 +59,17 @@ def train_step(model: nn.Module, batch: Dict, optimizer: torch.optim.Optimizer, 
     return loss, total_norm
 
 
+class LossHandle:
+    """Pinned host slot + the event that marks its device->host copy complete."""
+
+    def __init__(self, slot: torch.Tensor, event: torch.cuda.Event):
+        self.slot, self.event = slot, event
+
+    def result(self) -> float:
+        self.event.synchronize()
+        return float(self.slot)
+
+
 class FusedTrainStep:
     """Flat-buffer, CUDA-graph-captured train step for BiEncoder(Cnn8Rnn, EmbeddingAgg, DotProduct)."""
 
@@ -83,6 +94,11 @@ class FusedTrainStep:
         self._staging = None
         self._prefetched = None
         self._calls = 0
+        # BatchNorm's num_batches_tracked (an int64 bookkeeping buffer no kernel reads) is counted on the host and
+        # written back by flush_counters() / before state_dict(): nine 1-element kernels per step otherwise
+        self._nbt_pending = 0
+        self._loss_slots = None
+        model.register_state_dict_pre_hook(lambda *a, **k: self.flush_counters())
         # weight-gradient GEMMs on a second stream (TAG_B200_OVERLAP=1)
         self.side_stream = torch.cuda.Stream(self.device) if os.environ.get("TAG_B200_OVERLAP", "0") == "1" else None
 
@@ -211,15 +227,17 @@ class FusedTrainStep:
         length = torch.clamp((length // engine.HOP + 1) // 4, 1, trunc)      # run_strong.py:107-118
         src = {"waveform": wav, "text": batch["text"],
                "text_len": torch.as_tensor(batch["text_len"]).to(torch.long), "label": label, "length": length}
-        key = (B, L, batch["text"].shape[1], label.shape[1])
+        # float16 waveforms (the reference's h5 storage type) are uploaded as they are and widened by the frontend
+        wdt = torch.float16 if wav.dtype == torch.float16 else torch.float32
+        key = (B, L, batch["text"].shape[1], label.shape[1], wdt)
         return key, src
 
     def _alloc_inputs(self, key):
-        B, L, N, Tl = key
+        B, L, N, Tl, wdt = key
         dev = self.device
         return {
             "key": key,
-            "waveform": torch.empty(B, L, device=dev, dtype=torch.float32),
+            "waveform": torch.empty(B, L, device=dev, dtype=wdt),
             "text": torch.empty(B, N, device=dev, dtype=torch.long),
             "text_len": torch.empty(B, device=dev, dtype=torch.long),
             "label": torch.empty(B, Tl, device=dev, dtype=torch.float32),
@@ -266,15 +284,36 @@ class FusedTrainStep:
             self._prefetched = None
         return s
 
+    def flush_counters(self) -> None:
+        """Write the host-side step count into the BatchNorm ``num_batches_tracked`` buffers."""
+        if self._nbt_pending:
+            for bn in self.enc._bns():
+                if bn.training and bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += self._nbt_pending
+            self._nbt_pending = 0
+
+    def step_async(self, batch: Optional[Dict]) -> "LossHandle":
+        """``step`` + a non-blocking device->host copy of this step's loss into a pinned slot.  The returned handle's
+        ``result()`` waits for that copy only, so a training loop can queue step i+1 before it reads the loss of
+        step i (the reference reads ``loss.item()`` synchronously, run_strong.py:147)."""
+        if self._loss_slots is None:
+            self._loss_slots = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._loss_idx = 0
+        loss = self.step(batch)
+        slot = self._loss_slots[self._loss_idx % len(self._loss_slots)]
+        self._loss_idx += 1
+        slot.copy_(loss, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return LossHandle(slot, ev)
+
     def step(self, batch: Optional[Dict]) -> torch.Tensor:
         """One train step on ``batch`` (collate schema; host or device tensors).  Returns the
         device scalar holding the loss of this step.  ``batch=None`` re-uses the inputs already
         resident in the static device buffers (device-only timing)."""
         s = self._static if batch is None else self._prepare_static(batch)
         if self.enc.training:
-            for bn in self.enc._bns():
-                if bn.training:
-                    bn.num_batches_tracked += 1
+            self._nbt_pending += 1
         self._calls += 1
         if not self.use_graph or self._calls == 1:
             # the first step runs eagerly (sets kernel attributes, primes the allocator)
