@@ -190,6 +190,19 @@ int tag_align_text_pool_fwd(const float* colpool, const long long* text_len, int
                             int N, int Cpad, cudaStream_t stream);
 int tag_align_text_pool_bwd(const float* d_out, const float* colpool, const long long* text_len, int t_mode,
                             float* d_colpool, int Ba, int Bt, int N, int Cpad, cudaStream_t stream);
+/* Tensor-core route of the same path for large batches: the logits [Ba*T, Cpad] (Cpad a multiple of 128) come from one
+ * split-bf16 tcgen05 GEMM (tag_split_bf16x3 + tag_conv_tc_fwd); _fwd applies sigmoid / clamp / frame pooling, _bwd
+ * writes the logit gradient as split-bf16 GEMM operands: g_kcat [Ba*T][3*Cpad] and g_planes [2][Ba*T][Cpad]. */
+int tag_align_logits_fwd(const float* logits, const long long* audio_len, int a_mode, float* sim_matrix,
+                         float* colpool, float* aux, int Ba, int T, int Bt, int N, int Cpad, float scale,
+                         cudaStream_t stream);
+int tag_align_logits_bwd(const float* logits, const long long* audio_len, int a_mode, const float* d_colpool,
+                         const float* colpool, const float* aux, void* g_kcat, void* g_planes, int Ba, int T,
+                         int Cpad, float scale, cudaStream_t stream);
+/* fp32 -> split-bf16 GEMM operands (x = hi + lo, 16 mantissa bits): mode 0 -> [rows][hi|hi|lo] (3K per row),
+ * mode 1 -> [rows][hi|lo|hi], mode 2 -> planes [2][rows][K].  transpose != 0: `in` is [K][rows].  A mode-0 operand times
+ * a mode-1 operand in ONE bf16 tensor-core GEMM of depth 3K gives the fp32 product to ~2^-16 relative. */
+int tag_split_bf16x3(const float* in, void* out, long rows, int K, int mode, int transpose, cudaStream_t stream);
 /* MaxMarginRankingLoss (losses.py:226-264) on sim [n, n]: loss (scalar) and d(loss)/d(sim) in one launch */
 int tag_max_margin_rank(const float* sim, int n, float margin, float lamda1, int fix_norm, float* loss,
                         float* d_sim, cudaStream_t stream);

@@ -82,7 +82,8 @@ def _gen(seed):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(POOLINGS))
-@pytest.mark.parametrize("B,T,N,scaled", [(3, 37, 5, True), (4, 50, 6, False), (2, 250, 8, True), (9, 13, 9, True)])
+@pytest.mark.parametrize("B,T,N,scaled", [(3, 37, 5, True), (4, 50, 6, False), (2, 250, 8, True), (9, 13, 9, True),
+                                          (8, 250, 8, False), (12, 101, 11, True)])     # last two: tensor-core route
 def test_fused_align_pool_fwd_bwd_matches_oracle(name, B, T, N, scaled):
     from texttoaudiogrounding_b200.models.align import DotProduct
     import texttoaudiogrounding_b200.models.sim_pooling as sp
@@ -108,7 +109,8 @@ def test_fused_align_pool_fwd_bwd_matches_oracle(name, B, T, N, scaled):
         scale = want.abs().max().item()
         assert (got.cpu() - want).abs().max().item() <= 2e-4 * scale + 1e-7
     m = sim.materialize().cpu()
-    assert (m - O.align_dot_product(a, x, scaled).detach()).abs().max().item() <= 1e-5
+    # >= 1024 rows run the split-bf16 tensor-core GEMM: logits to ~2e-5 relative (|logit| reaches 15 here)
+    assert (m - O.align_dot_product(a, x, scaled).detach()).abs().max().item() <= (1e-4 if B * T >= 1024 else 1e-5)
 
 
 @pytest.mark.gpu

@@ -73,7 +73,8 @@ def _close(got, want, tol=2e-4):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("R,Cin,Cout", [(37, 512, 512), (576, 512, 1536), (9, 1024, 64)])
+@pytest.mark.parametrize("R,Cin,Cout", [(37, 512, 512), (576, 512, 1536), (9, 1024, 64),
+                                        (2000, 512, 512), (1300, 1024, 192)])        # last two: tensor-core route
 def test_linear_fwd_bwd_matches_autograd(R, Cin, Cout):
     from texttoaudiogrounding_b200.models import nn_ops
     x = torch.randn(R, Cin, generator=_gen(1)).requires_grad_(True)
@@ -126,7 +127,7 @@ def test_multi_head_attention_matches_torch(B, Lq, Lk, heads):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,T,N", [(3, 50, 7), (2, 37, 1), (2, 70, 24)])
+@pytest.mark.parametrize("B,T,N", [(3, 50, 7), (2, 37, 1), (2, 70, 24), (5, 250, 7)])
 def test_cross_attention_gating_matches_oracle(B, T, N):
     from texttoaudiogrounding_b200.models.cross_encoder import CrossAttentionGating
     E = 512

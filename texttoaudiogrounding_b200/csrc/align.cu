@@ -190,6 +190,78 @@ align_bwd_kernel(const float* __restrict__ audio, const float* __restrict__ text
     }
 }
 
+
+// ---- tensor-core route (large batches): the logits [Ba*T, Cpad] come from ONE split-bf16 tcgen05 GEMM (split.cu);
+// these kernels do the sigmoid / clamp / frame pooling (fwd) and the logit gradient (bwd) per (clip, text row)
+// column, coalesced across the columns.  grid (Cpad / 128, Ba), 128 threads.
+template <int MODE>
+__global__ void __launch_bounds__(128)
+align_logits_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ audio_len,
+                        float* __restrict__ sim_matrix, float* __restrict__ colpool, float* __restrict__ aux, int T,
+                        int C, int Cpad, int N, int Bt, float scale) {
+    const int i = blockIdx.y, c = blockIdx.x * 128 + threadIdx.x;
+    const long long len_raw = audio_len[i];
+    const int len = (int)(len_raw < T ? len_raw : T);
+    const float* l = logits + (long)i * T * Cpad + c;
+    float r0 = MODE == A_MAX ? -INFINITY : 0.f, r1 = 0.f;
+    const bool write = sim_matrix != nullptr && c < C;
+    const int j = c / N, n = c - j * N;
+    const int t_stop = write ? T : len;
+    for (int t = 0; t < t_stop; ++t) {
+        const float v = prob_of(l[(long)t * Cpad] * scale);
+        if (write) sim_matrix[(((long)i * Bt + j) * T + t) * N + n] = v;
+        if (t < len) {
+            if (MODE == A_MEAN) r0 += v;
+            else if (MODE == A_LINEAR) { r0 += v; r1 = fmaf(v, v, r1); }
+            else if (MODE == A_MAX) { if (v > r0) { r0 = v; r1 = (float)t; } }
+            else { const float e = expf(v); r0 += e; r1 = fmaf(e, v, r1); }
+        }
+    }
+    float out, ax;
+    if (MODE == A_MEAN) { out = r0 / (float)len_raw; ax = 0.f; }
+    else if (MODE == A_LINEAR) { out = r1 / r0; ax = r0; }
+    else if (MODE == A_MAX) { out = r0; ax = r1; }
+    else { out = r1 / r0; ax = r0; }
+    colpool[(long)i * Cpad + c] = out;
+    aux[(long)i * Cpad + c] = ax;
+}
+
+// G = scale * d(loss)/d(logit) written as the split-bf16 operands of the two gradient GEMMs:
+// g_kcat [Ba*T][3*Cpad] = [hi | hi | lo] (d_audio = G x text) and g_planes [2][Ba*T][Cpad] = hi, lo (d_text = G^T x audio)
+template <int MODE>
+__global__ void __launch_bounds__(128)
+align_logits_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ audio_len,
+                        const float* __restrict__ d_colpool, const float* __restrict__ colpool,
+                        const float* __restrict__ aux, bf16* __restrict__ g_kcat, bf16* __restrict__ g_planes, int Ba,
+                        int T, int Cpad, float scale) {
+    const int i = blockIdx.y, c = blockIdx.x * 128 + threadIdx.x;
+    const long long len_raw = audio_len[i];
+    const int len = (int)(len_raw < T ? len_raw : T);
+    const float* l = logits + (long)i * T * Cpad + c;
+    const long o = (long)i * Cpad + c;
+    const float g = d_colpool[o], cp = colpool[o], ax = aux[o];
+    const long plane = (long)Ba * T * Cpad;
+    for (int t = 0; t < T; ++t) {
+        float dl = 0.f;
+        if (t < len && g != 0.f) {
+            const float v = prob_of(l[(long)t * Cpad] * scale);
+            float dp;
+            if (MODE == A_MEAN) dp = g / (float)len_raw;
+            else if (MODE == A_LINEAR) dp = g * (2.0f * v - cp) / ax;
+            else if (MODE == A_MAX) dp = (float)t == ax ? g : 0.f;
+            else dp = g * expf(v) * (1.0f + v - cp) / ax;
+            dl = v > 1e-7f ? dp * v * (1.0f - v) * scale : 0.f;
+        }
+        const bf16 hi = __float2bfloat16_rn(dl);
+        const bf16 lo = __float2bfloat16_rn(dl - __bfloat162float(hi));
+        const long row = (long)i * T + t;
+        bf16* k = g_kcat + row * 3 * Cpad + c;
+        k[0] = hi; k[Cpad] = hi; k[2 * Cpad] = lo;
+        g_planes[row * Cpad + c] = hi;
+        g_planes[plane + row * Cpad + c] = lo;
+    }
+}
+
 // ---- token pooling: out[i, j] from colpool[i, j*N + n], n < text_len[j] (models/sim_pooling.py); one thread per pair
 __global__ void align_text_pool_fwd_kernel(const float* __restrict__ colpool, const long long* __restrict__ text_len,
                                            int mode, float* __restrict__ out, int Ba, int Bt, int N, int Cpad) {
@@ -349,6 +421,35 @@ extern "C" int tag_max_margin_rank(const float* sim, int n, float margin, float 
                                    float* d_sim, cudaStream_t stream) {
     if (n <= 0 || (fix_norm && n < 2)) return TAG_ERR_BAD_ARG;
     max_margin_rank_kernel<<<1, 256, 0, stream>>>(sim, n, margin, lamda1, fix_norm, loss, d_sim);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_align_logits_fwd(const float* logits, const long long* audio_len, int a_mode, float* sim_matrix,
+                                    float* colpool, float* aux, int Ba, int T, int Bt, int N, int Cpad, float scale,
+                                    cudaStream_t stream) {
+    if (Ba <= 0 || T <= 0 || Bt <= 0 || N <= 0 || a_mode < 0 || a_mode > 3) return TAG_ERR_BAD_ARG;
+    if (Cpad % 128 != 0 || Cpad < Bt * N) return TAG_ERR_UNSUPPORTED;
+    const int C = Bt * N;
+    const dim3 grid(Cpad / 128, Ba);
+#define TAG_ALF(M_) align_logits_fwd_kernel<M_><<<grid, 128, 0, stream>>>(logits, audio_len, sim_matrix, colpool, aux, T, C, Cpad, N, Bt, scale)
+    if (a_mode == A_MEAN) TAG_ALF(A_MEAN); else if (a_mode == A_MAX) TAG_ALF(A_MAX);
+    else if (a_mode == A_LINEAR) TAG_ALF(A_LINEAR); else TAG_ALF(A_EXP);
+#undef TAG_ALF
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_align_logits_bwd(const float* logits, const long long* audio_len, int a_mode,
+                                    const float* d_colpool, const float* colpool, const float* aux, void* g_kcat,
+                                    void* g_planes, int Ba, int T, int Cpad, float scale, cudaStream_t stream) {
+    if (Ba <= 0 || T <= 0 || a_mode < 0 || a_mode > 3) return TAG_ERR_BAD_ARG;
+    if (Cpad % 128 != 0) return TAG_ERR_UNSUPPORTED;
+    const dim3 grid(Cpad / 128, Ba);
+#define TAG_ALB(M_) align_logits_bwd_kernel<M_><<<grid, 128, 0, stream>>>(logits, audio_len, d_colpool, colpool, aux, (bf16*)g_kcat, (bf16*)g_planes, Ba, T, Cpad, scale)
+    if (a_mode == A_MEAN) TAG_ALB(A_MEAN); else if (a_mode == A_MAX) TAG_ALB(A_MAX);
+    else if (a_mode == A_LINEAR) TAG_ALB(A_LINEAR); else TAG_ALB(A_EXP);
+#undef TAG_ALB
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }

@@ -23,16 +23,33 @@ def _need_cuda(t: torch.Tensor, what: str) -> None:
         raise RuntimeError(f"{what} (B200) needs CUDA tensors: there is no CPU fallback")
 
 
+TC_MIN_ROWS = 1024      # rows from which F.linear runs as split-bf16 tcgen05 GEMMs (csrc/split.cu)
+
+
+def _bf16(*shape, device):
+    return torch.empty(*shape, device=device, dtype=torch.bfloat16)
+
+
 class _LinearFunction(torch.autograd.Function):
-    """y [R, Cout] = x [R, Cin] W^T + b — F.linear; Cin % 16 == 0, Cout % 64 == 0."""
+    """y [R, Cout] = x [R, Cin] W^T + b — F.linear; Cin % 64 == 0, Cout % 64 == 0.  Small R: fp32 CUDA-core GEMMs
+    (conv_simt.cu).  R >= TC_MIN_ROWS: every operand is split into bf16 hi + lo and the three products
+    hi.hi + hi.lo + lo.hi run as ONE bf16 tcgen05 GEMM of depth 3K with fp32 accumulation (fp32-level accuracy)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         R, Cin = x.shape
         Cout = weight.shape[0]
         y = torch.empty(R, Cout, device=x.device, dtype=torch.float32)
-        ops.annotate(f"fwd M={R} N={Cout} K={Cin}", 2.0 * R * Cout * Cin)
-        call("tag_conv_fwd", x, ops.F32, weight, y, ops.F32, bias, 0, None, 1, R, 1, Cin, Cout, 1)
+        ctx.tc = ops.USE_TC and R >= TC_MIN_ROWS and Cin >= 128
+        if ctx.tc:
+            x_k, w_k = _bf16(R, 3 * Cin, device=x.device), _bf16(Cout, 3 * Cin, device=x.device)
+            call("tag_split_bf16x3", x, x_k, R, Cin, 0, 0)
+            call("tag_split_bf16x3", weight, w_k, Cout, Cin, 1, 0)
+            ops.annotate(f"fwd M={R} N={Cout} K={3 * Cin}", 2.0 * R * Cout * 3 * Cin)
+            call("tag_conv_tc_fwd", x_k, w_k, y, ops.F32, bias, 0, None, 1, R, 1, 3 * Cin, Cout, 1)
+        else:
+            ops.annotate(f"fwd M={R} N={Cout} K={Cin}", 2.0 * R * Cout * Cin)
+            call("tag_conv_fwd", x, ops.F32, weight, y, ops.F32, bias, 0, None, 1, R, 1, Cin, Cout, 1)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         return y
@@ -42,20 +59,38 @@ class _LinearFunction(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         R, Cin = x.shape
         Cout = weight.shape[0]
+        dev = x.device
         dy = dy.contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wt = torch.empty(Cin * Cout, device=x.device, dtype=torch.float32)
-            call("tag_weight_flip_transpose", weight, wt, Cout, Cin, 1)
-            dx = torch.empty(R, Cin, device=x.device, dtype=torch.float32)
-            ops.annotate(f"fwd M={R} N={Cin} K={Cout}", 2.0 * R * Cout * Cin)
-            call("tag_conv_fwd", dy, ops.F32, wt, dx, ops.F32, None, 0, None, 1, R, 1, Cout, Cin, 1)
+            dx = torch.empty(R, Cin, device=dev, dtype=torch.float32)
+            if ctx.tc:
+                dy_k, wt_k = _bf16(R, 3 * Cout, device=dev), _bf16(Cin, 3 * Cout, device=dev)
+                call("tag_split_bf16x3", dy, dy_k, R, Cout, 0, 0)
+                call("tag_split_bf16x3", weight, wt_k, Cin, Cout, 1, 1)           # W^T as the [Cin][3*Cout] operand
+                ops.annotate(f"fwd M={R} N={Cin} K={3 * Cout}", 2.0 * R * Cin * 3 * Cout)
+                call("tag_conv_tc_fwd", dy_k, wt_k, dx, ops.F32, None, 0, None, 1, R, 1, 3 * Cout, Cin, 1)
+            else:
+                wt = torch.empty(Cin * Cout, device=dev, dtype=torch.float32)
+                call("tag_weight_flip_transpose", weight, wt, Cout, Cin, 1)
+                ops.annotate(f"fwd M={R} N={Cin} K={Cout}", 2.0 * R * Cout * Cin)
+                call("tag_conv_fwd", dy, ops.F32, wt, dx, ops.F32, None, 0, None, 1, R, 1, Cout, Cin, 1)
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros(Cout, Cin, device=x.device, dtype=torch.float32)
-            ops.annotate(f"wgrad P={R} Cout={Cout} K={Cin}", 2.0 * R * Cout * Cin)
-            call("tag_conv_wgrad", dy, ops.F32, x, ops.F32, dw, 1, R, 1, Cin, Cout, 1, ops.wgrad_splits(R, Cin, Cout, 1))
+            dw = torch.zeros(Cout, Cin, device=dev, dtype=torch.float32)
+            if ctx.tc:
+                dy_p, x_p = _bf16(2, R, Cout, device=dev), _bf16(2, R, Cin, device=dev)
+                call("tag_split_bf16x3", dy, dy_p, R, Cout, 2, 0)
+                call("tag_split_bf16x3", x, x_p, R, Cin, 2, 0)
+                splits = ops.tc_wgrad_splits(1, R, 1, Cin, Cout, 1)
+                for gh, xh in ((0, 0), (0, 1), (1, 0)):
+                    ops.annotate(f"wgrad P={R} Cout={Cout} K={Cin}", 2.0 * R * Cout * Cin)
+                    call("tag_conv_tc_wgrad", dy_p[gh], x_p[xh], dw, 1, R, 1, Cin, Cout, 1, splits)
+            else:
+                ops.annotate(f"wgrad P={R} Cout={Cout} K={Cin}", 2.0 * R * Cout * Cin)
+                call("tag_conv_wgrad", dy, ops.F32, x, ops.F32, dw, 1, R, 1, Cin, Cout, 1,
+                     ops.wgrad_splits(R, Cin, Cout, 1))
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.zeros(Cout, device=x.device, dtype=torch.float32)
+            db = torch.zeros(Cout, device=dev, dtype=torch.float32)
             call("tag_colsum", dy, ops.F32, R, Cout, db)
         return dx, dw, db
 
