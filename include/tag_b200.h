@@ -258,6 +258,21 @@ int tag_ln_linear_sigmoid_bwd(const float* d_prob, const float* prob, const floa
                               float* d_attn, float* d_gamma, float* d_beta, float* d_w, float* d_bias, long R, int E,
                               float dropout_p, uint64_t seed, const uint64_t* seed_dev, cudaStream_t stream);
 
+/* ---- CLAP text tower (inference; BASELINE.json configs[4]) — transformers ClapTextModel as wired by
+ * LaionClapEncoder (models/text_encoder.py:311-327 == models/hf_modeling_grounding.py:183-199).  Row-wise pieces
+ * only: the dense layers are bf16 tag_conv_tc_fwd GEMMs, the attention core is tag_mha_core_fwd.  E in {512, 768}.
+ * tag_roberta_embed_ln: word[ids] + token_type[0] + position[(#non-pad ids up to l) + pad_idx] -> LayerNorm. */
+int tag_roberta_embed_ln(const long long* ids, const float* word, const float* pos, const float* type0,
+                         const float* gamma, const float* beta, float* out, int B, int L, int E, int vocab,
+                         int max_pos, int pad_idx, float eps, cudaStream_t stream);
+/* out = LayerNorm(a + res) (res may be NULL) */
+int tag_add_layernorm(const float* a, const float* res, const float* gamma, const float* beta, float* out, long rows,
+                      int E, float eps, cudaStream_t stream);
+/* op 0: exact (erf) GELU, op 1: tanh */
+int tag_unary_f32(const float* in, float* out, long n, int op, cudaStream_t stream);
+/* F.normalize(x, dim=-1): rows / max(||row||_2, eps) */
+int tag_l2_normalize(const float* in, float* out, long rows, int E, float eps, cudaStream_t stream);
+
 /* ---- optimizer step — clip_grad_norm_ + Adam, python_scripts/training/run_strong.py:143-145 */
 int tag_sumsq(const float* g, long n, double* out, cudaStream_t stream);
 int tag_clip_adam(float* p, const float* g, float* m, float* v, long n, const double* sumsq,

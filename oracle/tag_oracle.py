@@ -801,3 +801,55 @@ def attn_biencoder_forward(sd, input_dict, variant: str, training=False, dropout
         u, s = cross_attention_gating(sd, audio, t["token_emb"], a["length"], input_dict["text_len"])
         sim = torch.sigmoid((u * s).sum(-1) / math.sqrt(u.size(-1))).clamp(1e-7, 1.0)     # match.py:43-60, "token"
     return {"frame_sim": sim, "length": a["length"], "token_emb": t["token_emb"], "seq_emb": t["seq_emb"]}
+
+
+# =====================================================================================================
+# BASELINE.json configs[4] — CLAP text tower behind the Hugging Face surface.  The arithmetic of the tower lives in
+# the `transformers` library (ClapTextModel / ClapProjectionLayer, version pinned by the image: the reference's
+# requirements.txt does not list it); the oracle for it IS that library code run on CPU in fp32, wired exactly as
+# the reference's LaionClapEncoder.forward does (models/hf_modeling_grounding.py:192-199).
+def clap_case_modules(tower_seed: int):
+    """(text tower, projection, extra state) of one parity case: full-size randomly initialised ClapTextModel +
+    ClapProjectionLayer under ``tower_seed`` and Xavier audio_proj / 100x-sharpened text_proj (seq_emb is unit-norm,
+    so the raw logits would sit in +-0.05)."""
+    from transformers import ClapTextConfig
+    from transformers.models.clap import modeling_clap as mc
+    torch.manual_seed(tower_seed)
+    cfg = ClapTextConfig()
+    tower = mc.ClapTextModel(cfg).eval()
+    proj = mc.ClapProjectionLayer(cfg).eval()
+    g = torch.Generator().manual_seed(tower_seed + 1)
+    a = math.sqrt(6.0 / (EMBED + EMBED))
+    extra = {
+        "audio_proj.weight": (torch.rand(EMBED, EMBED, generator=g) * 2 - 1) * a,
+        "audio_proj.bias": (torch.rand(EMBED, generator=g) * 2 - 1) * 0.1,
+        "text_proj.weight": (torch.rand(EMBED, EMBED, generator=g) * 2 - 1) * a * 100.0,
+        "text_proj.bias": (torch.rand(EMBED, generator=g) * 2 - 1) * 0.1,
+    }
+    return tower, proj, extra
+
+
+def synth_clap_batch(batch: int, n_samples: int, n_tokens: int, seed: int):
+    """waveforms as synth_batch; RoBERTa-style ids: <s>=0 ... </s>=2, right padded with pad id 1."""
+    base = synth_batch(batch, n_samples, 8, seed, ragged=True)
+    g = torch.Generator().manual_seed(seed + 3000)
+    lens = torch.randint(3, n_tokens + 1, (batch,), generator=g)
+    lens[0] = n_tokens
+    ids = torch.full((batch, n_tokens), 1, dtype=torch.long)
+    mask = torch.zeros(batch, n_tokens, dtype=torch.long)
+    for b in range(batch):
+        n = int(lens[b])
+        ids[b, 0] = 0
+        ids[b, 1:n - 1] = torch.randint(4, 50000, (n - 2,), generator=g)
+        ids[b, n - 1] = 2
+        mask[b, :n] = 1
+    return {"waveform": base["waveform"], "waveform_len": base["waveform_len"], "input_ids": ids,
+            "attention_mask": mask}
+
+
+def clap_text_encoder(tower, proj, input_ids, attention_mask):
+    """LaionClapEncoder.forward (models/hf_modeling_grounding.py:192-199) on the library modules."""
+    out = tower(input_ids=input_ids.long(), attention_mask=attention_mask.long())
+    token_emb = proj(out.last_hidden_state)
+    seq_emb = F.normalize(proj(out.pooler_output), dim=-1)
+    return {"seq_emb": seq_emb, "token_emb": token_emb}

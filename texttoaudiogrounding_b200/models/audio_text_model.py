@@ -22,8 +22,9 @@ class BiEncoder(nn.Module, LoadPretrainedMixin):
         self.match_fn = match_fn
         self.cross_encoder = cross_encoder
         if audio_encoder.embed_dim != text_encoder.embed_dim or add_proj:
-            raise NotImplementedError("audio_proj/text_proj (add_proj or mismatched embed dims) are "
-                                      "outside the cnn8rnn-w2vmean hot path (SURVEY.md §8f)")
+            # parameter containers; applied with nn_ops.linear (models/audio_text_model.py:35-46, 82-97)
+            self.audio_proj = nn.Linear(audio_encoder.embed_dim, shared_dim)
+            self.text_proj = nn.Linear(text_encoder.embed_dim, shared_dim)
         if upsample:
             raise NotImplementedError("upsample=True is outside the cnn8rnn-w2vmean hot path")
         self.interpolate_ratio = self.audio_encoder.downsample_ratio
@@ -49,6 +50,14 @@ class BiEncoder(nn.Module, LoadPretrainedMixin):
             forward_dict["text_len"] = input_dict["text_len"]
         if self.cross_encoder is not None:
             forward_dict.update(self.cross_encoder(forward_dict))     # audio_emb, text_emb (per-frame tokens)
+        if hasattr(self, "audio_proj"):
+            from . import nn_ops
+            forward_dict["audio_emb"] = nn_ops.linear(forward_dict["audio_emb"], self.audio_proj.weight,
+                                                      self.audio_proj.bias)
+            text_emb = forward_dict["text_emb"]
+            for key in ("seq_emb", "token_emb"):
+                if key in text_emb:
+                    text_emb[key] = nn_ops.linear(text_emb[key], self.text_proj.weight, self.text_proj.bias)
         frame_sim = self.match_fn(forward_dict)      # [batch_size, max_len]
         length = audio_output["length"]
         return {"frame_sim": frame_sim, "length": length}

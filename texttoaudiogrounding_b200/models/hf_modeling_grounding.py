@@ -56,3 +56,52 @@ class Cnn8RnnW2vMeanGroundingModel(nn.Module):
             "text_len": tokens["text_len"].to(device),
         }
         return self.model(input_dict)["frame_sim"]
+
+
+@dataclass
+class Cnn8RnnLaionClapGroundingConfig:
+    """reference models/hf_modeling_grounding.py:305-316; ``text_encoder_name`` may also be a ``ClapConfig`` /
+    ``ClapTextConfig`` for a randomly initialised text tower (no Hugging Face download)."""
+    sample_rate: int = 32000
+    shared_dim: int = 512
+    text_encoder_name: object = "laion/clap-htsat-fused"
+
+
+class Cnn8RnnLaionClapGroundingModel(nn.Module):
+    """``model(audio, audio_len, text) -> frame_sim`` of the released CLAP checkpoints (reference
+    models/hf_modeling_grounding.py:319-352): Cnn8Rnn + LaionClapEncoder + DotProduct inside
+    BiEncoder(add_proj=True).  ``text`` is a list of strings (needs the Hugging Face tokenizer of
+    ``text_encoder_name``) or an already tokenised dict with ``input_ids`` / ``attention_mask``."""
+    config_class = Cnn8RnnLaionClapGroundingConfig
+
+    def __init__(self, config: Cnn8RnnLaionClapGroundingConfig, text_tokenizer=None):
+        super().__init__()
+        from .text_encoder import LaionClapEncoder
+        self.config = config
+        self.text_tokenizer = text_tokenizer
+        if text_tokenizer is None and isinstance(config.text_encoder_name, str):
+            from transformers import AutoTokenizer
+            self.text_tokenizer = AutoTokenizer.from_pretrained(config.text_encoder_name)
+        self.model = BiEncoder(
+            audio_encoder=Cnn8Rnn(sample_rate=config.sample_rate),
+            text_encoder=LaionClapEncoder(model_type=config.text_encoder_name),
+            match_fn=DotProduct(),
+            shared_dim=config.shared_dim,
+            add_proj=True)
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def forward(self, audio: torch.Tensor, audio_len, text) -> torch.Tensor:
+        device = self.device
+        if isinstance(text, dict):
+            tokens = {k: torch.as_tensor(v).to(device) for k, v in text.items()}
+        else:
+            if self.text_tokenizer is None:
+                raise RuntimeError("no tokenizer: pass text_tokenizer=... or a tokenised dict")
+            tokens = dict(self.text_tokenizer(text, padding=True, return_tensors="pt", truncation=True).to(device))
+        tokens["text_len"] = tokens["attention_mask"].sum(dim=-1)
+        input_dict = {"waveform": audio.to(device), "waveform_len": audio_len, "specaug": False}
+        input_dict.update(tokens)
+        return self.model(input_dict)["frame_sim"]

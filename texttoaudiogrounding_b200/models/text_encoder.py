@@ -154,3 +154,109 @@ class SelfAttention(nn.Module):
         lens = (lens_to_device(input_dict["text_len"], weight.device) + 1).contiguous()
         x = nn_ops.multi_head_attention(self.mha, x, x, x, lens, self.training)
         return {"token_emb": x[:, 1:], "seq_emb": x[:, 0]}
+
+
+class LaionClapEncoder(nn.Module):
+    """CLAP text tower — mirror of reference models/text_encoder.py:311-327 (== models/hf_modeling_grounding.py:183-199):
+    ``transformers`` ClapModel.text_model (RoBERTa-base layout) + ClapModel.text_projection; ``token_emb`` is the
+    projection of every hidden state, ``seq_emb`` the L2-normalised projection of the pooler output.  The Hugging Face
+    modules are kept as parameter containers (identical state-dict keys: ``model.*``, ``projection.*``); the forward
+    pass runs on this repository's kernels: bf16 tcgen05 GEMMs for the 74 dense layers, csrc/attn.cu for the
+    attention core, csrc/transformer.cu for embeddings / LayerNorm / GELU / normalisation.  Inference path (no
+    autograd through the tower — the reference's released checkpoints keep it frozen).
+
+    ``model_type`` is a Hugging Face model id / local path as in the reference, or a ``ClapConfig`` /
+    ``ClapTextConfig`` for a randomly initialised tower (offline use)."""
+
+    def __init__(self, model_type):
+        super().__init__()
+        from transformers import ClapConfig, ClapTextConfig
+        if isinstance(model_type, (ClapConfig, ClapTextConfig)):
+            from transformers.models.clap import modeling_clap as mc
+            tcfg = model_type.text_config if isinstance(model_type, ClapConfig) else model_type
+            self.tokenizer = None
+            self.model = mc.ClapTextModel(tcfg)
+            self.projection = mc.ClapProjectionLayer(tcfg)
+            self.embed_dim = tcfg.projection_dim
+        else:
+            from transformers import ClapModel, ClapProcessor
+            self.tokenizer = ClapProcessor.from_pretrained(model_type)
+            model = ClapModel.from_pretrained(model_type)
+            self.model = model.text_model
+            self.projection = model.text_projection
+            self.embed_dim = model.text_projection.config.projection_dim
+        self._bf16 = {}
+
+    def refresh_operands(self) -> None:
+        """Drop the cached bf16 copies of the dense weights (call after loading / changing the weights)."""
+        self._bf16 = {}
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._bf16 = {}
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *a, **k):
+        self._bf16 = {}
+        return super()._apply(fn, *a, **k)
+
+    def _dense(self, x: torch.Tensor, lin: nn.Linear, relu: bool = False) -> torch.Tensor:
+        """x [R, K] fp32 -> x W^T + b [R, N] fp32 through a bf16 tensor-core GEMM (weights cast once)."""
+        from .. import ops
+        key = id(lin)
+        wb = self._bf16.get(key)
+        if wb is None:
+            wb = ops.to_bf16(lin.weight.detach().float().contiguous())
+            self._bf16[key] = wb
+        R, K = x.shape
+        N = lin.weight.shape[0]
+        y = torch.empty(R, N, device=x.device, dtype=torch.float32)
+        ops.annotate(f"fwd M={R} N={N} K={K}", 2.0 * R * N * K)
+        call("tag_conv_tc_fwd", ops.to_bf16(x), wb, y, ops.F32, lin.bias.detach().float().contiguous(), int(relu), None,
+             1, R, 1, K, N, 1)
+        return y
+
+    @torch.no_grad()
+    def forward(self, input_dict):
+        emb = self.model.embeddings
+        dev = emb.word_embeddings.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("LaionClapEncoder (B200) needs CUDA tensors: there is no CPU fallback")
+        ids = input_dict["input_ids"].long().to(dev).contiguous()
+        mask = input_dict["attention_mask"].long().to(dev)
+        B, L = ids.shape
+        cfg = self.model.config
+        E, heads = cfg.hidden_size, cfg.num_attention_heads
+        if L > 128:
+            raise NotImplementedError("LaionClapEncoder (B200): at most 128 tokens per phrase")
+        key_len = mask.sum(dim=-1).contiguous()          # right-padded batches (tokenizer(padding=True))
+        x = torch.empty(B * L, E, device=dev, dtype=torch.float32)
+        call("tag_roberta_embed_ln", ids, emb.word_embeddings.weight, emb.position_embeddings.weight,
+             emb.token_type_embeddings.weight, emb.LayerNorm.weight, emb.LayerNorm.bias, x, B, L, E,
+             emb.word_embeddings.weight.shape[0], emb.position_embeddings.weight.shape[0], emb.padding_idx,
+             float(emb.LayerNorm.eps))
+        for layer in self.model.encoder.layer:
+            att = layer.attention
+            q = self._dense(x, att.self.query).view(B, L, E)
+            k = self._dense(x, att.self.key).view(B, L, E)
+            v = self._dense(x, att.self.value).view(B, L, E)
+            ctx = torch.empty_like(q)
+            probs = torch.empty(B, heads, L, L, device=dev, dtype=torch.float32)
+            call("tag_mha_core_fwd", q, k, v, key_len, ctx, probs, B, L, L, E, heads, 0.0, 0, None)
+            a = self._dense(ctx.view(B * L, E), att.output.dense)
+            x1 = torch.empty_like(x)
+            call("tag_add_layernorm", a, x, att.output.LayerNorm.weight, att.output.LayerNorm.bias, x1, B * L, E,
+                 float(att.output.LayerNorm.eps))
+            h = self._dense(x1, layer.intermediate.dense)
+            call("tag_unary_f32", h, h, h.numel(), 0)                       # exact GELU
+            o = self._dense(h, layer.output.dense)
+            x = torch.empty_like(x1)
+            call("tag_add_layernorm", o, x1, layer.output.LayerNorm.weight, layer.output.LayerNorm.bias, x, B * L, E,
+                 float(layer.output.LayerNorm.eps))
+        first = x.view(B, L, E)[:, 0].contiguous()
+        pooled = self._dense(first, self.model.pooler.dense)
+        call("tag_unary_f32", pooled, pooled, pooled.numel(), 1)           # tanh
+        token_emb = self._dense(self._dense(x, self.projection.linear1, relu=True), self.projection.linear2)
+        seq = self._dense(self._dense(pooled, self.projection.linear1, relu=True), self.projection.linear2)
+        seq_emb = torch.empty_like(seq)
+        call("tag_l2_normalize", seq, seq_emb, B, seq.shape[1], 1e-12)
+        return {"seq_emb": seq_emb, "token_emb": token_emb.view(B, L, -1)}
