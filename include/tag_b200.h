@@ -100,6 +100,9 @@ int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, dou
  * [9][Cin][Cout] of the 180-degree rotated kernel (flip_transpose=1), from the fp32 master. */
 int tag_weight_prep_tapmajor_bf16(const float* w, void* out, int Co, int Ci, int flip_transpose,
                                   cudaStream_t stream);
+/* fp32-accurate convolution on the bf16 tensor cores: weights as [9][Cout][3*Cin] = [hi | lo | hi] for activations split
+ * with tag_split_bf16x3 mode 0 ([.., 3*Cin] = [hi | hi | lo]); run tag_conv_tc_fwd_halo with Cin' = 3*Cin, fp32 output */
+int tag_weight_prep_tapmajor_x3(const float* w, void* out, int Co, int Ci, cudaStream_t stream);
 int tag_weight_flip_transpose_bf16(const float* w, void* wt, int Co, int Ci, int taps, cudaStream_t stream);
 
 /* ---- BN + ReLU + avg+max pool + dropout — models/panns.py:50-58, audio_encoder.py:202-211 */

@@ -419,6 +419,25 @@ __global__ void weight_prep_tapmajor_kernel(const float* __restrict__ w, bf16* _
     }
 }
 
+// Split-bf16 ("bf16x3", csrc/split.cu) forward operand: out[tap'][co][3*Ci] = [w_hi | w_lo | w_hi]; with the activation
+// split as [x_hi | x_hi | x_lo] along the channels the same halo kernel computes an fp32-accurate convolution
+// (hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM) at three times the bf16 cost.
+__global__ void weight_prep_tapmajor_x3_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Ci) {
+    const long n = (long)Co * Ci * 9;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Ci);
+        const long r = i / Ci;
+        const int co = (int)(r % Co);
+        const int tp = (int)(r / Co);
+        const int tap = (tp % 3) * 3 + tp / 3;
+        const float v = w[((long)co * 9 + tap) * Ci + c];
+        const bf16 hi = __float2bfloat16_rn(v);
+        const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        bf16* o = out + ((long)tp * Co + co) * 3 * Ci + c;
+        o[0] = hi; o[Ci] = lo; o[2 * Ci] = hi;
+    }
+}
+
 // weights [9][Cout][Cin] bf16 viewed as (Cin, Cout, 9); box = (64, block_n, tps)
 int make_w3_tmap(CUtensorMap* map, const void* ptr, int Cout, int Cin, int block_n, int tps) {
     EncodeTiledFn enc = get_encode_fn();
@@ -441,6 +460,15 @@ extern "C" int tag_weight_prep_tapmajor_bf16(const float* w, void* out, int Co, 
     int blocks = (int)((n + 255) / 256);
     if (blocks > 4096) blocks = 4096;
     weight_prep_tapmajor_kernel<<<blocks, 256, 0, stream>>>(w, (bf16*)out, Co, Ci, flip_transpose);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_weight_prep_tapmajor_x3(const float* w, void* out, int Co, int Ci, cudaStream_t stream) {
+    const long n = (long)Co * Ci * 9;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 4096) blocks = 4096;
+    weight_prep_tapmajor_x3_kernel<<<blocks, 256, 0, stream>>>(w, (bf16*)out, Co, Ci);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }

@@ -163,6 +163,15 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
         ctx.db, ctx.x0 = db, x0
         ctx.bn_aux.append(aux0)
 
+    # fp32 inference (no statistics, nothing saved): the dense contractions run on the bf16 tensor cores with
+    # split-bf16 operands (fp32-accurate to ~2^-16, three times the bf16 cost) instead of CUDA-core FMA
+    x3 = dtype == torch.float32 and not save and not bn_training
+
+    def fwd_operand(w, halo_W=None):
+        if x3 and ops.x3_eligible(w, halo_W):
+            return ops.prep_weight_x3(w, halo_W)
+        return ops.prep_weight(w, dtype, halo_W)
+
     # ---- conv blocks
     x = x0
     H, W = T0, N_MELS
@@ -174,7 +183,7 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
         if cin == 1:
             call("tag_conv_c1_fwd", x, Wt.conv[0], y1, ops.dt(y1), st1, B, H, W)
         else:
-            ops.conv_fwd(x, _operand(Wt, ("f", 2 * blk), lambda: ops.prep_weight(Wt.conv[2 * blk], dtype, W)), y1, None, False, st1, B, H, W, cin, cout, 9)
+            ops.conv_fwd(x, _operand(Wt, ("f", 2 * blk), lambda: fwd_operand(Wt.conv[2 * blk], W)), y1, None, False, st1, B, H, W, cin, cout, 9)
         aux1 = bn_aux(cout)
         finalize(st1, count, cout, 1 + 2 * blk, aux1)
         a1 = torch.empty(B, H, W, cout, **act)
@@ -182,7 +191,7 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
         # conv2
         y2 = torch.empty(B, H, W, cout, **act)
         st2 = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if bn_training else None
-        ops.conv_fwd(a1, _operand(Wt, ("f", 2 * blk + 1), lambda: ops.prep_weight(Wt.conv[2 * blk + 1], dtype, W)), y2, None, False, st2, B, H, W, cout, cout, 9)
+        ops.conv_fwd(a1, _operand(Wt, ("f", 2 * blk + 1), lambda: fwd_operand(Wt.conv[2 * blk + 1], W)), y2, None, False, st2, B, H, W, cout, cout, 9)
         aux2 = bn_aux(cout)
         finalize(st2, count, cout, 2 + 2 * blk, aux2)
         # bn2 + relu + pool + dropout
@@ -208,9 +217,9 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
     call("tag_freq_mean_fwd", x, m, ops.dt(m), rows, Wf, C, P_FC if use_dropout else 0.0,
          _seed_for(seed, 4), seed_dev)
     f = torch.empty(rows, 512, **act)
-    ops.conv_fwd(m, _operand(Wt, "fc", lambda: ops.prep_weight(Wt.fc_w, dtype)), f, Wt.fc_b, True, None, 1, rows, 1, C, 512, 1)
+    ops.conv_fwd(m, _operand(Wt, "fc", lambda: fwd_operand(Wt.fc_w)), f, Wt.fc_b, True, None, 1, rows, 1, C, 512, 1)
     gi = torch.empty(rows, 1536, **f32)
-    ops.conv_fwd(f, _operand(Wt, "ih", lambda: ops.prep_weight(Wt.w_ih, dtype)), gi, Wt.b_ih, False, None, 1, rows, 1, 512, 1536, 1)
+    ops.conv_fwd(f, _operand(Wt, "ih", lambda: fwd_operand(Wt.w_ih)), gi, Wt.b_ih, False, None, 1, rows, 1, 512, 1536, 1)
     out = torch.empty(B, Tp, 512, **f32)
     gates = torch.empty(B, Tp, 2, 4, 256, **f32) if save else None
     gru_fwd = "tag_gru_fwd_bf16" if (dtype == torch.bfloat16 and ops.USE_TC) else "tag_gru_fwd"

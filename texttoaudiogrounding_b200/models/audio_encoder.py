@@ -96,7 +96,8 @@ class _Cnn8RnnFunction(torch.autograd.Function):
     def forward(ctx, module, waveform, *params):
         training = module.training
         Wt = module._weights()
-        save = any(ctx.needs_input_grad)
+        # needs_input_grad ignores torch.no_grad(); the module records the grad mode before apply()
+        save = module._grad_mode and any(ctx.needs_input_grad)
         module._call_count += 1
         seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * module._call_count) & 0x7FFFFFFFFFFFFFFF
         out, ectx = engine.encoder_forward(
@@ -148,6 +149,7 @@ class Cnn8Rnn(nn.Module, LoadPretrainedMixin):
         self.dropout_enabled = True       # parity tests switch the five F.dropout sites off
         self._stages = None               # set to a dict to capture stage tensors (tests)
         self._call_count = 0
+        self._grad_mode = True
         self._mel_range = None
         self._mel_nnz = 0
 
@@ -254,6 +256,7 @@ class Cnn8Rnn(nn.Module, LoadPretrainedMixin):
         if not waveform.is_cuda:
             raise RuntimeError("Cnn8Rnn (B200) needs CUDA tensors: there is no CPU fallback")
         waveform = waveform.float()
+        self._grad_mode = torch.is_grad_enabled()
         x = _Cnn8RnnFunction.apply(self, waveform, *self._param_list())
         if self.training:
             for bn in self._bns():

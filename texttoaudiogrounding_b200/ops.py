@@ -55,6 +55,18 @@ def tc_eligible(W: int, Cin: int, Cout: int) -> bool:
 def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps, bn_fuse=None):
     """Dispatch on the weight dtype: bf16 weights -> tcgen05 kernel, fp32 weights -> SIMT kernel.
     ``bn_fuse`` = (bn_y, scale, shift, mean, invstd): fused ReLU+BN backward reduce (halo kernel only)."""
+    if getattr(w, "_tag_x3", False):
+        # fp32 activations x split-bf16 weights: fp32-accurate product on the bf16 tensor cores (csrc/split.cu)
+        if x.dtype != torch.float32 or y.dtype != torch.float32 or stats is not None or bn_fuse is not None:
+            raise _lib.TagError("split-bf16 conv: fp32 activations in and out, no fused statistics")
+        xs = torch.empty(B * H * W, 3 * Cin, device=x.device, dtype=torch.bfloat16)
+        call("tag_split_bf16x3", x, xs, B * H * W, Cin, 0, 0)
+        annotate(f"fwd M={B * H * W} N={Cout} K={taps * 3 * Cin}", 2.0 * B * H * W * Cout * taps * 3 * Cin)
+        if taps == 9:
+            call("tag_conv_tc_fwd_halo", xs, w, y, dt(y), None, B, H, W, 3 * Cin, Cout, None, None, None, None, None)
+        else:
+            call("tag_conv_tc_fwd", xs, w, y, dt(y), bias, int(relu), None, B, H, W, 3 * Cin, Cout, taps)
+        return
     annotate(f"fwd M={B * H * W} N={Cout} K={taps * Cin}", 2.0 * B * H * W * Cout * taps * Cin)
     if w.dtype == torch.bfloat16:
         if x.dtype != torch.bfloat16 or not tc_eligible(W, Cin, Cout):
@@ -121,6 +133,30 @@ def prep_weight(w: torch.Tensor, dtype: torch.dtype, halo_W=None) -> torch.Tenso
     else:
         call("tag_cast_f32_to_bf16", w, wb, w.numel())
     return wb
+
+
+def x3_eligible(w: torch.Tensor, halo_W) -> bool:
+    """3x3 conv on a width that suits the halo kernel, or a linear layer; channel counts multiples of 64."""
+    if not USE_TC or os.environ.get("TAG_B200_FP32_X3", "1") == "0":
+        return False
+    if w.dim() == 4:
+        return _halo_ok(halo_W) and w.shape[0] % 64 == 0 and w.shape[3] % 64 == 0
+    return w.dim() == 2 and w.shape[0] % 64 == 0 and w.shape[1] % 64 == 0
+
+
+def prep_weight_x3(w: torch.Tensor, halo_W=None) -> torch.Tensor:
+    """fp32 master weight -> split-bf16 forward operand ([9][Cout][3Cin] tap-major for a 3x3 conv, [Cout][3Cin] for a
+    linear layer), marked ``_tag_x3`` so conv_fwd splits the fp32 activations to match."""
+    if w.dim() == 4:
+        Co, Ci = w.shape[0], w.shape[3]
+        out = torch.empty(9 * Co * 3 * Ci, device=w.device, dtype=torch.bfloat16)
+        call("tag_weight_prep_tapmajor_x3", w, out, Co, Ci)
+    else:
+        Co, Ci = w.shape
+        out = torch.empty(Co * 3 * Ci, device=w.device, dtype=torch.bfloat16)
+        call("tag_split_bf16x3", w, out, Co, Ci, 1, 0)
+    out._tag_x3 = True
+    return out
 
 
 def prep_weight_t(w: torch.Tensor, Co: int, Ci: int, taps: int, dtype: torch.dtype, halo_W=None) -> torch.Tensor:
