@@ -276,6 +276,15 @@ int tag_unary_f32(const float* in, float* out, long n, int op, cudaStream_t stre
 /* F.normalize(x, dim=-1): rows / max(||row||_2, eps) */
 int tag_l2_normalize(const float* in, float* out, long rows, int E, float eps, cudaStream_t stream);
 
+/* ---- post-processing of frame probabilities (SURVEY.md §8f rank 4 iii) — Runner.eval_inference,
+ * python_scripts/training/run_strong.py:222-247 with utils/eval_util.py:18-116: for every (sample, threshold) pair
+ * binarize (sim > threshold, float64 compare), median-filter along time (window, scipy "reflect" boundary), merge
+ * regions whose gap is <= n_connect frames, list the regions.  sim [B, T] (row stride sim_stride, floats),
+ * thresholds double[n_th]; regions int[B][n_th][max_regions][2] = (onset, offset) frames, counts int[B][n_th] (a count
+ * above max_regions means truncated output).  Bit-exact with the reference. */
+int tag_frame_regions(const float* sim, long sim_stride, const double* thresholds, int B, int T, int n_th, int window,
+                      int n_connect, int max_regions, int* regions, int* counts, cudaStream_t stream);
+
 /* ---- optimizer step — clip_grad_norm_ + Adam, python_scripts/training/run_strong.py:143-145 */
 int tag_sumsq(const float* g, long n, double* out, cudaStream_t stream);
 int tag_clip_adam(float* p, const float* g, float* m, float* v, long n, const double* sumsq,

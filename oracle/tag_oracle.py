@@ -853,3 +853,63 @@ def clap_text_encoder(tower, proj, input_ids, attention_mask):
     token_emb = proj(out.last_hidden_state)
     seq_emb = F.normalize(proj(out.pooler_output), dim=-1)
     return {"seq_emb": seq_emb, "token_emb": token_emb}
+
+
+# =====================================================================================================
+# SURVEY.md §8f rank 4(iii) — post-processing of frame probabilities.  Reference sites restated here (numpy):
+#   * find_contiguous_regions ... utils/eval_util.py:18-44
+#   * median_filter (+ binarize) . utils/eval_util.py:47-63 (sklearn binarize: x > th; scipy.ndimage.median_filter,
+#                                  size (1, w), mode="reflect": window t - w//2 .. t - w//2 + w - 1, rank w // 2)
+#   * connect_clusters / connect_  utils/eval_util.py:74-116
+#   * the per-sample, per-threshold loop ... python_scripts/training/run_strong.py:222-247
+def contiguous_regions(activity):
+    import numpy as np
+    a = np.asarray(activity).astype(bool)
+    change = np.logical_xor(a[1:], a[:-1]).nonzero()[0] + 1
+    if a[0]:
+        change = np.r_[0, change]
+    if a[-1]:
+        change = np.r_[change, a.size]
+    return change.reshape((-1, 2))
+
+
+def median_filter_binary(x, window: int, threshold: float):
+    import numpy as np
+    x = np.asarray(x)
+    b = (x.astype(np.float64) > threshold).astype(np.int64)
+    T = b.size
+    out = np.zeros(T, dtype=np.int64)
+    half = window // 2
+    for t in range(T):
+        vals = []
+        for i in range(window):
+            idx = t - half + i
+            if idx < 0:
+                idx = -idx - 1
+            if idx >= T:
+                idx = 2 * T - idx - 1
+            idx = min(max(idx, 0), T - 1)
+            vals.append(b[idx])
+        out[t] = sorted(vals)[window // 2]
+    return out
+
+
+def connect_regions(pairs, n: int):
+    pairs = [tuple(int(v) for v in p) for p in pairs]
+    if not pairs:
+        return []
+    merged = []
+    start, end = pairs[0]
+    for s, e in pairs[1:]:
+        if s - end <= n:
+            end = e
+        else:
+            merged.append((start, end))
+            start, end = s, e
+    merged.append((start, end))
+    return merged
+
+
+def frame_regions(frame_sim_row, threshold: float, window: int, n_connect: int):
+    """(onset, offset) frame pairs of one sample at one threshold (run_strong.py:231-241)."""
+    return connect_regions(contiguous_regions(median_filter_binary(frame_sim_row, window, threshold)), n_connect)
