@@ -149,3 +149,34 @@ def test_hf_style_facade_builds_and_refuses_cpu():
     assert model.model.text_encoder.embedding.core.weight.shape == (3, 512)
     with pytest.raises(RuntimeError):
         model(torch.zeros(1, 32000), [32000], ["dog"])          # CPU tensors: no fallback
+
+
+def test_checkpoint_interchange_key_and_shape_matching(tmp_path):
+    """Reference checkpoint format {"model": state_dict, "epoch", ...} (run_strong.py:679-690) and the loaders'
+    key-AND-shape matching (utils/train_util.py:219-297, models/base.py:9-47; PANNs layout of
+    models/audio_encoder.py:153-160): matching tensors are taken, everything else is skipped silently."""
+    from texttoaudiogrounding_b200.models.audio_encoder import Cnn8Rnn
+    from texttoaudiogrounding_b200.models.audio_text_model import BiEncoder
+    from texttoaudiogrounding_b200.models.match import DotProduct
+    from texttoaudiogrounding_b200.models.text_encoder import EmbeddingAgg
+    sd = O.synth_state_dict(seed=11, vocab=50)
+    path = tmp_path / "ckpt.pth"
+    torch.save({"model": sd, "epoch": 3, "metric_monitor": 0.5, "not_improve_cnt": 0}, path)
+    model = BiEncoder(Cnn8Rnn(32000), EmbeddingAgg(50, 512), DotProduct(), 512)
+    msgs = []
+    model.load_pretrained(str(path), msgs.append)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    # a PANNs-style audio checkpoint: weights under ["model"] with the encoder's own keys, one tensor of another
+    # shape (skipped) and one unknown key (skipped)
+    enc_sd = {k[len("audio_encoder."):]: v + 1.0 if v.is_floating_point() else v for k, v in sd.items()
+              if k.startswith("audio_encoder.")}
+    enc_sd["fc1.weight"] = torch.zeros(7, 7)
+    enc_sd["fc_audioset.weight"] = torch.zeros(447, 512)
+    ppath = tmp_path / "panns.pth"
+    torch.save({"model": enc_sd}, ppath)
+    enc = Cnn8Rnn(32000, pretrained=str(ppath), output_fn=msgs.append)
+    assert torch.equal(enc.state_dict()["bn0.weight"], enc_sd["bn0.weight"])
+    assert torch.equal(enc.state_dict()["rnn.weight_hh_l0_reverse"], enc_sd["rnn.weight_hh_l0_reverse"])
+    assert enc.state_dict()["fc1.weight"].shape == (512, 512)            # mismatched shape: model value kept
+    assert "fc_audioset.weight" not in enc.state_dict()

@@ -163,7 +163,8 @@ class Cnn8Rnn(nn.Module, LoadPretrainedMixin):
 
     # ------------------------------------------------------------------ reference surface
     def process_state_dict(self, model_dict, pretrained_dict, output_fn, model_name):
-        pretrained_dict = pretrained_dict["model"]
+        if "model" in pretrained_dict:          # the mixin may already have unwrapped the checkpoint
+            pretrained_dict = pretrained_dict["model"]
         return merge_matched_keys(model_dict, pretrained_dict, output_fn, model_name)
 
     def train(self, mode: bool = True):

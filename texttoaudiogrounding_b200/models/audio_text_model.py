@@ -88,7 +88,8 @@ class MultiTextBiEncoder(BiEncoder):
             self.load_pretrained(pretrained, output_fn)
 
     def process_state_dict(self, model_dict, pretrained_dict, output_fn, model_name):
-        pretrained_dict = pretrained_dict["model"]
+        if "model" in pretrained_dict:          # the mixin may already have unwrapped the checkpoint
+            pretrained_dict = pretrained_dict["model"]
         return super().process_state_dict(model_dict, pretrained_dict, output_fn, model_name)
 
     def forward(self, input_dict):
