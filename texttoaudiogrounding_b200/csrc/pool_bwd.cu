@@ -39,13 +39,13 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dout, T* 
         s_sc[c] = sc;
         s_sh[c] = shift[c];
         if (MODE == 0 && POOL) {
-            // pooled reduce pass works on u = sign(gamma) * xhat: a = |gamma| * u + beta is monotone in u, so the
-            // window maximum of a is attained at the maximum of u (sc = gamma * invstd carries gamma's sign)
+            // pooled reduce pass: the ReLU gate is the forward's own test fma(y, scale, shift) > 0; sums run on
+            // w = sign(gamma) * invstd * y (u = sign(gamma) * xhat = w - off is monotone in the activation, so the window
+            // maximum of the activation sits at the maximum of w) and are moved to the u domain once per window:
+            // 7 instructions per element instead of 12 (this pass is issue-bound, not HBM-bound)
             const float sg = sc < 0.f ? -1.f : 1.f;
             s_pa[c] = sg * is;
-            s_pb[c] = -sg * mu * is;
-            s_sc[c] = sg * sc / is;          // |gamma|  (invstd > 0)
-            s_sh[c] = shift[c] + sc * mu;    // beta = shift + gamma * invstd * mean
+            s_pb[c] = sg * mu * is;
         } else if (MODE == 0) {
             s_pa[c] = is;
             s_pb[c] = -mu * is;
@@ -137,20 +137,19 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dout, T* 
                 // hang over the edge carry no gradient (floor-mode pooling) and were skipped above.
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    float S = 0.f, cnt = 0.f, m = -INFINITY;
+                    float Sw = 0.f, cnt = 0.f, m = -INFINITY;
 #pragma unroll
                     for (int e = 0; e < NE; ++e) {
                         float ve[4];
                         unpack4<T>(raw_y[e], sub, ve);
-                        const float u = fmaf(ve[k], pa[k], pb[k]);
-                        const bool pos = fmaf(u, sc[k], sh[k]) > 0.f;
-                        S += pos ? u : 0.f;
-                        cnt += pos ? 1.f : 0.f;
-                        m = fmaxf(m, u);
+                        const float w = ve[k] * pa[k];
+                        if (fmaf(ve[k], sc[k], sh[k]) > 0.f) { Sw += w; cnt += 1.f; }
+                        m = fmaxf(m, w);
                     }
                     const bool any = cnt > 0.f;
+                    const float S = fmaf(-cnt, pb[k], Sw);                 // sum of u over the active elements
                     rs[sub * 4 + k] = fmaf(go[k], fmaf(cnt, 1.0f / NE, any ? 1.f : 0.f), rs[sub * 4 + k]);
-                    rq[sub * 4 + k] = fmaf(go[k], fmaf(S, 1.0f / NE, any ? m : 0.f), rq[sub * 4 + k]);
+                    rq[sub * 4 + k] = fmaf(go[k], fmaf(S, 1.0f / NE, any ? m - pb[k] : 0.f), rq[sub * 4 + k]);
                 }
             } else if (POOL) {
                 // ---- apply pass, pooled: first maximum in scan order takes the max-pool gradient (torch semantics)
