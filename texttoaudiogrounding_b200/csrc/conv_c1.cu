@@ -49,11 +49,37 @@ conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __re
     for (int c = 0; c < 8; ++c) { cs[c] = 0.f; cq[c] = 0.f; }
     // persistent over tiles: the per-channel statistics stay in registers and are flushed ONCE per CTA (one
     // flush per tile meant ~1 M double atomics on 8 cache lines, which serialise in L2)
+    // the halo tile of the NEXT tile is fetched into registers before this tile's arithmetic and committed to shared
+    // memory after it: the global-load latency (~1 us against ~1.5 us of work per tile) is off the critical path
+    constexpr int XN = ((TH + 2) * XS_W + 255) / 256;
+    float xnext[XN];
+    auto fetch_tile = [&](int tile) {
+        const bool ok = tile < B * tiles_h;
+        const int b = ok ? tile / tiles_h : 0, h0 = ok ? (tile % tiles_h) * TH : 0;
+#pragma unroll
+        for (int j = 0; j < XN; ++j) {
+            const int i = threadIdx.x + 256 * j;
+            const int r = i / XS_W, c = i - r * XS_W;
+            const int h = h0 - 1 + r, wc = c - 1;
+            float v = 0.f;
+            if (ok && i < (TH + 2) * XS_W && h >= 0 && h < H && wc >= 0 && wc < W) v = to_f<T>(x[((long)b * H + h) * W + wc]);
+            xnext[j] = v;
+        }
+    };
+    auto commit_tile = [&]() {
+#pragma unroll
+        for (int j = 0; j < XN; ++j) {
+            const int i = threadIdx.x + 256 * j;
+            if (i < (TH + 2) * XS_W) (&xs[0][0])[i] = xnext[j];
+        }
+    };
+    fetch_tile(blockIdx.x);
     for (int tile = blockIdx.x; tile < B * tiles_h; tile += gridDim.x) {
     const int b = tile / tiles_h, h0 = (tile % tiles_h) * TH;
     __syncthreads();
-    load_x_tile<T>(xs, x, b, h0, H, W);
+    commit_tile();
     __syncthreads();
+    fetch_tile(tile + gridDim.x);
 #pragma unroll 2
     for (int it = 0; it < TH * TW / 32; ++it) {
         const int pix = it * 32 + pl;
