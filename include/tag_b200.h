@@ -157,6 +157,15 @@ int tag_frame_bce(const float* sim, long sim_stride, const float* label, long la
                   const long long* length, int B, int Tt, float* loss_out, float* d_sim,
                   long dsim_stride, float grad_scale, cudaStream_t stream);
 
+/* Normalised match heads on seq-level text (audio [B,T,512], seq [B,512] -> sim [B,T]):
+ * mode 1 DotProduct(l2norm=True) = cosine similarity -> scale -> sigmoid -> clamp (models/match.py:43-60);
+ * mode 2 / 3 ExpNegL2 with / without l2norm: exp(-|a^ - s^|) (models/match.py:10-33).  F.normalize eps 1e-12.
+ * bwd: d_audio overwritten, d_seq accumulated (pre-zeroed). */
+int tag_match_norm_fwd(const float* audio, const float* seq, float* sim, int B, int T, int D, int mode, float scale,
+                       cudaStream_t stream);
+int tag_match_norm_bwd(const float* d_sim, const float* sim, const float* audio, const float* seq, float* d_audio,
+                       float* d_seq, int B, int T, int D, int mode, float scale, cudaStream_t stream);
+
 /* ---- multi-phrase (weakly supervised) head — SURVEY.md §8f rank 1.  MultiTextBiEncoder.forward
  * (models/audio_text_model.py:147-229) matches every clip against n phrases; the reference expands the audio
  * embedding to [B*n,T,D] and calls DotProduct (models/match.py:43-60) — here audio [B,T,D] is read in place:

@@ -913,3 +913,22 @@ def connect_regions(pairs, n: int):
 def frame_regions(frame_sim_row, threshold: float, window: int, n_connect: int):
     """(onset, offset) frame pairs of one sample at one threshold (run_strong.py:231-241)."""
     return connect_regions(contiguous_regions(median_filter_binary(frame_sim_row, window, threshold)), n_connect)
+
+
+# =====================================================================================================
+# Normalised match heads.  Reference sites: DotProduct(l2norm=True) models/match.py:43-60 (F.normalize both sides =
+# cosine similarity), ExpNegL2 models/match.py:10-33.
+def dot_product_match_l2norm(audio_emb, seq_emb, scale: bool = True):
+    a = F.normalize(audio_emb, dim=-1)
+    s = F.normalize(seq_emb, dim=-1).unsqueeze(1)
+    score = (a * s).sum(-1)
+    if scale:
+        score = score / math.sqrt(audio_emb.size(-1))
+    return torch.sigmoid(score).clamp(1e-7, 1.0)
+
+
+def exp_neg_l2_match(audio_emb, seq_emb, l2norm: bool = True):
+    a, s = audio_emb, seq_emb
+    if l2norm:
+        a, s = F.normalize(a, dim=-1), F.normalize(s, dim=-1)
+    return torch.exp(-torch.norm(a - s.unsqueeze(1), dim=-1))

@@ -324,3 +324,28 @@ def test_clip_adam_matches_torch():
         ops.call("tag_clip_adam", pc, gc, m, v, n, ss, step, 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, norm)
         np.testing.assert_allclose(norm.item(), float(tn), rtol=1e-5)
         assert (pc.cpu() - ref_p.detach()).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("mode", ["cosine", "cosine_unscaled", "expnegl2", "expnegl2_raw"])
+def test_normalised_match_heads_match_torch_autograd(mode):
+    """DotProduct(l2norm=True) (cosine) and ExpNegL2 (models/match.py:10-60) against autograd of the oracle."""
+    from texttoaudiogrounding_b200.models.match import DotProduct, ExpNegL2
+    B, T, D = 3, 41, 512
+    a = torch.randn(B, T, D, generator=g(1)).requires_grad_(True)
+    s = (torch.randn(B, D, generator=g(2)) * (0.05 if mode == "expnegl2_raw" else 1.0)).requires_grad_(True)
+    if mode == "expnegl2_raw":
+        a.data.mul_(0.05)
+    w = torch.randn(B, T, generator=g(3))
+    if mode.startswith("cosine"):
+        ref = O.dot_product_match_l2norm(a, s, scale=mode == "cosine")
+        head = DotProduct(l2norm=True, scale=mode == "cosine")
+    else:
+        ref = O.exp_neg_l2_match(a, s, l2norm=mode == "expnegl2")
+        head = ExpNegL2(l2norm=mode == "expnegl2")
+    (ref * w).sum().backward()
+    ac, sc = a.detach().cuda().requires_grad_(True), s.detach().cuda().requires_grad_(True)
+    out = head({"audio_emb": ac, "text_emb": {"seq_emb": sc}})
+    (out * w.cuda()).sum().backward()
+    assert (out.detach().cpu() - ref.detach()).abs().max().item() < 1e-6
+    assert rel_err(ac.grad.cpu(), a.grad) < 1e-4
+    assert rel_err(sc.grad.cpu(), s.grad) < 1e-4

@@ -101,14 +101,18 @@ def test_run_strong_dialect_config_instantiates_b200_classes(tmp_path):
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         train_util.init_obj_from_str({"type": "models.match.DotProduct", "args": {"text_level": "token"}})(
             {"audio_emb": torch.zeros(1, 2, 4), "text_emb": {"token_emb": torch.zeros(1, 2, 4)}})
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         train_util.init_obj_from_str({"type": "models.match.DotProduct", "args": {"l2norm": True}})(
             {"audio_emb": torch.zeros(1, 2, 4), "text_emb": {"seq_emb": torch.zeros(1, 4)}})
+    # the class name the reference's eg_configs use for the audio encoder resolves as well
+    import texttoaudiogrounding_b200.models.audio_encoder as ae2
+    assert train_util.get_obj_from_str("models.audio_encoder.Cnn8_Rnn") is ae2.Cnn8Rnn
     # the later-config components resolve through the same registry
     for typ, args in (("models.text_encoder.SelfAttention", {"vocab_size": 50, "embed_dim": 512, "num_heads": 8}),
                       ("models.match.CrossAttention", {"embed_dim": 512, "num_heads": 8, "dropout": 0.2}),
                       ("models.cross_encoder.CrossAttentionGating", {"embed_dim": 512}),
                       ("models.align.DotProduct", {"l2norm": False, "scaled": False}),
+                      ("models.match.ExpNegL2", {"text_level": "seq"}),
                       ("models.sim_pooling.AudioMeanTextMean", {}),
                       ("losses.MaxMarginRankingLoss", {"margin": 1})):
         obj = train_util.init_obj_from_str({"type": typ, "args": args})

@@ -164,6 +164,102 @@ __global__ void frame_bce_kernel(const float* __restrict__ sim, long sim_stride,
     }
 }
 
+
+// ---- normalised match heads (seq-level text): one warp per (b, t) row, D = 512
+//   mode 1: DotProduct(l2norm=True)  sim = clamp(sigmoid(scale * <a^, s^>), 1e-7, 1)     (models/match.py:43-60; cosine)
+//   mode 2: ExpNegL2(l2norm=True)    sim = exp(-|a^ - s^|)                                (models/match.py:10-33)
+//   mode 3: ExpNegL2(l2norm=False)   sim = exp(-|a - s|)
+// a^ = a / max(|a|, 1e-12) (F.normalize).  Backward: d_audio overwritten, d_seq accumulated (pre-zeroed).
+constexpr int MN_EL = 16;       // 512 / 32
+
+__device__ __forceinline__ void mn_load(const float* __restrict__ p, int lane, float (&v)[MN_EL]) {
+#pragma unroll
+    for (int i = 0; i < MN_EL; ++i) v[i] = p[lane + 32 * i];
+}
+
+__global__ void match_norm_fwd_kernel(const float* __restrict__ audio, const float* __restrict__ seq,
+                                      float* __restrict__ sim, long BT, int T, int mode, float scale) {
+    const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= BT) return;
+    float a[MN_EL], s[MN_EL];
+    mn_load(audio + wid * 512, lane, a);
+    mn_load(seq + (wid / T) * 512, lane, s);
+    float ia = 1.f, is = 1.f;
+    if (mode != 3) {
+        float aa = 0.f, ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < MN_EL; ++i) { aa = fmaf(a[i], a[i], aa); ss = fmaf(s[i], s[i], ss); }
+        ia = 1.0f / fmaxf(sqrtf(warp_sum(aa)), 1e-12f);
+        is = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < MN_EL; ++i) {
+        const float x = a[i] * ia, y = s[i] * is;
+        if (mode == 1) acc = fmaf(x, y, acc);
+        else { const float d = x - y; acc = fmaf(d, d, acc); }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0)
+        sim[wid] = mode == 1 ? fminf(fmaxf(1.0f / (1.0f + expf(-acc * scale)), 1e-7f), 1.0f) : expf(-sqrtf(acc));
+}
+
+__global__ void match_norm_bwd_kernel(const float* __restrict__ d_sim, const float* __restrict__ sim,
+                                      const float* __restrict__ audio, const float* __restrict__ seq,
+                                      float* __restrict__ d_audio, float* __restrict__ d_seq, long BT, int T, int mode,
+                                      float scale) {
+    const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= BT) return;
+    const long b = wid / T;
+    float a[MN_EL], s[MN_EL];
+    mn_load(audio + wid * 512, lane, a);
+    mn_load(seq + b * 512, lane, s);
+    float ia = 1.f, is = 1.f;
+    if (mode != 3) {
+        float aa = 0.f, ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < MN_EL; ++i) { aa = fmaf(a[i], a[i], aa); ss = fmaf(s[i], s[i], ss); }
+        ia = 1.0f / fmaxf(sqrtf(warp_sum(aa)), 1e-12f);
+        is = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+    }
+    // normalised rows, their dot product c and (modes 2, 3) the distance n
+    float c = 0.f, n2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MN_EL; ++i) {
+        a[i] *= ia; s[i] *= is;
+        c = fmaf(a[i], s[i], c);
+        const float d = a[i] - s[i];
+        n2 = fmaf(d, d, n2);
+    }
+    c = warp_sum(c);
+    n2 = warp_sum(n2);
+    const float p = sim[wid], g = d_sim[wid];
+    // d(loss)/d(a^) = ka * a^ + ks * s^ written per mode; then through the normalisation (modes 1, 2):
+    //   da = (dA - a^ <a^, dA>) / |a|,  ds = (dS - s^ <s^, dS>) / |s|
+    float da_a, da_s, ds_a, ds_s;          // coefficients of (a^, s^) in dA and dS
+    if (mode == 1) {
+        const float dc = p > 1e-7f ? g * p * (1.0f - p) * scale : 0.f;
+        da_a = 0.f; da_s = dc; ds_a = dc; ds_s = 0.f;
+    } else {
+        const float n = sqrtf(n2);
+        const float k = n > 1e-12f ? -g * p / n : 0.f;         // d(loss)/d(diff) = k * diff
+        da_a = k; da_s = -k; ds_a = -k; ds_s = k;
+    }
+    if (mode != 3) {
+        // <a^, dA> = da_a + da_s c ;  <s^, dS> = ds_a c + ds_s   (unit vectors)
+        const float pa = da_a + da_s * c, ps = ds_a * c + ds_s;
+        da_a = (da_a - pa) * ia; da_s = da_s * ia;
+        ds_s = (ds_s - ps) * is; ds_a = ds_a * is;
+    }
+#pragma unroll
+    for (int i = 0; i < MN_EL; ++i) {
+        d_audio[wid * 512 + lane + 32 * i] = fmaf(da_a, a[i], da_s * s[i]);
+        atomicAdd(d_seq + b * 512 + lane + 32 * i, fmaf(ds_a, a[i], ds_s * s[i]));
+    }
+}
+
 }  // namespace
 
 extern "C" int tag_embed_mean_fwd(const long long* text, const long long* text_len, const float* emb,
@@ -220,6 +316,28 @@ extern "C" int tag_frame_bce(const float* sim, long sim_stride, const float* lab
     if (B <= 0 || Tt <= 0) return TAG_ERR_BAD_ARG;
     frame_bce_kernel<<<1, 1024, 0, stream>>>(sim, sim_stride, label, label_stride, length, B, Tt, loss_out,
                                              d_sim, dsim_stride, grad_scale);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_match_norm_fwd(const float* audio, const float* seq, float* sim, int B, int T, int D, int mode,
+                                  float scale, cudaStream_t stream) {
+    if (B <= 0 || T <= 0 || mode < 1 || mode > 3) return TAG_ERR_BAD_ARG;
+    if (D != 512) return TAG_ERR_UNSUPPORTED;
+    const long BT = (long)B * T;
+    match_norm_fwd_kernel<<<(int)((BT * 32 + 255) / 256), 256, 0, stream>>>(audio, seq, sim, BT, T, mode, scale);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_match_norm_bwd(const float* d_sim, const float* sim, const float* audio, const float* seq,
+                                  float* d_audio, float* d_seq, int B, int T, int D, int mode, float scale,
+                                  cudaStream_t stream) {
+    if (B <= 0 || T <= 0 || mode < 1 || mode > 3) return TAG_ERR_BAD_ARG;
+    if (D != 512) return TAG_ERR_UNSUPPORTED;
+    const long BT = (long)B * T;
+    match_norm_bwd_kernel<<<(int)((BT * 32 + 255) / 256), 256, 0, stream>>>(d_sim, sim, audio, seq, d_audio, d_seq, BT, T,
+                                                                          mode, scale);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }

@@ -268,3 +268,8 @@ class Cnn8Rnn(nn.Module, LoadPretrainedMixin):
                            rounding_mode="floor") + 1
         length = torch.div(length, self.downsample_ratio, rounding_mode="floor")
         return {"embedding": x, "length": length}
+
+
+# the reference's example configs name this class ``models.audio_encoder.Cnn8_Rnn`` (eg_configs/weakly_supervised/**),
+# a spelling its own module no longer defines; the alias lets those YAMLs resolve
+Cnn8_Rnn = Cnn8Rnn

@@ -62,6 +62,29 @@ class _MultiDotSigmoidFunction(torch.autograd.Function):
         return d_audio, d_seq, None
 
 
+class _MatchNormFunction(torch.autograd.Function):
+    """mode 1: cosine -> scale -> sigmoid -> clamp; mode 2 / 3: exp(-|a^ - s^|) with / without L2 normalisation."""
+
+    @staticmethod
+    def forward(ctx, audio, seq, mode, scale):
+        B, T, D = audio.shape
+        sim = torch.empty(B, T, device=audio.device, dtype=torch.float32)
+        call("tag_match_norm_fwd", audio, seq, sim, B, T, D, mode, scale)
+        ctx.save_for_backward(audio, seq, sim)
+        ctx.cfg = (mode, scale)
+        return sim
+
+    @staticmethod
+    def backward(ctx, d_sim):
+        audio, seq, sim = ctx.saved_tensors
+        mode, scale = ctx.cfg
+        B, T, D = audio.shape
+        d_audio = torch.empty_like(audio)
+        d_seq = torch.zeros_like(seq)
+        call("tag_match_norm_bwd", d_sim.contiguous(), sim, audio, seq, d_audio, d_seq, B, T, D, mode, scale)
+        return d_audio, d_seq, None, None
+
+
 MULTI_MAX_PHRASES = 64      # phrases per clip handled by one kernel launch
 
 
@@ -75,11 +98,14 @@ class DotProduct(nn.Module):
     def forward(self, input_dict):
         audio = input_dict["audio_emb"]  # [bs, n_seg, dim]
         text = input_dict["text_emb"]
-        if self.l2norm:
-            raise NotImplementedError("l2norm=True is outside the cnn8rnn-w2vmean hot path")
         if not audio.is_cuda:
             raise RuntimeError("DotProduct (B200) needs CUDA tensors: there is no CPU fallback")
         scale = 1.0 / math.sqrt(audio.size(-1)) if self.scale else 1.0
+        if self.l2norm:
+            # cosine similarity (F.normalize on both sides, models/match.py:51-53)
+            if self.text_level != "seq":
+                raise NotImplementedError("DotProduct(l2norm=True) is built for text_level='seq'")
+            return _MatchNormFunction.apply(audio.float().contiguous(), text["seq_emb"].float().contiguous(), 1, scale)
         if self.text_level == "seq":
             text = text["seq_emb"]      # [bs, dim]
         elif self.text_level == "token":
@@ -132,3 +158,23 @@ class CrossAttention(nn.Module):
                                           text_len, self.training)
         p = self.dropout.p if self.training else 0.0
         return nn_ops.ln_linear_sigmoid(audio, out, self.norm, self.linear, p)
+
+
+class ExpNegL2(nn.Module):
+    """exp(-|a - s|) on (optionally L2-normalised) embeddings — mirror of reference models/match.py:10-33
+    (the match function of eg_configs/strongly_supervised/audiogrounding/biencoder/cdur_w2vmean.yaml)."""
+
+    def __init__(self, l2norm=True, text_level="seq") -> None:
+        super().__init__()
+        self.l2norm = l2norm
+        self.text_level = text_level
+
+    def forward(self, input_dict):
+        audio = input_dict["audio_emb"]
+        if self.text_level != "seq":
+            raise NotImplementedError("ExpNegL2 (B200) is built for text_level='seq'")
+        if not audio.is_cuda:
+            raise RuntimeError("ExpNegL2 (B200) needs CUDA tensors: there is no CPU fallback")
+        text = input_dict["text_emb"]["seq_emb"]
+        return _MatchNormFunction.apply(audio.float().contiguous(), text.float().contiguous(),
+                                        2 if self.l2norm else 3, 1.0)
