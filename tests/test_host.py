@@ -184,3 +184,30 @@ def test_checkpoint_interchange_key_and_shape_matching(tmp_path):
     assert torch.equal(enc.state_dict()["rnn.weight_hh_l0_reverse"], enc_sd["rnn.weight_hh_l0_reverse"])
     assert enc.state_dict()["fc1.weight"].shape == (512, 512)            # mismatched shape: model value kept
     assert "fc_audioset.weight" not in enc.state_dict()
+
+
+def test_clap_facade_is_a_pretrained_model_and_round_trips(tmp_path):
+    """reference models/hf_modeling_grounding.py:305-352: PretrainedConfig / PreTrainedModel with the same fields and
+    parameter names, so save_pretrained / from_pretrained directories interchange (tiny random tower here)."""
+    from transformers import ClapTextConfig, PreTrainedModel
+    from texttoaudiogrounding_b200.models.hf_modeling_grounding import (Cnn8RnnLaionClapGroundingConfig,
+                                                                        Cnn8RnnLaionClapGroundingModel)
+    cfg = Cnn8RnnLaionClapGroundingConfig(
+        text_encoder_name=ClapTextConfig(num_hidden_layers=1, vocab_size=120, max_position_embeddings=40))
+    assert cfg.sample_rate == 32000 and cfg.shared_dim == 512 and cfg.text_encoder_name == "laion/clap-htsat-fused"
+    model = Cnn8RnnLaionClapGroundingModel(cfg)
+    assert isinstance(model, PreTrainedModel)
+    keys = set(model.state_dict())
+    for k in ("model.audio_encoder.conv_block1.conv1.weight", "model.audio_encoder.rnn.weight_hh_l0_reverse",
+              "model.text_encoder.model.embeddings.word_embeddings.weight",
+              "model.text_encoder.model.encoder.layer.0.attention.self.query.weight",
+              "model.text_encoder.projection.linear2.bias", "model.audio_proj.weight", "model.text_proj.bias"):
+        assert k in keys, k
+    model.save_pretrained(tmp_path)
+    assert (tmp_path / "config.json").exists()
+    again = Cnn8RnnLaionClapGroundingModel.from_pretrained(tmp_path)
+    sd1, sd2 = model.state_dict(), again.state_dict()
+    assert set(sd1) == set(sd2) and all(torch.equal(sd1[k], sd2[k]) for k in sd1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        again(torch.zeros(1, 32000), [32000], {"input_ids": torch.tensor([[0, 5, 2]]),
+                                                 "attention_mask": torch.ones(1, 3, dtype=torch.long)})

@@ -10,7 +10,7 @@ import torch
 
 def hann_window(n: int = 1024) -> torch.Tensor:
     """Periodic Hann window, as torch.hann_window(n)."""
-    k = torch.arange(n, dtype=torch.float64)
+    k = torch.arange(n, dtype=torch.float64, device="cpu")      # "cpu": also under a meta-device init context
     return (0.5 - 0.5 * torch.cos(2.0 * math.pi * k / n)).to(torch.float32)
 
 
@@ -34,8 +34,8 @@ def _mel_to_hz(m: torch.Tensor) -> torch.Tensor:
 def slaney_mel_fbanks(n_freqs: int = 513, f_min: float = 50.0, f_max: float = 14000.0,
                       n_mels: int = 64, sample_rate: int = 32000) -> torch.Tensor:
     """[n_freqs, n_mels] triangular filters, slaney mel scale and slaney (area) normalisation."""
-    freqs = torch.linspace(0, sample_rate // 2, n_freqs)
-    m_pts = torch.linspace(_hz_to_mel(f_min), _hz_to_mel(f_max), n_mels + 2)
+    freqs = torch.linspace(0, sample_rate // 2, n_freqs, device="cpu")
+    m_pts = torch.linspace(_hz_to_mel(f_min), _hz_to_mel(f_max), n_mels + 2, device="cpu")
     f_pts = _mel_to_hz(m_pts)
     width = f_pts[1:] - f_pts[:-1]
     slopes = f_pts.unsqueeze(0) - freqs.unsqueeze(1)

@@ -58,43 +58,68 @@ class Cnn8RnnW2vMeanGroundingModel(nn.Module):
         return self.model(input_dict)["frame_sim"]
 
 
-@dataclass
-class Cnn8RnnLaionClapGroundingConfig:
-    """reference models/hf_modeling_grounding.py:305-316; ``text_encoder_name`` may also be a ``ClapConfig`` /
-    ``ClapTextConfig`` for a randomly initialised text tower (no Hugging Face download)."""
-    sample_rate: int = 32000
-    shared_dim: int = 512
-    text_encoder_name: object = "laion/clap-htsat-fused"
+try:                                    # transformers is optional for everything but the CLAP graph
+    from transformers import PretrainedConfig, PreTrainedModel
+except Exception:                       # pragma: no cover
+    PretrainedConfig, PreTrainedModel = object, nn.Module
 
 
-class Cnn8RnnLaionClapGroundingModel(nn.Module):
+class Cnn8RnnLaionClapGroundingConfig(PretrainedConfig):
+    """reference models/hf_modeling_grounding.py:305-316 (a ``PretrainedConfig`` with the same fields, so a released
+    ``config.json`` loads).  Offline extension: ``text_config`` (a ``ClapTextConfig`` or its dict) builds a randomly
+    initialised text tower instead of downloading ``text_encoder_name``; ``text_encoder_name`` may also be given as a
+    ``ClapConfig`` / ``ClapTextConfig`` object directly."""
+    model_type = "cnn8rnn_laionclap_grounding"
+
+    def __init__(self, sample_rate: int = 32000, shared_dim: int = 512,
+                 text_encoder_name="laion/clap-htsat-fused", text_config=None, **kwargs):
+        if not isinstance(text_encoder_name, str) and text_config is None:
+            text_config, text_encoder_name = text_encoder_name, "laion/clap-htsat-fused"
+        if text_config is not None and not isinstance(text_config, dict):
+            text_config = getattr(text_config, "text_config", text_config).to_dict()
+        self.sample_rate = sample_rate
+        self.shared_dim = shared_dim
+        self.text_encoder_name = text_encoder_name
+        self.text_config = text_config
+        super().__init__(**kwargs)
+
+
+class Cnn8RnnLaionClapGroundingModel(PreTrainedModel):
     """``model(audio, audio_len, text) -> frame_sim`` of the released CLAP checkpoints (reference
     models/hf_modeling_grounding.py:319-352): Cnn8Rnn + LaionClapEncoder + DotProduct inside
-    BiEncoder(add_proj=True).  ``text`` is a list of strings (needs the Hugging Face tokenizer of
-    ``text_encoder_name``) or an already tokenised dict with ``input_ids`` / ``attention_mask``."""
+    BiEncoder(add_proj=True); a ``PreTrainedModel``, so ``save_pretrained`` / ``from_pretrained`` directories
+    interchange with the reference's (identical parameter names under ``model.``).  ``text`` is a list of strings
+    (needs the Hugging Face tokenizer of ``text_encoder_name``) or an already tokenised dict with ``input_ids`` /
+    ``attention_mask``."""
     config_class = Cnn8RnnLaionClapGroundingConfig
+    base_model_prefix = "model"
 
     def __init__(self, config: Cnn8RnnLaionClapGroundingConfig, text_tokenizer=None):
-        super().__init__()
+        super().__init__(config)
         from .text_encoder import LaionClapEncoder
-        self.config = config
         self.text_tokenizer = text_tokenizer
-        if text_tokenizer is None and isinstance(config.text_encoder_name, str):
-            from transformers import AutoTokenizer
-            self.text_tokenizer = AutoTokenizer.from_pretrained(config.text_encoder_name)
+        if config.text_config is not None:
+            from transformers import ClapTextConfig
+            tower = ClapTextConfig(**{k: v for k, v in config.text_config.items() if k != "model_type"})
+        else:
+            tower = config.text_encoder_name
+            if text_tokenizer is None:
+                from transformers import AutoTokenizer
+                self.text_tokenizer = AutoTokenizer.from_pretrained(config.text_encoder_name)
         self.model = BiEncoder(
             audio_encoder=Cnn8Rnn(sample_rate=config.sample_rate),
-            text_encoder=LaionClapEncoder(model_type=config.text_encoder_name),
+            text_encoder=LaionClapEncoder(model_type=tower),
             match_fn=DotProduct(),
             shared_dim=config.shared_dim,
             add_proj=True)
+        if hasattr(self, "post_init"):
+            self.post_init()
 
-    @property
-    def device(self):
-        return next(self.parameters()).device
+    def _init_weights(self, module):       # the sub-modules initialise themselves (reference init distributions)
+        pass
 
     def forward(self, audio: torch.Tensor, audio_len, text) -> torch.Tensor:
-        device = self.device
+        device = next(self.parameters()).device
         if isinstance(text, dict):
             tokens = {k: torch.as_tensor(v).to(device) for k, v in text.items()}
         else:
