@@ -208,6 +208,12 @@ def test_clap_facade_is_a_pretrained_model_and_round_trips(tmp_path):
     again = Cnn8RnnLaionClapGroundingModel.from_pretrained(tmp_path)
     sd1, sd2 = model.state_dict(), again.state_dict()
     assert set(sd1) == set(sd2) and all(torch.equal(sd1[k], sd2[k]) for k in sd1)
+    # the README call: AutoModel.from_pretrained(<checkpoint dir>) after registering the B200 classes
+    from transformers import AutoModel
+    from texttoaudiogrounding_b200.models.hf_modeling_grounding import register_auto_classes
+    register_auto_classes()
+    auto = AutoModel.from_pretrained(tmp_path)
+    assert type(auto) is Cnn8RnnLaionClapGroundingModel and auto.config.sample_rate == 32000
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         again(torch.zeros(1, 32000), [32000], {"input_ids": torch.tensor([[0, 5, 2]]),
                                                  "attention_mask": torch.ones(1, 3, dtype=torch.long)})

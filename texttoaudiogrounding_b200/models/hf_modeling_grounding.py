@@ -130,3 +130,18 @@ class Cnn8RnnLaionClapGroundingModel(PreTrainedModel):
         input_dict = {"waveform": audio.to(device), "waveform_len": audio_len, "specaug": False}
         input_dict.update(tokens)
         return self.model(input_dict)["frame_sim"]
+
+
+def register_auto_classes() -> None:
+    """``AutoConfig`` / ``AutoModel`` resolve ``model_type: cnn8rnn_laionclap_grounding`` to the B200 classes, so the
+    reference README's ``AutoModel.from_pretrained(path)`` call (README.md:8-39) works on a local checkpoint
+    directory without ``trust_remote_code``."""
+    from transformers import AutoConfig, AutoModel
+    try:
+        AutoConfig.register(Cnn8RnnLaionClapGroundingConfig.model_type, Cnn8RnnLaionClapGroundingConfig)
+    except ValueError:
+        pass                                   # already registered
+    try:
+        AutoModel.register(Cnn8RnnLaionClapGroundingConfig, Cnn8RnnLaionClapGroundingModel)
+    except ValueError:
+        pass
