@@ -407,7 +407,13 @@ extern "C" int tag_conv_tc_fwd(const void* x, const void* w, void* y, int y_dtyp
         return TAG_ERR_BAD_ARG;
     const int TH = 128 / W;
     if (TH > 256) return TAG_ERR_BAD_ARG;
-    const int block_n = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    // widest N tile that still gives about one tile per SM: a 320-row GEMM (the CLAP text tower) on 256-wide tiles
+    // would run on 9 CTAs, each walking the whole K loop at single-SM TMA speed
+    int block_n = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    {
+        const long m_tiles = (long)B * ((H + TH - 1) / TH);
+        while (block_n > 64 && m_tiles * (Cout / block_n) < 111) block_n /= 2;
+    }
     CUtensorMap tx, tw;
     int rc = make_act_tmap(&tx, x, B, H, W, Cin, W, TH);
     if (rc != TAG_OK) return rc;
