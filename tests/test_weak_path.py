@@ -156,3 +156,34 @@ def test_multitext_weak_losses_and_gradients_match_reference_golden(tag):
         gn = p.grad.double().pow(2).sum().sqrt().item()
         assert abs(gn - ref) <= 1e-2 * ref + 1e-6, (n, gn, ref)
         assert cosine(sub(p.grad, 128), g[f"grad_sub/{tag}/{n}"]) > 0.999, n
+
+
+@pytest.mark.gpu
+def test_weak_fused_train_step_matches_reference_golden():
+    """Production path of the weak runners: flat buffers + fused clip/Adam (and CUDA-graph replay) for
+    MultiTextBiEncoder + ClipBceLoss, against the reference's loss / gradient norms and against its own eager run."""
+    from texttoaudiogrounding_b200.train import WeakFusedTrainStep
+    g, sd, batch = load()
+    model = _build_multi(sd).train()
+    model.audio_encoder.dropout_enabled = False
+    ts = WeakFusedTrainStep(model, lr=1e-3, max_grad_norm=1.0, use_graph=False)
+    loss = ts.step(batch).item()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(loss, g["train_loss/clip"].item(), rtol=1e-3)
+    np.testing.assert_allclose(ts.norm_out.item(), g["train_total_norm/clip"].item(), rtol=1e-2)
+    np.testing.assert_allclose(ts.clip.cpu().numpy(), g["train_clip_sim/clip"], atol=1e-3)
+    for n, p in model.named_parameters():
+        ref = g[f"grad_norm/clip/{n}"].item()
+        gn = p.grad.double().pow(2).sum().sqrt().item()
+        assert abs(gn - ref) <= 1e-2 * ref + 1e-6, (n, gn, ref)
+        assert cosine(sub(p.grad, 128), g[f"grad_sub/clip/{n}"]) > 0.999, n
+    # graph replay follows the eager trajectory
+    sd2 = O.synth_state_dict(seed=1, sharpen=1.0, perturb_bn=True)
+    losses = {}
+    for use_graph in (False, True):
+        m = _build_multi(sd2).train()
+        m.audio_encoder.dropout_enabled = False
+        t2 = WeakFusedTrainStep(m, use_graph=use_graph)
+        losses[use_graph] = [t2.step(batch).item() for _ in range(5)]
+    np.testing.assert_allclose(losses[True], losses[False], rtol=5e-3)
+    assert losses[False][-1] < losses[False][0]

@@ -332,3 +332,81 @@ class FusedTrainStep:
         self._allreduce()
         self._graphs["optim"].replay()
         return self.loss_out
+
+
+class WeakFusedTrainStep(FusedTrainStep):
+    """The same flat-buffer / CUDA-graph step for the weakly supervised multi-phrase configuration
+    MultiTextBiEncoder(Cnn8Rnn, EmbeddingAgg, DotProduct, pooling=...) + ClipBceLoss + Adam — the body of the weak
+    runners' train loop (reference python_scripts/training/run_weak_phrase.py:39-96; most of the reference's
+    eg_configs).  Batch schema: ``waveform`` [B, L], ``waveform_len`` [B], ``text`` [B, n, N], ``text_len`` [B, n],
+    ``label`` [B, n] (clip-level 0/1 targets), n <= 64 phrases per clip."""
+
+    def __init__(self, model: nn.Module, **kw):
+        from .models.utils import POOL_MODES
+        super().__init__(model, **kw)
+        self.pool_mode = POOL_MODES[getattr(model, "pooling", "linear_softmax")]
+
+    def _host_views(self, batch: Dict):
+        wav = batch["waveform"]
+        B, L = wav.shape
+        Tp = (L // engine.HOP + 1) // 4
+        text = torch.as_tensor(batch["text"])
+        n, N = text.shape[1], text.shape[2]
+        if n > 64:
+            raise NotImplementedError("WeakFusedTrainStep: at most 64 phrases per clip")
+        length = torch.as_tensor(batch["waveform_len"]).to(torch.long)
+        length = torch.clamp((length // engine.HOP + 1) // 4, 1, Tp)
+        label = torch.as_tensor(batch["label"]).to(torch.float32)
+        src = {"waveform": wav, "text": text.reshape(B * n, N),
+               "text_len": torch.as_tensor(batch["text_len"]).to(torch.long).reshape(B * n),
+               "label": label.reshape(B, n), "length": length}
+        wdt = torch.float16 if wav.dtype == torch.float16 else torch.float32
+        return (B, L, n, N, wdt), src
+
+    def _alloc_inputs(self, key):
+        B, L, n, N, wdt = key
+        dev = self.device
+        return {
+            "key": key,
+            "waveform": torch.empty(B, L, device=dev, dtype=wdt),
+            "text": torch.empty(B * n, N, device=dev, dtype=torch.long),
+            "text_len": torch.empty(B * n, device=dev, dtype=torch.long),
+            "label": torch.empty(B, n, device=dev, dtype=torch.float32),
+            "length": torch.empty(B, device=dev, dtype=torch.long),
+        }
+
+    def _fwd_bwd(self, wav, text, text_len, label, length):
+        enc = self.enc
+        self.flat_g.zero_()
+        if self.prep is not None:
+            self.prep.run()
+        emb, ectx = engine.encoder_forward(
+            self.Wt, wav, training=True, bn_training=enc.bn0.training, dropout=enc.dropout_enabled,
+            seed=self.base_seed, dtype=enc.compute_dtype, save=True, seed_dev=self.step_dev)
+        B, Tp, D = emb.shape
+        n = label.shape[1]
+        dev = emb.device
+        ew = self.txt.embedding.core.weight
+        V, N = ew.shape[0], text.shape[1]
+        f32 = dict(device=dev, dtype=torch.float32)
+        seq = torch.empty(B * n, D, **f32)
+        call("tag_embed_mean_fwd", text, text_len, ew.data, None, seq, B * n, N, D, V)
+        sim = torch.empty(B, Tp, n, **f32)
+        call("tag_multi_dot_sigmoid_fwd", emb, seq, sim, B, Tp, n, D, self.scale)
+        clip = torch.empty(B, n, **f32)
+        call("tag_pool_with_lens_fwd", sim, length, self.pool_mode, clip, B, Tp, n)
+        # ClipBceLoss = mean BCE over all B*n clip-level probabilities (losses.py:38-43)
+        if getattr(self, "_full_n", None) is None or self._full_n.numel() != B or int(self._n_cached) != n:
+            self._full_n = torch.full((B,), n, device=dev, dtype=torch.long)
+            self._n_cached = n
+        d_clip = torch.empty(B, n, **f32)
+        call("tag_frame_bce", clip, n, label, label.stride(0), self._full_n, B, n, self.loss_out, d_clip, n, 1.0)
+        d_sim = torch.empty_like(sim)
+        call("tag_pool_with_lens_bwd", d_clip, sim, clip, length, self.pool_mode, d_sim, B, Tp, n)
+        d_emb = torch.empty_like(emb)
+        d_seq = torch.empty_like(seq)
+        ws = torch.empty_like(sim)
+        call("tag_multi_dot_sigmoid_bwd", d_sim, sim, emb, seq, d_emb, d_seq, ws, B, Tp, n, D, self.scale)
+        call("tag_embed_mean_bwd", text, text_len, d_seq, ew.grad, B * n, N, D, V)
+        engine.encoder_backward(self.Wt, ectx, d_emb, self.G, side_stream=self.side_stream)
+        self.sim, self.clip = sim, clip
