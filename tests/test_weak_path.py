@@ -187,3 +187,23 @@ def test_weak_fused_train_step_matches_reference_golden():
         losses[use_graph] = [t2.step(batch).item() for _ in range(5)]
     np.testing.assert_allclose(losses[True], losses[False], rtol=5e-3)
     assert losses[False][-1] < losses[False][0]
+
+
+@pytest.mark.gpu
+def test_weak_fused_train_step_clip_frame_loss_matches_reference_golden():
+    """ClipFrameBceLoss(frame_weight=0.3) inside the fused weak step (eager and graph-replayed)."""
+    from texttoaudiogrounding_b200.train import WeakFusedTrainStep
+    g, sd, batch = load()
+    for use_graph in (False, True):
+        model = _build_multi(sd).train()
+        model.audio_encoder.dropout_enabled = False
+        ts = WeakFusedTrainStep(model, frame_weight=0.3, lr=0.0, use_graph=use_graph)
+        for _ in range(3 if use_graph else 1):           # lr = 0: every step sees the same weights
+            loss = ts.step(batch).item()
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(loss, g["train_loss/clipframe"].item(), rtol=1e-3)
+        np.testing.assert_allclose(ts.norm_out.item(), g["train_total_norm/clipframe"].item(), rtol=1e-2)
+        for n, p in model.named_parameters():
+            ref = g[f"grad_norm/clipframe/{n}"].item()
+            gn = p.grad.double().pow(2).sum().sqrt().item()
+            assert abs(gn - ref) <= 1e-2 * ref + 1e-6, (n, gn, ref, use_graph)

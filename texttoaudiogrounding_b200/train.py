@@ -341,10 +341,17 @@ class WeakFusedTrainStep(FusedTrainStep):
     eg_configs).  Batch schema: ``waveform`` [B, L], ``waveform_len`` [B], ``text`` [B, n, N], ``text_len`` [B, n],
     ``label`` [B, n] (clip-level 0/1 targets), n <= 64 phrases per clip."""
 
-    def __init__(self, model: nn.Module, **kw):
+    _INPUT_KEYS = ("waveform", "text", "text_len", "label", "length", "strong_label")
+
+    def __init__(self, model: nn.Module, frame_weight: Optional[float] = None, **kw):
+        """``frame_weight`` = w selects ClipFrameBceLoss: (1 - w) * clip BCE + w * frame BCE on ``strong_label``
+        [B, T', n] (losses.py:186-210); None = ClipBceLoss."""
         from .models.utils import POOL_MODES
         super().__init__(model, **kw)
         self.pool_mode = POOL_MODES[getattr(model, "pooling", "linear_softmax")]
+        self.frame_weight = frame_weight
+        self.loss_clip = torch.zeros((), device=self.device, dtype=torch.float32)
+        self.loss_frame = torch.zeros((), device=self.device, dtype=torch.float32)
 
     def _host_views(self, batch: Dict):
         wav = batch["waveform"]
@@ -360,6 +367,13 @@ class WeakFusedTrainStep(FusedTrainStep):
         src = {"waveform": wav, "text": text.reshape(B * n, N),
                "text_len": torch.as_tensor(batch["text_len"]).to(torch.long).reshape(B * n),
                "label": label.reshape(B, n), "length": length}
+        if self.frame_weight is not None:
+            strong = torch.as_tensor(batch["strong_label"]).to(torch.float32)
+            if tuple(strong.shape) != (B, Tp, n):
+                raise RuntimeError(f"strong_label must be [B, T', n] = {(B, Tp, n)}, got {tuple(strong.shape)}")
+            src["strong_label"] = strong
+        else:
+            src["strong_label"] = torch.zeros(1)
         wdt = torch.float16 if wav.dtype == torch.float16 else torch.float32
         return (B, L, n, N, wdt), src
 
@@ -373,7 +387,14 @@ class WeakFusedTrainStep(FusedTrainStep):
             "text_len": torch.empty(B * n, device=dev, dtype=torch.long),
             "label": torch.empty(B, n, device=dev, dtype=torch.float32),
             "length": torch.empty(B, device=dev, dtype=torch.long),
+            "strong_label": torch.empty((B, (L // engine.HOP + 1) // 4, n) if self.frame_weight is not None else (1,),
+                                        device=dev, dtype=torch.float32),
         }
+
+    def _prepare_static(self, batch: Dict):
+        s = super()._prepare_static(batch)
+        self._strong = s["strong_label"]
+        return s
 
     def _fwd_bwd(self, wav, text, text_len, label, length):
         enc = self.enc
@@ -400,9 +421,19 @@ class WeakFusedTrainStep(FusedTrainStep):
             self._full_n = torch.full((B,), n, device=dev, dtype=torch.long)
             self._n_cached = n
         d_clip = torch.empty(B, n, **f32)
-        call("tag_frame_bce", clip, n, label, label.stride(0), self._full_n, B, n, self.loss_out, d_clip, n, 1.0)
+        fw = self.frame_weight
+        call("tag_frame_bce", clip, n, label, label.stride(0), self._full_n, B, n,
+             self.loss_out if fw is None else self.loss_clip, d_clip, n, 1.0 if fw is None else 1.0 - fw)
         d_sim = torch.empty_like(sim)
         call("tag_pool_with_lens_bwd", d_clip, sim, clip, length, self.pool_mode, d_sim, B, Tp, n)
+        if fw is not None:
+            # frame BCE over [B, T', n] with the length mask expanded over the phrases (losses.py:26-35): element
+            # (b, t, j) is valid iff its flat index t*n + j < length[b]*n
+            strong = self._strong
+            d_frame = torch.empty_like(sim)
+            call("tag_frame_bce", sim, Tp * n, strong, Tp * n, length * n, B, Tp * n, self.loss_frame, d_frame, Tp * n, fw)
+            d_sim.add_(d_frame)
+            torch.add(self.loss_clip * (1.0 - fw), self.loss_frame, alpha=fw, out=self.loss_out)
         d_emb = torch.empty_like(emb)
         d_seq = torch.empty_like(seq)
         ws = torch.empty_like(sim)
