@@ -191,3 +191,27 @@ def test_align_models_loss_and_gradients_match_reference_golden(level, pooling):
         gn = p.grad.double().pow(2).sum().sqrt().item()
         assert abs(gn - ref) <= 1e-2 * ref + 1e-6, (n, gn, ref)
         assert cosine(sub(p.grad, 128), g[f"grad_sub/{tag}/{n}"]) > 0.999, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level,pooling", TRAIN_TAGS[:3])
+def test_align_fused_train_step_matches_reference_golden(level, pooling):
+    """Production path of the sentence-level runners: flat buffers + fused clip/Adam (+ CUDA-graph replay) for
+    AudioTextAlignBy{Word,Phrase} + MaxMarginRankingLoss, against the reference's loss and gradient norms."""
+    from texttoaudiogrounding_b200.train import AlignFusedTrainStep
+    g, sd, batch = load()
+    tag = f"{level}/{pooling}"
+    for use_graph in (False, True):
+        model = _build(sd, level, pooling).train()
+        model.audio_encoder.dropout_enabled = False
+        ts = AlignFusedTrainStep(model, margin=1, fix_norm=True, lamda1=1, lr=0.0, use_graph=use_graph)
+        for _ in range(3 if use_graph else 1):           # lr = 0: every step sees the same weights
+            loss = ts.step(batch).item()
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(loss, g[f"train_loss/{tag}"].item(), rtol=1e-3)
+        np.testing.assert_allclose(ts.sim.cpu().numpy(), g[f"train_sim/{tag}"], atol=1e-3)
+        np.testing.assert_allclose(ts.norm_out.item(), g[f"train_total_norm/{tag}"].item(), rtol=1e-2)
+        for n, p in model.named_parameters():
+            ref = g[f"grad_norm/{tag}/{n}"].item()
+            gn = p.grad.double().pow(2).sum().sqrt().item()
+            assert abs(gn - ref) <= 1e-2 * ref + 1e-6, (n, gn, ref, use_graph)

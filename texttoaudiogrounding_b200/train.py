@@ -212,7 +212,7 @@ class FusedTrainStep:
             torch.distributed.all_reduce(self.flat_g, group=self.pg)
 
     def _eager(self, s):
-        self._fwd_bwd(s["waveform"], s["text"], s["text_len"], s["label"], s["length"])
+        self._fwd_bwd(s["waveform"], s["text"], s["text_len"], s.get("label"), s["length"])
         self._allreduce()
         self._optim()
 
@@ -323,7 +323,7 @@ class FusedTrainStep:
             torch.cuda.synchronize()
             g1 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
-                self._fwd_bwd(s["waveform"], s["text"], s["text_len"], s["label"], s["length"])
+                self._fwd_bwd(s["waveform"], s["text"], s["text_len"], s.get("label"), s["length"])
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2):
                 self._optim()
@@ -441,3 +441,108 @@ class WeakFusedTrainStep(FusedTrainStep):
         call("tag_embed_mean_bwd", text, text_len, d_seq, ew.grad, B * n, N, D, V)
         engine.encoder_backward(self.Wt, ectx, d_emb, self.G, side_stream=self.side_stream)
         self.sim, self.clip = sim, clip
+
+
+class _CtxShim:
+    """Stand-in for the autograd context so a fused step can drive an autograd Function's forward / backward bodies."""
+    needs_input_grad = (True, True, False, False, False, False, False)
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
+
+
+class AlignFusedTrainStep(FusedTrainStep):
+    """Flat-buffer / CUDA-graph train step of the sentence-level alignment configurations: AudioTextAlignByWord or
+    AudioTextAlignByPhrase (Cnn8Rnn + EmbeddingAgg + align.DotProduct + a sim_pooling.Audio*Text* module) with
+    MaxMarginRankingLoss and Adam (reference eg_configs/weakly_supervised/audiocaps/sentence_level/*).  Batch schema:
+    word level ``text`` [B, N], ``text_len`` [B]; phrase level ``phrases`` [txt_num, N], ``phrases_len`` [txt_num],
+    ``phrases_num`` (B counts summing to txt_num); plus ``waveform`` / ``waveform_len``."""
+    _INPUT_KEYS = ("waveform", "text", "text_len", "pool_len", "pad_index", "length")
+
+    def __init__(self, model: nn.Module, margin: float = 1.0, fix_norm: bool = True, lamda1: float = 1.0, **kw):
+        from .models.align import AUDIO_POOL, TEXT_POOL
+        from .models.audio_text_model import AudioTextAlignByWord
+        super().__init__(model, **kw)
+        self.word_level = isinstance(model, AudioTextAlignByWord)
+        self.a_mode = AUDIO_POOL[model.sim_pooling.audio_pool]
+        self.t_mode = TEXT_POOL[model.sim_pooling.text_pool]
+        self.scale = 1.0 / (self.enc.embed_dim ** 0.5) if getattr(model.match_fn, "scaled", False) else 1.0
+        self.margin, self.fix_norm, self.lamda1 = float(margin), bool(fix_norm), float(lamda1)
+
+    def _host_views(self, batch: Dict):
+        wav = batch["waveform"]
+        B, L = wav.shape
+        Tp = (L // engine.HOP + 1) // 4
+        length = torch.as_tensor(batch["waveform_len"]).to(torch.long)
+        length = (length // engine.HOP + 1) // 4
+        if self.word_level:
+            text = torch.as_tensor(batch["text"]).to(torch.long)
+            text_len = torch.as_tensor(batch["text_len"]).to(torch.long)
+            pool_len, pad_index, width = text_len, torch.zeros(1, dtype=torch.long), text.shape[1]
+        else:
+            key = batch.get("text_key", "phrases")
+            text = torch.as_tensor(batch[key]).to(torch.long)
+            text_len = torch.as_tensor(batch[f"{key}_len"]).to(torch.long)
+            num = [int(v) for v in batch[f"{key}_num"]]
+            width = max(num)
+            pad_index = torch.as_tensor([b * width + j for b, c in enumerate(num) for j in range(c)], dtype=torch.long)
+            pool_len = torch.as_tensor(num, dtype=torch.long)
+        src = {"waveform": wav, "text": text, "text_len": text_len, "pool_len": pool_len, "pad_index": pad_index,
+               "length": length}
+        wdt = torch.float16 if wav.dtype == torch.float16 else torch.float32
+        return (B, L, text.shape[0], text.shape[1], width, wdt), src
+
+    def _alloc_inputs(self, key):
+        B, L, rows, N, width, wdt = key
+        dev = self.device
+        lng = dict(device=dev, dtype=torch.long)
+        self._width = width
+        return {"key": key, "waveform": torch.empty(B, L, device=dev, dtype=wdt), "text": torch.empty(rows, N, **lng),
+                "text_len": torch.empty(rows, **lng), "pool_len": torch.empty(B, **lng),
+                "pad_index": torch.empty(1 if self.word_level else rows, **lng), "length": torch.empty(B, **lng)}
+
+    def _prepare_static(self, batch: Dict):
+        s = super()._prepare_static(batch)
+        self._extra = (s["pool_len"], s["pad_index"], s["key"][4])
+        return s
+
+    def _eager(self, s):
+        self._fwd_bwd(s["waveform"], s["text"], s["text_len"], None, s["length"])
+        self._allreduce()
+        self._optim()
+
+    def _fwd_bwd(self, wav, text, text_len, label, length):
+        from .models.align import _AlignPoolFunction
+        enc = self.enc
+        pool_len, pad_index, width = self._extra
+        self.flat_g.zero_()
+        if self.prep is not None:
+            self.prep.run()
+        emb, ectx = engine.encoder_forward(
+            self.Wt, wav, training=True, bn_training=enc.bn0.training, dropout=enc.dropout_enabled,
+            seed=self.base_seed, dtype=enc.compute_dtype, save=True, seed_dev=self.step_dev)
+        B, Tp, D = emb.shape
+        dev = emb.device
+        ew = self.txt.embedding.core.weight
+        V = ew.shape[0]
+        rows, N = text.shape
+        f32 = dict(device=dev, dtype=torch.float32)
+        seq = torch.empty(rows, D, **f32)
+        token_emb = torch.empty(rows, N, D, **f32) if self.word_level else None
+        call("tag_embed_mean_fwd", text, text_len, ew.data, token_emb, seq, rows, N, D, V)
+        if self.word_level:
+            text3 = token_emb                                              # [B, N, D]
+        else:
+            text3 = torch.zeros(B * width, D, **f32).index_copy_(0, pad_index, seq).view(B, width, D)
+        ctx = _CtxShim()
+        sim = _AlignPoolFunction.forward(ctx, emb, text3, length, pool_len, self.a_mode, self.t_mode, self.scale)
+        d_sim = torch.empty(B, B, **f32)
+        call("tag_max_margin_rank", sim, B, self.margin, self.lamda1, int(self.fix_norm), self.loss_out, d_sim)
+        d_emb, d_text3 = _AlignPoolFunction.backward(ctx, d_sim)[:2]
+        if self.word_level:
+            call("tag_embed_token_bwd", text, d_text3.contiguous(), ew.grad, rows, N, D, V)
+        else:
+            d_seq = d_text3.reshape(B * width, D).index_select(0, pad_index)
+            call("tag_embed_mean_bwd", text, text_len, d_seq, ew.grad, rows, N, D, V)
+        engine.encoder_backward(self.Wt, ectx, d_emb.contiguous(), self.G, side_stream=self.side_stream)
+        self.sim = sim
