@@ -62,7 +62,16 @@ def main():
     mr = engine.compute_mel_range(fb)
     db = torch.empty(B, T0, 64, **f32)
     st = torch.zeros(128, device=dev, dtype=torch.float64)
-    report("logmel_fwd", timeit(lambda: call("tag_logmel_fwd", wav, B, L, L, window, fb, mr, db, st)),
+    nnz = engine.mel_nnz(mr)
+    report("logmel_fwd_v2 (warp per frame pair, fp32 wav)",
+           timeit(lambda: call("tag_logmel_fwd_v2", wav, 0, B, L, L, window, fb, mr, nnz, db, st)),
+           wav.numel() * 4 + db.numel() * 4)
+    wav16 = wav.half()
+    report("logmel_fwd_v2 (fp16 wav)",
+           timeit(lambda: call("tag_logmel_fwd_v2", wav16, 2, B, L, L, window, fb, mr, nnz, db, st)),
+           wav.numel() * 2 + db.numel() * 4)
+    report("logmel_fwd (smem Stockham, general filterbank)",
+           timeit(lambda: call("tag_logmel_fwd", wav, B, L, L, window, fb, mr, db, st)),
            wav.numel() * 4 + db.numel() * 4)
     x0 = torch.empty(B, T0, 64, device=dev, dtype=bf)
     sc = torch.rand(512, **f32) + 0.5
