@@ -217,3 +217,22 @@ def test_clap_facade_is_a_pretrained_model_and_round_trips(tmp_path):
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         again(torch.zeros(1, 32000), [32000], {"input_ids": torch.tensor([[0, 5, 2]]),
                                                  "attention_mask": torch.ones(1, 3, dtype=torch.long)})
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU restatement on the host cores) must print one JSON line with the same
+    metric / unit / config as the B200 arm plus the cpu_baseline and e2e objects; it needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    base = json.load(open(os.path.join(root, "BASELINE.json")))
+    assert line["impl"] == "reference" and line["metric"] == base["metric"] and line["unit"] == "clips/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["n_gpus"] == 1
+    assert "configs[2]" in line["config"]["workload"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
