@@ -81,5 +81,8 @@ def test_full_size_train_step_bf16_tensor_path_agrees_with_fp32_path():
     assert np.isfinite(l32) and np.isfinite(l16)
     assert abs(l16 - l32) <= 3e-2 * abs(l32), (l16, l32)
     assert abs(n16 - n32) <= 5e-2 * n32, (n16, n32)
+    # measured (scripts/fullsize_grad_agreement.py): every parameter >= 0.9837 except bn0.weight at 0.954 — the gradient
+    # of the input normalisation collects the bf16 rounding of all eight conv layers; run-to-run spread is 1e-13
     for n in g32:
-        assert cosine(g16[n], g32[n]) > 0.95, n
+        floor = 0.93 if ".bn0." in n else 0.97
+        assert cosine(g16[n], g32[n]) > floor, (n, cosine(g16[n], g32[n]))
