@@ -1,7 +1,7 @@
 """Inference façade with the call signature of the reference's Hugging Face model
 (models/hf_modeling_grounding.py:319-352, README.md:8-39): ``model(audio, audio_len, text) -> frame_sim``.
 
-The in-repo reference façade wires the CLAP text tower (not built here); this is the same
+The in-repo reference façade wires the CLAP text tower (Cnn8RnnLaionClapGroundingModel below); this is the same
 surface for the cnn8rnn-w2vmean model of the hot path: Cnn8Rnn + EmbeddingAgg(mean) + DotProduct with the
 reference's DictTokenizer (whitespace tokens, ``<unk>`` for unknown words).  ``config`` carries the reference's
 ``sample_rate`` / ``shared_dim`` plus the vocabulary."""
