@@ -222,6 +222,19 @@ int tag_max_margin_rank(const float* sim, int n, float margin, float lamda1, int
 int tag_embed_token_bwd(const long long* text, const float* d_token, float* d_emb, int B, int N, int D, int vocab,
                         cudaStream_t stream);
 
+/* EmbeddingAgg(aggregation="attention") = AttentionPooling (models/text_encoder.py:46-58, 84-85): score = x w + bias
+ * masked with -1e10 beyond lens, softmax over the N tokens (N <= 128), out [B,D] = sum_n weight[n] x[b,n,:];
+ * weight [B,N] is saved for backward.  bwd: d_x overwritten, d_w [D] and d_bias [1] accumulated. */
+int tag_attn_pool_fwd(const float* x, const long long* lens, const float* w, const float* bias, float* out,
+                      float* weight, int B, int N, int D, cudaStream_t stream);
+int tag_attn_pool_bwd(const float* d_out, const float* x, const float* w, const float* weight, float* d_x,
+                      float* d_w, float* d_bias, int B, int N, int D, cudaStream_t stream);
+/* F.interpolate(size=To, mode="linear", align_corners=False) along T — BiEncoder / MultiTextBiEncoder(upsample=True),
+ * models/audio_text_model.py:90-97, 216-223.  x [outer, T, inner] -> y [outer, To, inner]; bwd is its transpose
+ * (dx is zeroed inside). */
+int tag_upsample_linear_fwd(const float* x, float* y, long outer, int T, int To, int inner, cudaStream_t stream);
+int tag_upsample_linear_bwd(const float* dy, float* dx, long outer, int T, int To, int inner, cudaStream_t stream);
+
 /* ---- attention-type heads of the later configurations — SURVEY.md §8f rank 2 (BASELINE.json configs[3]).  All fp32,
  * E = 512; the dense projections around them are tag_conv_fwd / tag_conv_wgrad with taps = 1.
  * text_encoder.SelfAttention (models/text_encoder.py:240-268): out[b,0] = cls + pe[0], out[b,1+n] = emb[text[b,n]] +
@@ -296,8 +309,9 @@ int tag_frame_regions(const float* sim, long sim_stride, const double* threshold
 
 /* ---- optimizer step — clip_grad_norm_ + Adam, python_scripts/training/run_strong.py:143-145 */
 int tag_sumsq(const float* g, long n, double* out, cudaStream_t stream);
+/* lr_dev (device float, may be NULL) overrides lr: a scheduler (run_strong.py:136-137) then acts on a captured graph */
 int tag_clip_adam(float* p, const float* g, float* m, float* v, long n, const double* sumsq,
-                  long long* step_ptr, float grad_mult, float max_norm, float lr, float beta1,
+                  long long* step_ptr, float grad_mult, float max_norm, float lr, const float* lr_dev, float beta1,
                   float beta2, float eps, float* norm_out, cudaStream_t stream);
 int tag_cast_f32_to_bf16(const float* x, void* y, long n, cudaStream_t stream);
 /* all bf16 GEMM operands of one step from the fp32 master weights in one launch; `table` (device) holds

@@ -932,3 +932,158 @@ def exp_neg_l2_match(audio_emb, seq_emb, l2norm: bool = True):
     if l2norm:
         a, s = F.normalize(a, dim=-1), F.normalize(s, dim=-1)
     return torch.exp(-torch.norm(a - s.unsqueeze(1), dim=-1))
+
+
+# =====================================================================================================
+# Options of the same model classes reachable from the run_strong.py / run_weak_phrase.py config surface:
+#   * BiEncoder / MultiTextBiEncoder(add_proj=True) ...... models/audio_text_model.py:35-46, 79-88, 150-151, 180-185
+#   * MultiTextBiEncoder(cross_encoder=...) ............... models/audio_text_model.py:166-178
+#   * upsample=True (F.interpolate linear) ............... models/audio_text_model.py:90-97, 216-223
+#   * EmbeddingAgg(aggregation="attention") .............. models/text_encoder.py:46-58, 84-85
+def proj_state(seed: int, E: int = EMBED, gain: float = 1.0):
+    """audio_proj / text_proj = nn.Linear(E, shared_dim = E): Xavier-uniform matrices (x gain), small biases."""
+    sd = {}
+    for idx, key in enumerate(("audio_proj", "text_proj")):
+        g = torch.Generator().manual_seed(seed * 4099 + idx)
+        a = gain * math.sqrt(6.0 / (2 * E))
+        sd[key + ".weight"] = (torch.rand(E, E, generator=g) * 2 - 1) * a
+        sd[key + ".bias"] = (torch.rand(E, generator=g) * 2 - 1) * 0.1
+    return sd
+
+
+def attn_pool_state(seed: int, E: int = EMBED, gain: float = 1.0):
+    """text_encoder.attn.fc = nn.Linear(E, 1) of AttentionPooling."""
+    g = torch.Generator().manual_seed(seed * 5003 + 1)
+    return {"text_encoder.attn.fc.weight": (torch.rand(1, E, generator=g) * 2 - 1) * gain * math.sqrt(6.0 / E),
+            "text_encoder.attn.fc.bias": (torch.rand(1, generator=g) * 2 - 1) * 0.1}
+
+
+def attention_pooling(sd, emb, lens):
+    """models/text_encoder.py:51-58: masked (-1e10) softmax over the tokens of fc(x), weighted sum of x."""
+    w, b = sd["text_encoder.attn.fc.weight"], sd["text_encoder.attn.fc.bias"]
+    score = (emb * w.view(1, 1, -1)).sum(-1) + b
+    mask = generate_length_mask(torch.as_tensor(lens), emb.size(1))
+    score = score.masked_fill(~mask, -1e10)
+    weight = torch.softmax(score, dim=1)
+    return (emb * weight.unsqueeze(-1)).sum(1)
+
+
+def linear_upsample(x, size: int):
+    """F.interpolate(size=size, mode="linear", align_corners=False) along dim 1 of x [B,T] or [B,T,n], written out
+    (ATen upsample_linear1d): scale = T/size, src = scale*(dst + 0.5) - 0.5 clamped at 0, neighbours
+    i0 = min(floor(src), T-1), i1 = min(i0+1, T-1), weight lam = src - i0."""
+    T = x.shape[1]
+    dst = torch.arange(size, dtype=torch.float32)
+    scale = torch.tensor(float(T)) / torch.tensor(float(size))          # float32 division, as ATen
+    src = (scale * (dst + 0.5) - 0.5).clamp_min(0.0)
+    i0 = torch.clamp(src.floor().long(), max=T - 1)
+    i1 = torch.clamp(i0 + 1, max=T - 1)
+    lam = (src - i0.to(src.dtype)).clamp(0.0, 1.0)
+    lam = lam.view([1, -1] + [1] * (x.ndim - 2))
+    return (1.0 - lam) * x.index_select(1, i0) + lam * x.index_select(1, i1)
+
+
+def biencoder_variant_forward(sd, input_dict, training=False, dropout=True, dropout_masks=None, fast_gru=False,
+                              add_proj=False, upsample=False, aggregation="mean"):
+    """BiEncoder.forward (models/audio_text_model.py:58-98) with its options: projections after the encoders,
+    attention aggregation of the word embeddings, x4 linear upsampling of frame_sim."""
+    a = cnn8rnn_forward(sd, input_dict["waveform"], input_dict["waveform_len"], training,
+                        dropout_masks, dropout, None, fast_gru)
+    t = embedding_mean(sd, input_dict["text"], input_dict["text_len"])
+    if aggregation == "attention":
+        t["seq_emb"] = attention_pooling(sd, t["token_emb"], input_dict["text_len"])
+    audio, seq = a["embedding"], t["seq_emb"]
+    if add_proj:
+        audio = audio @ sd["audio_proj.weight"].t() + sd["audio_proj.bias"]
+        seq = seq @ sd["text_proj.weight"].t() + sd["text_proj.bias"]
+    frame_sim, _ = dot_product_match(audio, seq)
+    length = a["length"]
+    if upsample:
+        frame_sim = linear_upsample(frame_sim, frame_sim.size(1) * 4)
+        length = length * 4
+    return {"frame_sim": frame_sim, "length": length}
+
+
+def multitext_variant_forward(sd, input_dict, pooling="linear_softmax", training=False, dropout=True,
+                              dropout_masks=None, fast_gru=False, add_proj=False, cross=False, upsample=False):
+    """MultiTextBiEncoder.forward (models/audio_text_model.py:147-229) with its options.  Order: audio_proj on the
+    audio embedding first (:150-151), text encoder on [B*n, N], expansion to one (clip, phrase) pair per row
+    (:166-170), cross encoder (:177-179), text_proj (:180-185), match, pooling, upsampling (:216-223)."""
+    a = cnn8rnn_forward(sd, input_dict["waveform"], input_dict["waveform_len"], training,
+                        dropout_masks, dropout, None, fast_gru)
+    audio = a["embedding"]
+    if add_proj:
+        audio = audio @ sd["audio_proj.weight"].t() + sd["audio_proj.bias"]
+    text = input_dict["text"]
+    B, n = text.shape[0], text.shape[1]
+    text_len = torch.as_tensor(input_dict["text_len"]).reshape(B * n)
+    t = embedding_mean(sd, text.reshape(B * n, -1), text_len)
+    audio_rep = audio.unsqueeze(1).expand(-1, n, -1, -1).reshape(B * n, *audio.shape[1:])
+    audio_len = torch.as_tensor(a["length"]).repeat_interleave(n)
+    if cross:
+        u, s = cross_attention_gating(sd, audio_rep, t["token_emb"], audio_len, text_len)
+        if add_proj:
+            s = s @ sd["text_proj.weight"].t() + sd["text_proj.bias"]
+        frame_sim = torch.sigmoid((u * s).sum(-1) / math.sqrt(u.size(-1))).clamp(1e-7, 1.0)
+    else:
+        seq = t["seq_emb"]
+        if add_proj:
+            seq = seq @ sd["text_proj.weight"].t() + sd["text_proj.bias"]
+        frame_sim, _ = dot_product_match(audio_rep, seq)
+    frame_sim = frame_sim.reshape(B, n, -1).transpose(1, 2)
+    length = a["length"]
+    clip_sim = pool_with_lens(frame_sim, length, pooling)
+    if upsample:
+        # reference quirk: the target size is frame_sim.size(-1) * ratio on the [B,T,n] tensor = n * 4 frames (:217-219)
+        frame_sim = linear_upsample(frame_sim, frame_sim.size(-1) * 4)
+        length = length * 4
+    return {"frame_sim": frame_sim, "clip_sim": clip_sim, "length": length}
+
+
+VARIANT_CASE = dict(batch=3, n_samples=32000, n_phrases=4, n_tokens=6, seed=8, data_seed=9, head_seed=17)
+
+
+def variant_state(variant: str):
+    """Weights of one option-parity case (tests/golden/variants_b3_1s.npz)."""
+    c = VARIANT_CASE
+    if variant in ("multi_proj", "bi_proj_upsample"):
+        sd = synth_state_dict(seed=c["seed"], sharpen=100.0, perturb_bn=True)
+        sd.update(proj_state(c["head_seed"]))
+    elif variant == "multi_gating_proj":
+        sd = synth_state_dict(seed=c["seed"], sharpen=20.0, perturb_bn=True)
+        sd.update(proj_state(c["head_seed"], gain=4.0))
+        sd.update(synth_attn_state(c["head_seed"], ("gating",)))
+    elif variant == "bi_attnagg":
+        sd = synth_state_dict(seed=c["seed"], sharpen=100.0, perturb_bn=True)
+        sd.update(attn_pool_state(c["head_seed"], gain=0.05))
+    elif variant == "multi_upsample":
+        sd = synth_state_dict(seed=c["seed"], sharpen=100.0, perturb_bn=True)
+    else:
+        raise KeyError(variant)
+    return sd
+
+
+def variant_forward(variant: str, sd, batch, **kw):
+    if variant == "multi_proj":
+        return multitext_variant_forward(sd, batch, add_proj=True, **kw)
+    if variant == "multi_gating_proj":
+        return multitext_variant_forward(sd, batch, add_proj=True, cross=True, **kw)
+    if variant == "multi_upsample":
+        return multitext_variant_forward(sd, batch, upsample=True, **kw)
+    if variant == "bi_proj_upsample":
+        return biencoder_variant_forward(sd, batch, add_proj=True, upsample=True, **kw)
+    if variant == "bi_attnagg":
+        return biencoder_variant_forward(sd, batch, aggregation="attention", **kw)
+    raise KeyError(variant)
+
+
+def variant_batch(variant: str):
+    c = VARIANT_CASE
+    if variant.startswith("multi"):
+        return synth_weak_batch(c["batch"], c["n_samples"], c["n_phrases"], c["n_tokens"], seed=c["data_seed"])
+    b = synth_batch(c["batch"], c["n_samples"], c["n_tokens"], seed=c["data_seed"], ragged=True)
+    if variant == "bi_proj_upsample":        # labels at the upsampled resolution
+        g = torch.Generator().manual_seed(c["data_seed"] + 77)
+        t_out = (c["n_samples"] // HOP + 1) // 4
+        b["label"] = (torch.rand(c["batch"], 4 * t_out + 1, generator=g) > 0.5).float()
+    return b

@@ -135,7 +135,7 @@ def main():
     step = torch.zeros(1, device=dev, dtype=torch.int64)
     norm = torch.zeros(1, **f32)
     report("sumsq", timeit(lambda: call("tag_sumsq", g, n, ss)), n * 4)
-    report("clip_adam", timeit(lambda: call("tag_clip_adam", pbuf, g, mm, vv, n, ss, step, 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, norm)),
+    report("clip_adam", timeit(lambda: call("tag_clip_adam", pbuf, g, mm, vv, n, ss, step, 1.0, 1.0, 1e-3, None, 0.9, 0.999, 1e-8, norm)),
            n * 4 * 7)
     if len(sys.argv) > 1:
         os.makedirs(os.path.dirname(sys.argv[1]) or ".", exist_ok=True)

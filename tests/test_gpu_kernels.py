@@ -321,7 +321,7 @@ def test_clip_adam_matches_torch():
         ss = torch.zeros(1, device="cuda", dtype=torch.float64)
         gc = gr.cuda()
         ops.call("tag_sumsq", gc, n, ss)
-        ops.call("tag_clip_adam", pc, gc, m, v, n, ss, step, 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, norm)
+        ops.call("tag_clip_adam", pc, gc, m, v, n, ss, step, 1.0, 1.0, 1e-3, None, 0.9, 0.999, 1e-8, norm)
         np.testing.assert_allclose(norm.item(), float(tn), rtol=1e-5)
         assert (pc.cpu() - ref_p.detach()).abs().max().item() < 2e-6
 

@@ -260,6 +260,132 @@ __global__ void match_norm_bwd_kernel(const float* __restrict__ d_sim, const flo
     }
 }
 
+// ---- EmbeddingAgg(aggregation="attention") (models/text_encoder.py:46-58,84-85): score[n] = <x[b,n,:], w> + bias,
+// masked to n < len with -1e10, softmax over n, out = sum_n weight[n] x[b,n,:].  One CTA (128 threads) per sequence.
+constexpr int AP_MAX_N = 128;
+
+__global__ void attn_pool_fwd_kernel(const float* __restrict__ x, const long long* __restrict__ lens,
+                                     const float* __restrict__ w, const float* __restrict__ bias,
+                                     float* __restrict__ out, float* __restrict__ weight, int N, int D) {
+    __shared__ float s_score[AP_MAX_N];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const long long len = lens[b];
+    const float* xb = x + (long)b * N * D;
+    for (int n = warp; n < N; n += nwarp) {
+        float acc = 0.f;
+        for (int d = lane; d < D; d += 32) acc = fmaf(xb[(long)n * D + d], w[d], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) s_score[n] = n < len ? acc + bias[0] : -1e10f;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float m = -INFINITY;
+        for (int n = lane; n < N; n += 32) m = fmaxf(m, s_score[n]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float z = 0.f;
+        for (int n = lane; n < N; n += 32) z += expf(s_score[n] - m);
+        z = warp_sum(z);
+        for (int n = lane; n < N; n += 32) {
+            const float p = expf(s_score[n] - m) / z;
+            s_score[n] = p;
+            weight[(long)b * N + n] = p;
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+        for (int n = 0; n < N; ++n) acc = fmaf(s_score[n], xb[(long)n * D + d], acc);
+        out[(long)b * D + d] = acc;
+    }
+}
+
+// d_x[b,n,:] = weight[n] d_out + d_score[n] w ; d_score[n] = weight[n] (g[n] - sum_m weight[m] g[m]), g[n] = <d_out, x[n]>
+// d_w += sum_n d_score[n] x[n,:] ; d_bias += sum_n d_score[n]
+__global__ void attn_pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ x,
+                                     const float* __restrict__ w, const float* __restrict__ weight,
+                                     float* __restrict__ d_x, float* __restrict__ d_w, float* __restrict__ d_bias,
+                                     int N, int D) {
+    __shared__ float s_g[AP_MAX_N];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const float* xb = x + (long)b * N * D;
+    const float* go = d_out + (long)b * D;
+    const float* pw = weight + (long)b * N;
+    for (int n = warp; n < N; n += nwarp) {
+        float acc = 0.f;
+        for (int d = lane; d < D; d += 32) acc = fmaf(go[d], xb[(long)n * D + d], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) s_g[n] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float mean = 0.f;
+        for (int n = lane; n < N; n += 32) mean = fmaf(pw[n], s_g[n], mean);
+        mean = warp_sum(mean);
+        float tot = 0.f;
+        for (int n = lane; n < N; n += 32) {
+            const float ds = pw[n] * (s_g[n] - mean);
+            s_g[n] = ds;
+            tot += ds;
+        }
+        tot = warp_sum(tot);
+        if (lane == 0) atomicAdd(d_bias, tot);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float g = go[d], wd = w[d];
+        float dw = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const float ds = s_g[n];
+            d_x[((long)b * N + n) * D + d] = fmaf(pw[n], g, ds * wd);
+            dw = fmaf(ds, xb[(long)n * D + d], dw);
+        }
+        atomicAdd(d_w + d, dw);
+    }
+}
+
+// ---- F.interpolate(mode="linear", align_corners=False) along T to `To` frames (BiEncoder upsample=True,
+// models/audio_text_model.py:90-97 and :216-223).  x [outer, T, inner] -> y [outer, To, inner].
+// ATen: scale = T / To (float), src = scale * (dst + 0.5) - 0.5 clamped at 0; i0 = min(floor(src), T-1); i1 = min(i0+1, T-1).
+__device__ __forceinline__ void upsample_src(int dst, int T, float scale, int* i0, int* i1, float* lam) {
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    int a = (int)src;
+    if (a > T - 1) a = T - 1;
+    *i0 = a;
+    *i1 = a + (a < T - 1 ? 1 : 0);
+    *lam = fminf(fmaxf(src - (float)a, 0.f), 1.f);
+}
+
+__global__ void upsample_linear_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long total, int T,
+                                           int To, int inner) {
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % inner);
+    const int t = (int)((i / inner) % To);
+    const long o = i / ((long)inner * To);
+    int i0, i1; float lam;
+    upsample_src(t, T, (float)T / (float)To, &i0, &i1, &lam);
+    const float* xo = x + o * (long)T * inner + c;
+    y[i] = (1.0f - lam) * xo[(long)i0 * inner] + lam * xo[(long)i1 * inner];
+}
+
+// transpose of the above: every output frame scatters into its two source frames (dx pre-zeroed by the caller)
+__global__ void upsample_linear_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long total, int T,
+                                           int To, int inner) {
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % inner);
+    const int t = (int)((i / inner) % To);
+    const long o = i / ((long)inner * To);
+    int i0, i1; float lam;
+    upsample_src(t, T, (float)T / (float)To, &i0, &i1, &lam);
+    float* xo = dx + o * (long)T * inner + c;
+    const float g = dy[i];
+    atomicAdd(xo + (long)i0 * inner, (1.0f - lam) * g);
+    atomicAdd(xo + (long)i1 * inner, lam * g);
+}
+
 }  // namespace
 
 extern "C" int tag_embed_mean_fwd(const long long* text, const long long* text_len, const float* emb,
@@ -338,6 +464,44 @@ extern "C" int tag_match_norm_bwd(const float* d_sim, const float* sim, const fl
     const long BT = (long)B * T;
     match_norm_bwd_kernel<<<(int)((BT * 32 + 255) / 256), 256, 0, stream>>>(d_sim, sim, audio, seq, d_audio, d_seq, BT, T,
                                                                           mode, scale);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_attn_pool_fwd(const float* x, const long long* lens, const float* w, const float* bias, float* out,
+                                 float* weight, int B, int N, int D, cudaStream_t stream) {
+    if (B <= 0 || N <= 0 || D <= 0) return TAG_ERR_BAD_ARG;
+    if (N > AP_MAX_N) return TAG_ERR_UNSUPPORTED;
+    attn_pool_fwd_kernel<<<B, 128, 0, stream>>>(x, lens, w, bias, out, weight, N, D);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_attn_pool_bwd(const float* d_out, const float* x, const float* w, const float* weight, float* d_x,
+                                 float* d_w, float* d_bias, int B, int N, int D, cudaStream_t stream) {
+    if (B <= 0 || N <= 0 || D <= 0) return TAG_ERR_BAD_ARG;
+    if (N > AP_MAX_N) return TAG_ERR_UNSUPPORTED;
+    attn_pool_bwd_kernel<<<B, 128, 0, stream>>>(d_out, x, w, weight, d_x, d_w, d_bias, N, D);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_upsample_linear_fwd(const float* x, float* y, long outer, int T, int To, int inner,
+                                       cudaStream_t stream) {
+    if (outer <= 0 || T <= 0 || inner <= 0 || To <= 0) return TAG_ERR_BAD_ARG;
+    const long total = outer * To * inner;
+    upsample_linear_fwd_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(x, y, total, T, To, inner);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_upsample_linear_bwd(const float* dy, float* dx, long outer, int T, int To, int inner,
+                                       cudaStream_t stream) {
+    if (outer <= 0 || T <= 0 || inner <= 0 || To <= 0) return TAG_ERR_BAD_ARG;
+    const long total = outer * To * inner;
+    cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * outer * T * inner, stream);
+    if (e != cudaSuccess) return (int)e;
+    upsample_linear_bwd_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(dy, dx, total, T, To, inner);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }

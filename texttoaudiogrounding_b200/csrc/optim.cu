@@ -33,7 +33,9 @@ __global__ void step_inc_kernel(long long* step) { *step += 1; }
 __global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, long n, const double* __restrict__ sumsq,
                                  const long long* __restrict__ step_ptr, float grad_mult, float max_norm,
-                                 float lr, float beta1, float beta2, float eps, float* __restrict__ norm_out) {
+                                 float lr, const float* __restrict__ lr_dev, float beta1, float beta2, float eps,
+                                 float* __restrict__ norm_out) {
+    if (lr_dev != nullptr) lr = *lr_dev;      // device-resident learning rate: schedulers act on a replayed graph
     const double total_norm = sqrt(*sumsq) * (double)grad_mult;
     float coef = 1.0f;
     if (max_norm > 0.f) coef = fminf((float)((double)max_norm / (total_norm + 1e-6)), 1.0f);
@@ -72,14 +74,14 @@ extern "C" int tag_sumsq(const float* g, long n, double* out, cudaStream_t strea
 
 // step_ptr is incremented first (device-side counter, so the step replays inside a CUDA graph)
 extern "C" int tag_clip_adam(float* p, const float* g, float* m, float* v, long n, const double* sumsq,
-                             long long* step_ptr, float grad_mult, float max_norm, float lr, float beta1,
-                             float beta2, float eps, float* norm_out, cudaStream_t stream) {
+                             long long* step_ptr, float grad_mult, float max_norm, float lr, const float* lr_dev,
+                             float beta1, float beta2, float eps, float* norm_out, cudaStream_t stream) {
     step_inc_kernel<<<1, 1, 0, stream>>>(step_ptr);
     TAG_RETURN_IF_LAUNCH_FAILED();
     long blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     clip_adam_kernel<<<(int)blocks, 256, 0, stream>>>(p, g, m, v, n, sumsq, step_ptr, grad_mult, max_norm, lr,
-                                                      beta1, beta2, eps, norm_out);
+                                                      lr_dev, beta1, beta2, eps, norm_out);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }

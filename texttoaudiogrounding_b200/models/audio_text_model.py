@@ -25,8 +25,6 @@ class BiEncoder(nn.Module, LoadPretrainedMixin):
             # parameter containers; applied with nn_ops.linear (models/audio_text_model.py:35-46, 82-97)
             self.audio_proj = nn.Linear(audio_encoder.embed_dim, shared_dim)
             self.text_proj = nn.Linear(text_encoder.embed_dim, shared_dim)
-        if upsample:
-            raise NotImplementedError("upsample=True is outside the cnn8rnn-w2vmean hot path")
         self.interpolate_ratio = self.audio_encoder.downsample_ratio
         self.upsample = upsample
         self.shared_dim = shared_dim
@@ -60,6 +58,10 @@ class BiEncoder(nn.Module, LoadPretrainedMixin):
                     text_emb[key] = nn_ops.linear(text_emb[key], self.text_proj.weight, self.text_proj.bias)
         frame_sim = self.match_fn(forward_dict)      # [batch_size, max_len]
         length = audio_output["length"]
+        if self.interpolate_ratio != 1 and self.upsample:
+            from . import nn_ops
+            frame_sim = nn_ops.upsample_linear(frame_sim, frame_sim.size(1) * self.interpolate_ratio)
+            length = length * self.interpolate_ratio
         return {"frame_sim": frame_sim, "length": length}
 
 
@@ -92,10 +94,23 @@ class MultiTextBiEncoder(BiEncoder):
             pretrained_dict = pretrained_dict["model"]
         return super().process_state_dict(model_dict, pretrained_dict, output_fn, model_name)
 
+    def _text_proj(self, text_emb):
+        if hasattr(self, "text_proj"):
+            from . import nn_ops
+            for key in ("seq_emb", "token_emb"):
+                if key in text_emb:
+                    text_emb[key] = nn_ops.linear(text_emb[key], self.text_proj.weight, self.text_proj.bias)
+
     def forward(self, input_dict):
+        """Order of operations as in the reference (models/audio_text_model.py:147-229): audio_proj on the audio
+        embedding FIRST, text encoder on the flattened [B*text_num, ...] phrases, cross encoder on the per-pair
+        batch, text_proj, match function, clip-level pooling, optional upsampling."""
         import torch
+        from . import nn_ops
         audio_output = self.audio_encoder(input_dict)
         audio_emb = audio_output["embedding"]                        # [B, T', D]
+        if hasattr(self, "audio_proj"):
+            audio_emb = nn_ops.linear(audio_emb, self.audio_proj.weight, self.audio_proj.bias)
         batch_size = audio_emb.size(0)
         text_num = input_dict[self.text_forward_keys[0]].shape[1]
         text_forward_dict = {}
@@ -103,13 +118,32 @@ class MultiTextBiEncoder(BiEncoder):
             x = torch.as_tensor(input_dict[key])
             text_forward_dict[key] = x.reshape(x.shape[0] * x.shape[1], *x.shape[2:])
         text_emb = self.text_encoder(text_forward_dict)
-        seq_emb = text_emb["seq_emb"].view(batch_size, text_num, -1)
-        if not hasattr(self.match_fn, "forward_multi"):
-            raise NotImplementedError("MultiTextBiEncoder (B200) needs a match function with forward_multi "
-                                      "(models.match.DotProduct)")
-        frame_sim = self.match_fn.forward_multi(audio_emb, seq_emb)  # [B, T', text_num]
         length = audio_output["length"]
+        fast = (self.cross_encoder is None and hasattr(self.match_fn, "forward_multi")
+                and getattr(self.match_fn, "text_level", None) == "seq" and not getattr(self.match_fn, "l2norm", True))
+        if fast:
+            # every clip against its phrases with the audio embedding read in place (no [B*n, T', D] expansion)
+            self._text_proj(text_emb)
+            seq_emb = text_emb["seq_emb"].view(batch_size, text_num, -1)
+            frame_sim = self.match_fn.forward_multi(audio_emb, seq_emb)       # [B, T', text_num]
+        else:
+            # general route: one (clip, phrase) pair per row, exactly the reference's expansion
+            audio_rep = audio_emb.unsqueeze(1).expand(-1, text_num, -1, -1).reshape(-1, *audio_emb.shape[1:])
+            audio_len = torch.as_tensor(length).repeat_interleave(text_num)
+            forward_dict = {"audio_emb": audio_rep, "text_emb": text_emb, "audio_len": audio_len,
+                            "text_len": text_forward_dict["text_len"]}
+            if self.cross_encoder is not None:
+                forward_dict.update(self.cross_encoder(forward_dict))
+            self._text_proj(forward_dict["text_emb"])
+            frame_sim = self.match_fn(forward_dict)                           # [B * text_num, T']
+            frame_sim = frame_sim.reshape(batch_size, text_num, -1).transpose(1, 2)
         clip_sim = pool_with_lens(frame_sim, length, self.pooling)
+        if self.interpolate_ratio != 1 and self.upsample:
+            # the reference sizes the interpolation by frame_sim.size(-1) of the [B, T', text_num] tensor, i.e. by
+            # the NUMBER OF PHRASES (models/audio_text_model.py:217-219): T' frames are resampled to
+            # text_num * ratio frames.  Reproduced as is — results must equal the reference's.
+            frame_sim = nn_ops.upsample_linear(frame_sim, frame_sim.size(-1) * self.interpolate_ratio)
+            length = length * self.interpolate_ratio
         return {"frame_sim": frame_sim, "clip_sim": clip_sim, "length": length}
 
 

@@ -256,3 +256,30 @@ def ln_linear_sigmoid(audio, attn_out, norm: torch.nn.LayerNorm, lin: torch.nn.L
         norm.weight.float().contiguous(), norm.bias.float().contiguous(), lin.weight.reshape(-1).float().contiguous(),
         lin.bias.float().contiguous(), norm.eps, dropout_p, next_seed())
     return out.view(*lead)
+
+
+class _UpsampleLinearFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size):
+        outer, T, inner = x.shape
+        y = torch.empty(outer, size, inner, device=x.device, dtype=torch.float32)
+        call("tag_upsample_linear_fwd", x, y, outer, T, size, inner)
+        ctx.cfg = (outer, T, inner, size)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        outer, T, inner, size = ctx.cfg
+        dx = torch.empty(outer, T, inner, device=dy.device, dtype=torch.float32)
+        call("tag_upsample_linear_bwd", dy.contiguous(), dx, outer, T, size, inner)
+        return dx, None
+
+
+def upsample_linear(x: torch.Tensor, size: int) -> torch.Tensor:
+    """F.interpolate(x, size=size, mode="linear", align_corners=False) along dim 1 of x [B, T] or [B, T, n]
+    (the reference interpolates [B, 1, T] / [B, n, T] views, models/audio_text_model.py:90-97, 216-223)."""
+    _need_cuda(x, "upsample")
+    squeeze = x.dim() == 2
+    x3 = x.unsqueeze(-1) if squeeze else x
+    y = _UpsampleLinearFunction.apply(x3.float().contiguous(), int(size))
+    return y.squeeze(-1) if squeeze else y

@@ -66,6 +66,49 @@ class EmbeddingLayer(nn.Module):
         return _EmbedMeanFunction.apply(self.core.weight, tokens.contiguous(), lens)[0]
 
 
+class _AttnPoolFunction(torch.autograd.Function):
+    """AttentionPooling.forward (reference models/text_encoder.py:51-58) as one kernel per direction."""
+
+    @staticmethod
+    def forward(ctx, x, lens, w, bias):
+        B, N, D = x.shape
+        out = torch.empty(B, D, device=x.device, dtype=torch.float32)
+        weight = torch.empty(B, N, device=x.device, dtype=torch.float32)
+        call("tag_attn_pool_fwd", x, lens, w, bias, out, weight, B, N, D)
+        ctx.save_for_backward(x, w, weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, w, weight = ctx.saved_tensors
+        B, N, D = x.shape
+        d_x = torch.empty_like(x)
+        d_w = torch.zeros_like(w)
+        d_b = torch.zeros(1, device=x.device, dtype=torch.float32)
+        call("tag_attn_pool_bwd", d_out.contiguous(), x, w, weight, d_x, d_w, d_b, B, N, D)
+        return d_x, None, d_w, d_b
+
+
+class AttentionPooling(nn.Module):
+    """Mirror of reference models/text_encoder.py:46-58: ``fc`` = Linear(emb_dim, 1) holds the parameters (same
+    state-dict keys ``attn.fc.{weight,bias}``); score, mask, softmax and the weighted sum run in csrc/head.cu."""
+
+    def __init__(self, emb_dim):
+        super().__init__()
+        self.fc = nn.Linear(emb_dim, 1)
+
+    def forward(self, x, lens):
+        if not x.is_cuda:
+            raise RuntimeError("AttentionPooling (B200) needs CUDA tensors: there is no CPU fallback")
+        host_lens = torch.as_tensor(lens)
+        if not host_lens.is_cuda and int(host_lens.max()) != x.shape[1]:
+            # generate_length_mask(lens) is max(lens) wide; masked_fill then fails to broadcast (text_encoder.py:54-55)
+            raise RuntimeError(f"The size of tensor a ({x.shape[1]}) must match the size of tensor b "
+                               f"({int(host_lens.max())}) at non-singleton dimension 1")
+        return _AttnPoolFunction.apply(x.float().contiguous(), lens_to_device(lens, x.device).contiguous(),
+                                       self.fc.weight.reshape(-1), self.fc.bias)
+
+
 class EmbeddingAgg(nn.Module):
     def __init__(self, vocab_size, embed_dim, pretrained_embedding: str = None,
                  freeze_embedding: bool = False, aggregation: str = "mean"):
@@ -74,10 +117,10 @@ class EmbeddingAgg(nn.Module):
         self.embed_dim = self.embedding.embed_dim
         self.agg = aggregation
         if aggregation == "attention":
-            raise NotImplementedError("aggregation='attention' is outside the cnn8rnn-w2vmean hot path")
+            self.attn = AttentionPooling(embed_dim)
 
     def forward(self, input_dict):
-        if self.agg != "mean":
+        if self.agg not in ("mean", "attention"):
             raise Exception(f"{self.agg} not supported")
         weight = self.embedding.core.weight
         if not weight.is_cuda:
@@ -85,6 +128,8 @@ class EmbeddingAgg(nn.Module):
         tokens = input_dict["text"].long().to(weight.device).contiguous()
         lens = lens_to_device(input_dict["text_len"], weight.device).contiguous()
         token_emb, seq_emb = _EmbedMeanFunction.apply(weight, tokens, lens)
+        if self.agg == "attention":
+            seq_emb = self.attn(token_emb, input_dict["text_len"])
         return {"token_emb": token_emb, "seq_emb": seq_emb}
 
 
