@@ -24,10 +24,13 @@ def _worker(rank, world, port, ret):
     try:
         from helpers import build_model
         from texttoaudiogrounding_b200.train import FusedTrainStep
-        torch.manual_seed(1)
+        torch.manual_seed(1 + rank)          # replicas start DIFFERENT; the constructor broadcasts rank 0's state
         model = build_model(None, "fp32", device="cpu", vocab=300)
-        ts = FusedTrainStep(model, use_graph=False)
-        assert ts.world == world
+        model.audio_encoder.bn0.running_mean.fill_(float(rank))
+        ts = FusedTrainStep(model, use_graph=False, base_seed=5)
+        assert ts.world == world and ts.rank == rank
+        assert ts.base_seed == 5 + 7919 * rank          # every rank draws its own dropout masks
+        assert float(model.audio_encoder.bn0.running_mean.abs().max()) == 0.0
         n = ts.n_params
         assert n == sum(p.numel() for p in model.parameters())
         # parameters and .grad are views of the flat buffers, in the fixed order

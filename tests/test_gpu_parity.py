@@ -230,3 +230,31 @@ def test_dropout_training_forward_matches_oracle_with_same_masks():
                                 dropout_masks=masks)
     err = (out.cpu() - ref["embedding"]).abs().max().item()
     assert err < 2e-3, err
+
+
+def test_graphs_are_cached_per_shape_and_learning_rate_is_live():
+    """A collate that pads to the longest clip changes L between batches (datasets/collate_function.py:43-84):
+    the graphs of every shape seen are kept (alternating shapes replay, no re-capture) and follow the eager
+    trajectory; set_lr() acts on captured graphs (the kernel reads the device scalar)."""
+    from texttoaudiogrounding_b200.train import FusedTrainStep
+    sd = O.synth_state_dict(seed=1, sharpen=1.0, perturb_bn=True)
+    batches = [O.synth_batch(4, 64000, seed=0), O.synth_batch(3, 48000, seed=1)]
+    res = {}
+    for use_graph in (False, True):
+        model = build_model(sd, "fp32")
+        model.train()
+        model.audio_encoder.dropout_enabled = False
+        ts = FusedTrainStep(model, use_graph=use_graph)
+        ls = []
+        for i in range(8):
+            if i == 6:
+                ts.set_lr(0.0)                      # from here on the parameters must not move
+                frozen = ts.flat_p.clone()
+            ls.append(ts.step(batches[i % 2]).item())
+        torch.cuda.synchronize()
+        assert torch.equal(ts.flat_p, frozen)
+        assert int(ts.step_dev.item()) == 8
+        if use_graph:
+            assert len(ts._graphs) == 2             # one entry per shape, both still alive
+        res[use_graph] = ls
+    np.testing.assert_allclose(res[True], res[False], rtol=5e-3)

@@ -236,3 +236,64 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert "configs[2]" in line["config"]["workload"]
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_fused_step_refuses_configurations_it_does_not_compute():
+    """FusedTrainStep hard-codes mean-embedding -> scaled dot -> sigmoid; any other head must raise instead of being
+    trained as that.  Host logic only: CPU tensors, no kernels."""
+    from texttoaudiogrounding_b200.models.audio_encoder import Cnn8Rnn
+    from texttoaudiogrounding_b200.models.audio_text_model import BiEncoder, MultiTextBiEncoder
+    from texttoaudiogrounding_b200.models.match import DotProduct, ExpNegL2
+    from texttoaudiogrounding_b200.models.text_encoder import EmbeddingAgg
+    from texttoaudiogrounding_b200.train import FusedTrainStep, WeakFusedTrainStep
+
+    def enc():
+        return Cnn8Rnn(32000, compute_dtype="fp32")
+
+    bad = [
+        BiEncoder(enc(), EmbeddingAgg(50, 512), ExpNegL2(), 512),
+        BiEncoder(enc(), EmbeddingAgg(50, 512), DotProduct(l2norm=True), 512),
+        BiEncoder(enc(), EmbeddingAgg(50, 512), DotProduct(text_level="token"), 512),
+        BiEncoder(enc(), EmbeddingAgg(50, 512, aggregation="attention"), DotProduct(), 512),
+        BiEncoder(enc(), EmbeddingAgg(50, 512), DotProduct(), 512, add_proj=True),
+        BiEncoder(enc(), EmbeddingAgg(50, 512), DotProduct(), 512, upsample=True),
+    ]
+    for m in bad:
+        with pytest.raises(NotImplementedError):
+            FusedTrainStep(m, use_graph=False)
+    with pytest.raises(NotImplementedError):
+        WeakFusedTrainStep(BiEncoder(enc(), EmbeddingAgg(50, 512), DotProduct(), 512), use_graph=False)
+    with pytest.raises(NotImplementedError):
+        WeakFusedTrainStep(MultiTextBiEncoder(enc(), EmbeddingAgg(50, 512), DotProduct(), 512, ["text"], add_proj=True),
+                           use_graph=False)
+    FusedTrainStep(BiEncoder(enc(), EmbeddingAgg(50, 512), DotProduct(), 512), use_graph=False)
+
+
+def test_fused_step_optimizer_state_round_trips_through_torch_adam():
+    """optimizer_state_dict() is torch.optim.Adam's layout in model.parameters() order (what the reference stores
+    with include_optim_in_ckpt, run_strong.py:679-690): torch.optim.Adam loads it, and what Adam saves loads back."""
+    from helpers import build_model
+    from texttoaudiogrounding_b200.train import FusedTrainStep
+    torch.manual_seed(0)
+    model = build_model(None, "fp32", device="cpu", vocab=40)
+    ts = FusedTrainStep(model, lr=2e-3, use_graph=False)
+    assert ts.optimizer_state_dict()["state"] == {}
+    ts.flat_m.copy_(torch.randn(ts.n_params))
+    ts.flat_v.copy_(torch.rand(ts.n_params))
+    ts.step_dev.fill_(7)
+    ts.set_lr(5e-4)
+    assert ts.lr == 5e-4 and float(ts.lr_dev) == pytest.approx(5e-4)
+    sd = ts.optimizer_state_dict()
+    opt = torch.optim.Adam(model.parameters(), lr=1.0)
+    opt.load_state_dict(sd)
+    assert opt.param_groups[0]["lr"] == 5e-4
+    w = model.audio_encoder.conv_block2.conv1.weight
+    off, k = ts._views[[id(p) for p in ts._params].index(id(w))]
+    assert torch.equal(opt.state[w]["exp_avg"].permute(0, 2, 3, 1).reshape(-1), ts.flat_m[off:off + k])
+    assert int(opt.state[w]["step"]) == 7
+    torch.manual_seed(0)
+    model2 = build_model(None, "fp32", device="cpu", vocab=40)
+    ts2 = FusedTrainStep(model2, use_graph=False)
+    ts2.load_optimizer_state_dict(opt.state_dict())
+    assert torch.equal(ts2.flat_m, ts.flat_m) and torch.equal(ts2.flat_v, ts.flat_v)
+    assert int(ts2.step_dev) == 7 and ts2.lr == 5e-4

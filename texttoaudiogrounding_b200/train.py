@@ -12,6 +12,7 @@
 from __future__ import annotations
 
 import os
+from collections import OrderedDict
 from typing import Dict, Optional
 
 import torch
@@ -73,23 +74,35 @@ class LossHandle:
 class FusedTrainStep:
     """Flat-buffer, CUDA-graph-captured train step for BiEncoder(Cnn8Rnn, EmbeddingAgg, DotProduct)."""
 
+    MAX_GRAPHS = 8          # captured (shape -> graphs) entries kept, least recently used evicted first
+
     def __init__(self, model: nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  max_grad_norm: float = 1.0, process_group=None, use_graph: bool = True,
                  base_seed: int = 1):
         self.model = model
         self.enc = model.audio_encoder
         self.txt = model.text_encoder
-        self.lr, self.betas, self.eps, self.max_grad_norm = lr, betas, eps, max_grad_norm
+        self._check_model(model)
+        self.betas, self.eps, self.max_grad_norm = betas, eps, max_grad_norm
         self.pg = process_group
-        self.world = 1
+        self.world, self.rank = 1, 0
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
         self.use_graph = use_graph
-        self.base_seed = base_seed
+        # every rank draws its own dropout masks (same base seed on all ranks would repeat the masks N times)
+        self.base_seed = base_seed + 7919 * self.rank
         self.scale = 1.0 / (self.enc.embed_dim ** 0.5) if getattr(model.match_fn, "scale", True) else 1.0
         self.device = next(model.parameters()).device
         self._flatten()
-        self._graphs = {}
+        # the learning rate lives on the device: a scheduler (run_strong.py:136-137) acts on replayed graphs too
+        self.lr_dev = torch.full((1,), float(lr), device=self.device, dtype=torch.float32)
+        self._lr = float(lr)
+        if self.world > 1:
+            self._sync_replicas()
+        self._graphs = OrderedDict()      # shape key -> {"fwd_bwd", "optim", "static"}
+        self._seen = {}                   # shape key -> number of steps run with it
+        self._graph_pool = None
         self._static = None
         self._staging = None
         self._prefetched = None
@@ -101,6 +114,102 @@ class FusedTrainStep:
         model.register_state_dict_pre_hook(lambda *a, **k: self.flush_counters())
         # weight-gradient GEMMs on a second stream (TAG_B200_OVERLAP=1)
         self.side_stream = torch.cuda.Stream(self.device) if os.environ.get("TAG_B200_OVERLAP", "0") == "1" else None
+
+    # ------------------------------------------------------------------ what this step computes
+    def _check_model(self, model):
+        """The fused step hard-codes: masked-mean word embeddings -> scaled dot product -> sigmoid -> clamp.  Any
+        other head must go through the autograd path (``train_step``), never silently through this one."""
+        from .models.match import DotProduct
+        from .models.text_encoder import EmbeddingAgg
+        mf = model.match_fn
+        problems = []
+        if type(mf) is not DotProduct or mf.l2norm or mf.text_level != "seq":
+            problems.append("match_fn must be models.match.DotProduct(l2norm=False, text_level='seq')")
+        if not isinstance(self.txt, EmbeddingAgg) or self.txt.agg != "mean":
+            problems.append("text_encoder must be EmbeddingAgg(aggregation='mean')")
+        if getattr(model, "cross_encoder", None) is not None:
+            problems.append("cross_encoder is not None")
+        if hasattr(model, "audio_proj") or hasattr(model, "text_proj"):
+            problems.append("audio_proj / text_proj (add_proj or mismatched embed dims)")
+        if getattr(model, "upsample", False):
+            problems.append("upsample=True")
+        if problems:
+            raise NotImplementedError(f"{type(self).__name__} does not implement this configuration ("
+                                      + "; ".join(problems) + "): use train.train_step (autograd path)")
+
+    # ------------------------------------------------------------------ learning rate / optimizer state
+    @property
+    def lr(self) -> float:
+        return self._lr
+
+    @lr.setter
+    def lr(self, value: float) -> None:
+        self.set_lr(value)
+
+    def set_lr(self, value: float) -> None:
+        """Takes effect at the next step, captured graphs included (the kernel reads the device scalar)."""
+        self._lr = float(value)
+        self.lr_dev.fill_(self._lr)
+
+    def _param_views(self, flat: torch.Tensor):
+        """Views of a flat buffer shaped like the parameters, in the order of ``_flatten``."""
+        out = []
+        for p, (off, k) in zip(self._params, self._views):
+            if p.dim() == 4:
+                co, ci, kh, kw = p.shape
+                out.append(flat[off:off + k].view(co, kh, kw, ci).permute(0, 3, 1, 2))
+            else:
+                out.append(flat[off:off + k].view(p.shape))
+        return out
+
+    def optimizer_state_dict(self) -> Dict:
+        """The optimizer state in ``torch.optim.Adam.state_dict()`` layout with parameters indexed in
+        ``model.parameters()`` order, i.e. what the reference stores under ``"optimizer"`` with
+        ``include_optim_in_ckpt`` (run_strong.py:679-690) — loadable by ``torch.optim.Adam(model.parameters())``."""
+        m = {id(p): v for p, v in zip(self._params, self._param_views(self.flat_m))}
+        v = {id(p): x for p, x in zip(self._params, self._param_views(self.flat_v))}
+        step = self.step_dev.to(torch.float32).cpu().reshape(())
+        state, idx = {}, []
+        for i, p in enumerate(self.model.parameters()):
+            idx.append(i)
+            if int(step) > 0:
+                state[i] = {"step": step.clone(), "exp_avg": m[id(p)].detach().clone().contiguous(),
+                            "exp_avg_sq": v[id(p)].detach().clone().contiguous()}
+        group = {"lr": self._lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": idx}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd: Dict) -> None:
+        group = sd["param_groups"][0]
+        self.set_lr(group["lr"])
+        self.betas, self.eps = tuple(group["betas"]), group["eps"]
+        m = {id(p): x for p, x in zip(self._params, self._param_views(self.flat_m))}
+        v = {id(p): x for p, x in zip(self._params, self._param_views(self.flat_v))}
+        steps = set()
+        for i, p in zip(group["params"], self.model.parameters()):
+            st = sd["state"].get(i)
+            if st is None:
+                m[id(p)].zero_(); v[id(p)].zero_()
+                continue
+            m[id(p)].copy_(st["exp_avg"]); v[id(p)].copy_(st["exp_avg_sq"])
+            steps.add(int(st["step"]))
+        if len(steps) > 1:
+            raise NotImplementedError("per-parameter Adam step counts differ; the fused step keeps one counter")
+        self.step_dev.fill_(steps.pop() if steps else 0)
+        if self._graphs:
+            self._graphs.clear()          # betas / eps are baked into the captured optimizer graph
+
+    def _sync_replicas(self) -> None:
+        """Data-parallel replicas start identical: parameters, Adam moments and BatchNorm buffers of rank 0."""
+        dist = torch.distributed
+        for t in (self.flat_p, self.flat_m, self.flat_v, self.step_dev):
+            dist.broadcast(t, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+        for bn in self.enc._bns():
+            for buf in (bn.running_mean, bn.running_var, bn.num_batches_tracked):
+                if buf is not None:
+                    dist.broadcast(buf, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0,
+                                   group=self.pg)
 
     # ------------------------------------------------------------------ flat buffers
     def _flatten(self):
@@ -119,6 +228,7 @@ class FusedTrainStep:
         self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
         self.n_params = n
+        self._params = params
         off = 0
         self._views = []
         for p in params:
@@ -204,7 +314,7 @@ class FusedTrainStep:
         self.sumsq.zero_()
         call("tag_sumsq", self.flat_g, self.n_params, self.sumsq)
         call("tag_clip_adam", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_params,
-             self.sumsq, self.step_dev, 1.0 / self.world, float(self.max_grad_norm), float(self.lr),
+             self.sumsq, self.step_dev, 1.0 / self.world, float(self.max_grad_norm), float(self._lr), self.lr_dev,
              float(self.betas[0]), float(self.betas[1]), float(self.eps), self.norm_out)
 
     def _allreduce(self):
@@ -212,7 +322,7 @@ class FusedTrainStep:
             torch.distributed.all_reduce(self.flat_g, group=self.pg)
 
     def _eager(self, s):
-        self._fwd_bwd(s["waveform"], s["text"], s["text_len"], s.get("label"), s["length"])
+        self._run_fwd_bwd(s)
         self._allreduce()
         self._optim()
 
@@ -272,8 +382,9 @@ class FusedTrainStep:
         else:
             key, src = self._host_views(batch)
         if self._static is None or self._static["key"] != key:
-            self._static = self._alloc_inputs(key)
-            self._graphs = {}
+            entry = self._graphs.get(key)
+            # a shape seen before brings its own static buffers (its graphs read them); a new one gets fresh ones
+            self._static = entry["static"] if entry is not None else self._alloc_inputs(key)
         s = self._static
         if staged:
             torch.cuda.current_stream().wait_event(self._staging_ready)
@@ -315,23 +426,43 @@ class FusedTrainStep:
         if self.enc.training:
             self._nbt_pending += 1
         self._calls += 1
-        if not self.use_graph or self._calls == 1:
-            # the first step runs eagerly (sets kernel attributes, primes the allocator)
+        key = s["key"]
+        seen = self._seen[key] = self._seen.get(key, 0) + 1
+        if not self.use_graph or seen == 1:
+            # the first step of a shape runs eagerly (sets kernel attributes, primes the allocator); a collate that
+            # pads to the longest clip (datasets/collate_function.py:43-84) may never repeat a shape: all eager
             self._eager(s)
             return self.loss_out
-        if not self._graphs:
-            torch.cuda.synchronize()
-            g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
-                self._fwd_bwd(s["waveform"], s["text"], s["text_len"], s.get("label"), s["length"])
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2):
-                self._optim()
-            self._graphs = {"fwd_bwd": g1, "optim": g2}      # capture executes nothing
-        self._graphs["fwd_bwd"].replay()
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = self._capture(s)
+            self._graphs[key] = entry
+            while len(self._graphs) > self.MAX_GRAPHS:
+                old_key, _ = self._graphs.popitem(last=False)
+                self._seen.pop(old_key, None)
+        else:
+            self._graphs.move_to_end(key)
+        entry["fwd_bwd"].replay()
         self._allreduce()
-        self._graphs["optim"].replay()
+        entry["optim"].replay()
         return self.loss_out
+
+    def _capture(self, s) -> Dict:
+        """Two CUDA graphs (forward+backward, optimizer) for the shape of ``s``; all shapes share one memory pool
+        (replays are serialised on one stream, so their intermediates may alias)."""
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        torch.cuda.synchronize()
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1, pool=self._graph_pool):
+            self._run_fwd_bwd(s)
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, pool=self._graph_pool):
+            self._optim()
+        return {"fwd_bwd": g1, "optim": g2, "static": s}      # capture executes nothing
+
+    def _run_fwd_bwd(self, s):
+        self._fwd_bwd(s["waveform"], s["text"], s["text_len"], s.get("label"), s["length"])
 
 
 class WeakFusedTrainStep(FusedTrainStep):
@@ -346,9 +477,14 @@ class WeakFusedTrainStep(FusedTrainStep):
     def __init__(self, model: nn.Module, frame_weight: Optional[float] = None, **kw):
         """``frame_weight`` = w selects ClipFrameBceLoss: (1 - w) * clip BCE + w * frame BCE on ``strong_label``
         [B, T', n] (losses.py:186-210); None = ClipBceLoss."""
+        from .models.audio_text_model import MultiTextBiEncoder
         from .models.utils import POOL_MODES
+        if not isinstance(model, MultiTextBiEncoder):
+            raise NotImplementedError("WeakFusedTrainStep drives models.audio_text_model.MultiTextBiEncoder")
+        if model.pooling not in POOL_MODES:
+            raise Exception(f"Unsupported pooling {model.pooling}")
         super().__init__(model, **kw)
-        self.pool_mode = POOL_MODES[getattr(model, "pooling", "linear_softmax")]
+        self.pool_mode = POOL_MODES[model.pooling]
         self.frame_weight = frame_weight
         self.loss_clip = torch.zeros((), device=self.device, dtype=torch.float32)
         self.loss_frame = torch.zeros((), device=self.device, dtype=torch.float32)
@@ -391,10 +527,9 @@ class WeakFusedTrainStep(FusedTrainStep):
                                         device=dev, dtype=torch.float32),
         }
 
-    def _prepare_static(self, batch: Dict):
-        s = super()._prepare_static(batch)
+    def _run_fwd_bwd(self, s):
         self._strong = s["strong_label"]
-        return s
+        super()._run_fwd_bwd(s)
 
     def _fwd_bwd(self, wav, text, text_len, label, length):
         enc = self.enc
@@ -501,15 +636,26 @@ class AlignFusedTrainStep(FusedTrainStep):
                 "text_len": torch.empty(rows, **lng), "pool_len": torch.empty(B, **lng),
                 "pad_index": torch.empty(1 if self.word_level else rows, **lng), "length": torch.empty(B, **lng)}
 
-    def _prepare_static(self, batch: Dict):
-        s = super()._prepare_static(batch)
-        self._extra = (s["pool_len"], s["pad_index"], s["key"][4])
-        return s
+    def _check_model(self, model):
+        from .models import align, sim_pooling
+        from .models.audio_text_model import AudioTextAlignByPhrase, AudioTextAlignByWord
+        from .models.text_encoder import EmbeddingAgg
+        problems = []
+        if not isinstance(model, (AudioTextAlignByWord, AudioTextAlignByPhrase)):
+            problems.append("model must be AudioTextAlignByWord / AudioTextAlignByPhrase")
+        if type(model.match_fn) is not align.DotProduct:
+            problems.append("match_fn must be models.align.DotProduct")
+        if not isinstance(getattr(model, "sim_pooling", None), sim_pooling._AudioTextPooling):
+            problems.append("sim_pooling must be one of models.sim_pooling.Audio*Text*")
+        if not isinstance(model.text_encoder, EmbeddingAgg) or model.text_encoder.agg != "mean":
+            problems.append("text_encoder must be EmbeddingAgg(aggregation='mean')")
+        if problems:
+            raise NotImplementedError("AlignFusedTrainStep does not implement this configuration ("
+                                      + "; ".join(problems) + "): use the autograd path")
 
-    def _eager(self, s):
+    def _run_fwd_bwd(self, s):
+        self._extra = (s["pool_len"], s["pad_index"], s["key"][4])
         self._fwd_bwd(s["waveform"], s["text"], s["text_len"], None, s["length"])
-        self._allreduce()
-        self._optim()
 
     def _fwd_bwd(self, wav, text, text_len, label, length):
         from .models.align import _AlignPoolFunction
