@@ -1,14 +1,17 @@
 #!/usr/bin/env python
-"""bench.py — clips/s of the cnn8rnn-w2vmean train step (fwd + bwd + clip + Adam) on B200.
+"""bench.py — clips/s of the TextToAudioGrounding hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16|fp32]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config train_bf16|fwd_fp32|attn_bf16|clap_infer]
 
-One "step" = one pass of the hot path over one batch of 64 synthetic 10 s @ 32 kHz clips with
-8-token phrases PER GPU (weak scaling; BASELINE.json configs[2]).  Prints ONE JSON line (rank 0).
-`value` is device-timed with inputs resident in HBM; `e2e` runs the same step through the public
-API (`FusedTrainStep.step(host_batch)`) with pinned host buffers, H2D copies and the loss D2H read
-inside the timed region.  `--impl reference` times the CPU restatement of the reference's train
-step (oracle/, torch CPU ops with all host threads) on a bounded sample of the same workload.
+Default workload (the BASELINE.json metric, configs[2]): one "step" = the cnn8rnn-w2vmean train step (forward +
+backward + clip_grad_norm_ + Adam) over one batch of 64 synthetic 10 s @ 32 kHz clips with 8-token phrases PER GPU
+(weak scaling).  Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` runs the
+same step through the public API with pinned host buffers, the H2D copies and the loss / result D2H read inside the
+timed region.  `--impl reference` times the UNMODIFIED reference modules (staged under oracle/_ref by
+oracle/build_ref.py; the oracle port when they are absent) on the host cores, every step a bounded sample of the
+workload.  `gpu_baseline` (N=1) times the same reference modules with stock torch.cuda eager on the same GPU.
+--config selects the other BASELINE.json configurations: fwd_fp32 = configs[1], attn_bf16 = configs[3],
+clap_infer = configs[4].
 """
 import argparse
 import json
@@ -22,52 +25,171 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "clips/sec (10 s @32 kHz, bs=64) cnn8rnn-w2vmean fwd+bwd at 1/2/4/8 B200"
-BATCH = 64
 N_SAMPLES = 320000
 N_TOKENS = 8
+VOCAB = 5221
 FWD_GFLOP_PER_CLIP = 33.83          # conv 33.11 + fc1 0.131 + GRU 0.590
-TRAIN_GFLOP_PER_CLIP = 3 * FWD_GFLOP_PER_CLIP
-WORKLOAD = ("cnn8rnn-w2vmean full train step (fwd+bwd+clip+Adam), bs={B}/GPU, 10 s @32 kHz clips, 8-token phrases "
-            "(BASELINE.json configs[2])")
+REF_SAMPLE_CLIPS = 8                # clips per step of the CPU reference arm (a bounded sample of the batch)
+
+WORKLOADS = {
+    # name: (kind, per-GPU batch, compute dtype, metric string, config.workload)
+    "train_bf16": ("train", 64, "bf16", METRIC,
+                   "cnn8rnn-w2vmean full train step (fwd+bwd+clip+Adam), bs={B}/GPU, 10 s @32 kHz clips, 8-token "
+                   "phrases (BASELINE.json configs[2])"),
+    "fwd_fp32": ("infer", 64, "fp32", "clips/sec (10 s @32 kHz, bs=64) cnn8rnn-w2vmean forward only, fp32",
+                 "cnn8rnn-w2vmean eval forward (no_grad), bs={B}/GPU, 10 s @32 kHz clips, 8-token phrases, fp32 "
+                 "(BASELINE.json configs[1])"),
+    "attn_bf16": ("train", 32, "bf16",
+                  "clips/sec (10 s @32 kHz, bs=32) cnn8rnn + SelfAttention text encoder + CrossAttentionGating train step",
+                  "cnn8rnn + text_encoder.SelfAttention(8 heads) + cross_encoder.CrossAttentionGating + "
+                  "DotProduct(token) full train step, bs={B}/GPU, 10 s @32 kHz clips, 8-token phrases, bf16 "
+                  "(BASELINE.json configs[3])"),
+    "clap_infer": ("infer", 32, "bf16",
+                   "clips/sec (10 s @32 kHz, bs=32) cnn8rnn + LAION-CLAP text tower inference (HF facade)",
+                   "Cnn8RnnLaionClapGroundingModel(audio, audio_len, tokens) forward, random-init full-size CLAP text "
+                   "tower, bs={B}/GPU, 10 s @32 kHz clips, 10-token phrases, bf16 (BASELINE.json configs[4])"),
+}
+L2_NOTE = "per-step working set (GBs of activations / a 41-82 MB waveform batch) is larger than the 126 MB L2"
 
 
-def cpu_reference_step_time(batch_size: int, n_samples: int, steps: int, warmup: int):
-    """Seconds per train step of the CPU restatement (oracle) on all host threads."""
+def config_dict(name, B, world):
+    """Identical for both arms (the reference arm runs on this arm's config)."""
+    return {"workload": WORKLOADS[name][4].format(B=B), "global_batch": B * world, "parallelism": f"dp{world}",
+            "l2": L2_NOTE}
+
+
+def synth_host_batch(B, seed, fp16=False, pin=True, n_tokens=N_TOKENS):
     import torch
-    from oracle import tag_oracle as O
+    g = torch.Generator().manual_seed(seed)
+    host = {
+        "waveform": (0.1 * torch.randn(B, N_SAMPLES, generator=g)).to(torch.float16 if fp16 else torch.float32),
+        "waveform_len": torch.full((B,), N_SAMPLES, dtype=torch.long),
+        "text": torch.randint(2, VOCAB, (B, n_tokens), generator=g),
+        "text_len": torch.full((B,), n_tokens, dtype=torch.long),
+        "label": (torch.rand(B, 251, generator=g) > 0.5).float(),
+    }
+    return {k: v.pin_memory() for k, v in host.items()} if pin else host
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU + GPU baselines (measurement infrastructure: oracle/ is only ever used here as the baseline)
+def _reference_model(name, device, **kw):
+    """(step callable, batch maker, kind) for workload ``name`` built from the reference's own modules."""
+    import torch
+    from oracle import ref_runner
+    if not ref_runner.available():
+        return None
+    rs = ref_runner.ReferenceStep(device, **kw)
+    kind = WORKLOADS[name][0]
+    if name in ("train_bf16", "fwd_fp32"):
+        return rs, ("train" if kind == "train" else "eval")
+    if name == "attn_bf16":
+        import models.cross_encoder as ce
+        import models.match as match
+        import models.text_encoder as te
+        import models.audio_text_model as atm
+        import models.audio_encoder as ae
+        torch.manual_seed(1)
+        rs.model = atm.BiEncoder(ae.Cnn8Rnn(32000), te.SelfAttention(VOCAB, 512, 8, dropout=0.2),
+                                 match.DotProduct(text_level="token"), 512,
+                                 cross_encoder=ce.CrossAttentionGating(512)).to(rs.device)
+        rs.optimizer = torch.optim.Adam(rs.model.parameters(), lr=1e-3)
+        return rs, "train"
+    return None
+
+
+def cpu_reference_rate(name, clips, steps, warmup):
+    """(clips/s, mean s/step, cores, kind, per-step times) of the reference on all host threads."""
+    import torch
     torch.set_num_threads(os.cpu_count())
-    sd = O.synth_state_dict(seed=1)
-    batch = O.synth_batch(batch_size, n_samples, N_TOKENS, seed=0, tonal=False)
-    opt = O.AdamState(O.trainable_keys())
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        O.train_step(sd, batch, opt, dropout=True, fast_gru=True)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    times.sort()
-    return times[len(times) // 2], os.cpu_count()
+    built = _reference_model(name, "cpu")
+    if built is not None:
+        rs, mode = built
+        batch = synth_host_batch(clips, 0, pin=False)
+        times = rs.time(batch, steps, warmup, mode)
+        kind = "reference"
+    else:
+        if name != "train_bf16":
+            raise RuntimeError("oracle/_ref is not staged and the oracle port only restates the train step")
+        from oracle import tag_oracle as O
+        sd = O.synth_state_dict(seed=1)
+        batch = O.synth_batch(clips, N_SAMPLES, N_TOKENS, seed=0, tonal=False)
+        opt = O.AdamState(O.trainable_keys())
+        times = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.train_step(sd, batch, opt, dropout=True, fast_gru=True)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind = "port"
+    sec = sum(times) / len(times)
+    return clips / sec, sec, os.cpu_count(), kind, times
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the workload: rank 0 alone, exactly --warmup + --steps steps, every
+    step a bounded sample (REF_SAMPLE_CLIPS clips) of the per-GPU batch; the line says what was run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    bs = 8
-    sec, cores = cpu_reference_step_time(bs, N_SAMPLES, max(1, min(args.steps, 3)), min(args.warmup, 1))
-    v = bs / sec
-    sample = f"train step on {bs} of the 64 clips (10 s @32 kHz, 8 tokens), median of {max(1, min(args.steps, 3))}"
+    name = args.config
+    kind_w, B, _, metric, _ = WORKLOADS[name]
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    if name == "clap_infer":
+        print(json.dumps({"impl": "reference", "unavailable": "the CLAP configuration needs the pretrained "
+                          "laion/clap-htsat-fused download (no network); its random-init oracle lives in tests/"}))
+        return
+    clips = min(REF_SAMPLE_CLIPS, B)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    v, sec, cores, kind, _ = cpu_reference_rate(name, clips, steps, warmup)
+    what = "train step (zero_grad, forward, FrameBceLoss, backward, clip_grad_norm_, Adam)" if kind_w == "train" \
+        else "eval forward (no_grad)"
+    sample = (f"{what} of the {'unmodified reference modules (oracle/_ref)' if kind == 'reference' else 'oracle port'}"
+              f" on {clips} of the {B} clips per step (10 s @32 kHz, 8 tokens), fp32, {cores} host threads, one "
+              f"process; {warmup} warm-up + {steps} timed steps, mean")
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": metric, "value": v, "unit": "clips/s", "n_gpus": 1,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(B=BATCH), "global_batch": BATCH * args.gpus,
-                   "parallelism": f"dp{args.gpus}"},
-        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": config_dict(name, B, world),
+        "clips_per_step": clips, "gpus_used": 0, "processes": 1, "n_gpus_requested": args.gpus,
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def gpu_baseline(name, B):
+    """The reference modules under stock torch.cuda eager on this GPU (BASELINE.json configs[1] "vs reference
+    torch.cuda"): fp32 as set_seed leaves cuDNN (deterministic, benchmark off, no TF32), fp32 with
+    cudnn.benchmark + TF32, and bf16 autocast.  ms per step, median of 5 after 3 warm-up, synchronised per step."""
+    import torch
+    out = {"kind": None, "device": torch.cuda.get_device_name(0), "batch": B, "rows": []}
+    variants = [("fp32 cudnn deterministic, benchmark off, TF32 off (train_util.set_seed)", {}),
+                ("fp32 cudnn.benchmark on, TF32 on", {"cudnn_benchmark": True, "tf32": True}),
+                ("bf16 autocast, cudnn.benchmark on", {"cudnn_benchmark": True, "tf32": True, "autocast_bf16": True})]
+    batch = synth_host_batch(B, 0, pin=False)
+    for label, kw in variants:
+        row = {"setting": label}
+        try:
+            built = _reference_model(name, "cuda", **kw)
+            if built is None:
+                out["unavailable"] = "oracle/_ref not staged"
+                return out
+            rs, mode = built
+            out["kind"] = "reference"
+            for m in (("train", "eval") if mode == "train" else ("eval",)):
+                t = sorted(rs.time(batch, 5, 3, m))
+                med = t[len(t) // 2]
+                row[f"{m}_ms"] = round(med * 1e3, 3)
+                row[f"{m}_clips_per_s"] = round(B / med, 1)
+            del rs
+        except Exception as e:      # a stock-torch failure is a fact about the baseline, not about this repository
+            row["error"] = f"{type(e).__name__}: {str(e)[:200]}"
+        torch.cuda.empty_cache()
+        out["rows"].append(row)
+    torch.backends.cudnn.benchmark = False
+    return out
 
 
 class ClockSampler:
@@ -154,15 +276,176 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# the B200 arm
+class TrainWorkload:
+    """train_bf16: FusedTrainStep on BiEncoder(Cnn8Rnn, EmbeddingAgg, DotProduct) — the headline;
+    attn_bf16: AutogradTrainStep on BiEncoder(Cnn8Rnn, SelfAttention, DotProduct(token), CrossAttentionGating)."""
+
+    def __init__(self, name, B, precision, rank, args):
+        import torch
+        from texttoaudiogrounding_b200.models.audio_encoder import Cnn8Rnn
+        from texttoaudiogrounding_b200.models.audio_text_model import BiEncoder
+        from texttoaudiogrounding_b200.models.match import DotProduct
+        from texttoaudiogrounding_b200.models.text_encoder import EmbeddingAgg, SelfAttention
+        from texttoaudiogrounding_b200.train import AutogradTrainStep, FusedTrainStep
+        torch.manual_seed(1)
+        if name == "train_bf16":
+            model = BiEncoder(Cnn8Rnn(32000, compute_dtype=precision), EmbeddingAgg(VOCAB, 512), DotProduct(), 512)
+            self.ts = FusedTrainStep(model.cuda().train(), lr=1e-3, max_grad_norm=1.0, use_graph=not args.no_graph,
+                                     base_seed=1)
+        else:
+            from texttoaudiogrounding_b200.models.cross_encoder import CrossAttentionGating
+            model = BiEncoder(Cnn8Rnn(32000, compute_dtype=precision), SelfAttention(VOCAB, 512, 8, dropout=0.2),
+                              DotProduct(text_level="token"), 512, cross_encoder=CrossAttentionGating(512))
+            self.ts = AutogradTrainStep(model.cuda().train(), lr=1e-3, max_grad_norm=1.0, use_graph=not args.no_graph)
+        self.hosts = [synth_host_batch(B, 100 + rank, args.wav_fp16), synth_host_batch(B, 200 + rank, args.wav_fp16)]
+        self.h2d = sum(v.numel() * v.element_size() for v in self.hosts[0].values())
+        self.d2h = 4
+        self.flops_per_clip = 3 * FWD_GFLOP_PER_CLIP
+        self.last = None
+
+    def warm(self):
+        self.ts.step(self.hosts[0])
+
+    def resident(self):
+        self.ts.step(None)
+
+    def e2e(self, steps):
+        """two pinned host batches alternate; the copy of step i+1's inputs is started (prefetch) right after step i
+        is queued, so it overlaps step i's kernels; every step uploads its own inputs and its own loss is copied to
+        the host and read there one step late, so the host never stalls the queue (software pipelining of the
+        reference's synchronous loss.item())"""
+        ts, hosts = self.ts, self.hosts
+        ts.prefetch(hosts[0])
+        pending = None
+        for i in range(steps):
+            handle = ts.step_async(hosts[i % 2])
+            if i + 1 < steps:
+                ts.prefetch(hosts[(i + 1) % 2])
+            if pending is not None:
+                self.last = pending.result()
+            pending = handle
+        self.last = pending.result()
+
+    def result(self):
+        return float(self.ts.loss_out.item())
+
+    def profile_step(self):
+        ts = self.ts
+        g, w = ts.use_graph, ts.world
+        ts.use_graph, ts.world = False, 1      # rank-0-only pass: no collective (the other ranks are not in it)
+        ts.step(None)
+        ts.use_graph, ts.world = g, w
+
+
+class InferWorkload:
+    """fwd_fp32: BiEncoder eval forward in fp32 mode; clap_infer: the Hugging Face facade with the CLAP text tower."""
+
+    def __init__(self, name, B, precision, rank, args):
+        import torch
+        from texttoaudiogrounding_b200.models.audio_encoder import Cnn8Rnn
+        from texttoaudiogrounding_b200.models.audio_text_model import BiEncoder
+        from texttoaudiogrounding_b200.models.match import DotProduct
+        from texttoaudiogrounding_b200.models.text_encoder import EmbeddingAgg
+        self.torch = torch
+        torch.manual_seed(1)
+        self.name, self.B = name, B
+        g = torch.Generator().manual_seed(100 + rank)
+        wav = 0.1 * torch.randn(B, N_SAMPLES, generator=g)
+        self.host_wav = [wav.pin_memory(), wav.roll(1, 0).pin_memory()]
+        if name == "fwd_fp32":
+            self.model = BiEncoder(Cnn8Rnn(32000, compute_dtype=precision), EmbeddingAgg(VOCAB, 512), DotProduct(),
+                                   512).cuda().eval()
+            self.text = torch.randint(2, VOCAB, (B, N_TOKENS), generator=g).cuda()
+            self.text_len = torch.full((B,), N_TOKENS, dtype=torch.long, device="cuda")
+            text_bytes = self.text.numel() * 8 + B * 8
+        else:
+            from transformers import ClapTextConfig
+            from texttoaudiogrounding_b200.models.hf_modeling_grounding import (Cnn8RnnLaionClapGroundingConfig,
+                                                                                Cnn8RnnLaionClapGroundingModel)
+            self.model = Cnn8RnnLaionClapGroundingModel(
+                Cnn8RnnLaionClapGroundingConfig(text_encoder_name=ClapTextConfig())).cuda().eval()
+            ids = torch.randint(4, 50000, (B, 10), generator=g)
+            ids[:, 0], ids[:, -1] = 0, 2
+            self.tokens = {"input_ids": ids.cuda(), "attention_mask": torch.ones(B, 10, dtype=torch.long, device="cuda")}
+            text_bytes = 2 * ids.numel() * 8
+        self.dev_wav = [torch.empty(B, N_SAMPLES, device="cuda"), torch.empty(B, N_SAMPLES, device="cuda")]
+        self.dev_wav[0].copy_(self.host_wav[0])
+        self.wav_len = [N_SAMPLES] * B
+        self.out_host = [torch.empty(B, 250).pin_memory() for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream()
+        self.h2d = wav.numel() * 4 + text_bytes
+        self.d2h = B * 250 * 4
+        self.flops_per_clip = FWD_GFLOP_PER_CLIP
+        self.last = None
+
+    def _forward(self, wav):
+        with self.torch.no_grad():
+            if self.name == "fwd_fp32":
+                return self.model({"waveform": wav, "waveform_len": self.wav_len, "specaug": False, "text": self.text,
+                                   "text_len": self.text_len})["frame_sim"]
+            return self.model(wav, self.wav_len, self.tokens)
+
+    def warm(self):
+        self.sim = self._forward(self.dev_wav[0])
+
+    def resident(self):
+        self.sim = self._forward(self.dev_wav[0])
+
+    def e2e(self, steps):
+        """double-buffered: the waveform batch of step i+1 is uploaded on a copy stream while step i computes; every
+        step's frame_sim [B, 250] is copied back to pinned host memory (read there after the final synchronize)"""
+        torch = self.torch
+        cur = torch.cuda.current_stream()
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in free:
+            e.record()
+
+        def upload(i):
+            j = i % 2
+            self.copy_stream.wait_event(free[j])
+            with torch.cuda.stream(self.copy_stream):
+                self.dev_wav[j].copy_(self.host_wav[j], non_blocking=True)
+                ready[j].record()
+
+        upload(0)
+        for i in range(steps):
+            j = i % 2
+            if i + 1 < steps:
+                upload(i + 1)
+            cur.wait_event(ready[j])
+            sim = self._forward(self.dev_wav[j])
+            free[j].record()
+            self.out_host[j].copy_(sim, non_blocking=True)
+        torch.cuda.synchronize()
+        self.last = float(self.out_host[(steps - 1) % 2].mean())
+
+    def result(self):
+        return float(self.sim.mean().item())
+
+    def profile_step(self):
+        te = getattr(self.model, "model", self.model).text_encoder
+        g = getattr(te, "use_graph", None)
+        if g is not None:
+            te.use_graph = False                 # per-kernel events cannot see inside a replayed graph
+        self.resident()
+        if g is not None:
+            te.use_graph = g
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--precision", default="bf16")
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--config", default="train_bf16", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=None, help="override the workload's compute dtype (bf16 | fp32)")
+    ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--wav-fp16", action="store_true",
                     help="host waveforms in float16 (the reference's h5 storage type): halves the H2D bytes")
@@ -174,11 +457,6 @@ def main():
     import torch
     import torch.distributed as dist
     from texttoaudiogrounding_b200 import _lib, ops
-    from texttoaudiogrounding_b200.models.audio_encoder import Cnn8Rnn
-    from texttoaudiogrounding_b200.models.audio_text_model import BiEncoder
-    from texttoaudiogrounding_b200.models.match import DotProduct
-    from texttoaudiogrounding_b200.models.text_encoder import EmbeddingAgg
-    from texttoaudiogrounding_b200.train import FusedTrainStep
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -189,22 +467,11 @@ def main():
     if not os.path.exists(_lib.LIB_PATH):
         raise RuntimeError("libtag_b200.so missing: run __graft_entry__.build() (no fallback path)")
 
-    B = args.batch
-    torch.manual_seed(1)
-    model = BiEncoder(Cnn8Rnn(32000, compute_dtype=args.precision), EmbeddingAgg(5221, 512), DotProduct(), 512)
-    model = model.cuda().train()
-    ts = FusedTrainStep(model, lr=1e-3, max_grad_norm=1.0, use_graph=not args.no_graph, base_seed=1 + rank)
-
-    g = torch.Generator().manual_seed(100 + rank)
-    host = {
-        "waveform": (0.1 * torch.randn(B, N_SAMPLES, generator=g)).to(
-            torch.float16 if args.wav_fp16 else torch.float32).pin_memory(),
-        "waveform_len": torch.full((B,), N_SAMPLES, dtype=torch.long).pin_memory(),
-        "text": torch.randint(2, 5221, (B, N_TOKENS), generator=g).pin_memory(),
-        "text_len": torch.full((B,), N_TOKENS, dtype=torch.long).pin_memory(),
-        "label": (torch.rand(B, 251, generator=g) > 0.5).float().pin_memory(),
-    }
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    name = args.config
+    kind, B, precision, metric, _ = WORKLOADS[name]
+    B = args.batch or B
+    precision = args.precision or precision
+    wl = (TrainWorkload if kind == "train" else InferWorkload)(name, B, precision, rank, args)
 
     def barrier():
         if world > 1:
@@ -213,10 +480,10 @@ def main():
 
     # ---- warm-up (first step eager, second captures the graphs)
     launches0 = ops.LAUNCHES
-    ts.step(host)
+    wl.warm()
     launches_per_step = ops.LAUNCHES - launches0
     for _ in range(args.warmup - 1):
-        ts.step(host)
+        wl.warm()
     barrier()
 
     # ---- device-resident timing
@@ -227,44 +494,33 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        ts.step(None)
+        wl.resident()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    loss_dev = float(ts.loss_out.item())
+    res_resident = wl.result()
 
     # ---- end-to-end timing through the public API with host buffers
-    hosts = [host, {k: v.clone().pin_memory() for k, v in host.items()}]
     barrier()
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    last = 0.0
-    # two pinned host batches alternate; the copy of step i+1's inputs is started (prefetch) right after step i
-    # is queued, so it overlaps step i's kernels; every step uploads its own inputs and its own loss is copied to
-    # the host and read there — one step late, so the host never stalls the queue (software pipelining of the
-    # reference's synchronous loss.item())
-    ts.prefetch(hosts[0])
-    pending = None
-    for i in range(args.steps):
-        handle = ts.step_async(hosts[i % 2])      # queues the step and the D2H copy of ITS loss (pinned slot)
-        if i + 1 < args.steps:
-            ts.prefetch(hosts[(i + 1) % 2])
-        if pending is not None:
-            last = pending.result()               # host read of step i-1's loss while step i runs
-        pending = handle
-    last = pending.result()                       # every step's loss has been read on the host by here
+    wl.e2e(args.steps)
     f1.record()
     barrier()
-    ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3 * 0.0)
     wall_e2e = (time.perf_counter() - t0) * 1e3
+    ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([ms, max(ms_e2e, 0.0), wall_e2e], device="cuda", dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, wall_e2e], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e, wall_e2e = [float(x) for x in t.tolist()]
     ms_e2e = max(ms_e2e, wall_e2e)            # the host-visible time bounds the end-to-end figure
+
+    clips = B * world * args.steps
+    value = clips / (ms * 1e-3)
+    h2d_d2h, last, flops_per_clip = (wl.h2d, wl.d2h), wl.last, wl.flops_per_clip
 
     # ---- live per-kernel timing of one eager step (CUDA events around every C-ABI call)
     roofline, kernels = None, None
@@ -274,20 +530,16 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        ts_use_graph, ts_world = ts.use_graph, ts.world
-        ts.use_graph = False
-        ts.world = 1            # rank-0-only pass: no collective (the other ranks are not in it)
         ops.PROFILE = []
-        ts.step(None)
+        wl.profile_step()
         torch.cuda.synchronize()
         recs, ops.PROFILE = ops.PROFILE, None
-        ts.use_graph, ts.world = ts_use_graph, ts_world
         agg = {}
         total_ms = 0.0
-        for name, tag, flops, nbytes, s, e in recs:
+        for kname, tag, flops, nbytes, s, e in recs:
             d = s.elapsed_time(e)
             total_ms += d
-            a = agg.setdefault(name, {"ms": 0.0, "launches": 0, "flops": 0.0})
+            a = agg.setdefault(kname, {"ms": 0.0, "launches": 0, "flops": 0.0})
             a["ms"] += d; a["launches"] += 1; a["flops"] += flops
         top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
         kernels = {k: {"ms_per_step": round(v["ms"], 3), "launches": v["launches"],
@@ -295,61 +547,72 @@ def main():
                        **({"tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)} if v["flops"] else {})}
                    for k, v in top[:24]}
         layers = {}
-        for name, tag, flops, nbytes, s, e in recs:
+        for kname, tag, flops, nbytes, s, e in recs:
             if flops > 0:
-                a = layers.setdefault(f"{name.replace('tag_conv_', '')} {tag}", [0.0, 0.0])
+                a = layers.setdefault(f"{kname.replace('tag_conv_', '')} {tag}", [0.0, 0.0])
                 a[0] += flops; a[1] += s.elapsed_time(e)
         kernels["_sum_of_kernel_ms_eager_step"] = round(total_ms, 3)
-        kernels["_dense_layers_tflops"] ={k: [round(v[0] / (v[1] * 1e-3) / 1e12, 1), round(v[1], 3)]
+        kernels["_dense_layers_tflops"] = {k: [round(v[0] / (v[1] * 1e-3) / 1e12, 1), round(v[1], 3)]
                                            for k, v in layers.items()}
         dom_name, dom = top[0]
+        sust = peaks.get("bf16_tflops_sustained", 1400.0)
+        burst = peaks.get("bf16_tflops", 1650.0)
         if dom["flops"] > 0:
-            peak = peaks.get("bf16_tflops_sustained", 1400.0)
             ach = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
             traffic = None
             try:          # DRAM bytes per launch of the dominant kernel from the committed ncu capture
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[dom_name]["traffic_bytes_per_launch"]
+                tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                traffic = tr[dom_name]["traffic_bytes_per_launch"]
             except Exception:
                 pass
-            roofline = {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": traffic,
-                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-                        if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
+            roofline = {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": sust, "unit": "TFLOP/s",
+                        "frac": ach / sust, "traffic": traffic,
+                        "frac_sustained": ach / sust, "frac_burst": ach / burst, "peak_burst": burst,
+                        "sm_mhz_during_run": clocks.get("sm_mhz") if clocks else None,
+                        "peak_source": ("MEASURED_PEAKS.json: `peak` = bf16_tflops_sustained (cuBLAS back to back for 4 s,"
+                                        " power-capped clocks), `peak_burst` = bf16_tflops (best of 10); this kernel is "
+                                        "timed inside one eager step at the SM clock above, so frac_burst is the "
+                                        "conservative reading") if peaks else "fallback (B200_PROFILING.md)",
                         "flops_per_launch": dom["flops"] / dom["launches"],
                         "avg_launch_ms": dom["ms"] / dom["launches"], "launches_per_step": dom["launches"],
-                        "share_of_step": dom["ms"] / total_ms}
+                        "share_of_step": dom["ms"] / total_ms,
+                        "whole_step_tflops": value * wl.flops_per_clip / 1e3 / world,
+                        "whole_step_frac": value * wl.flops_per_clip / 1e3 / world / sust,
+                        "whole_step_frac_burst": value * wl.flops_per_clip / 1e3 / world / burst}
         else:
             peak = peaks.get("hbm_gbs", 6650.0)
             roofline = {"kernel": dom_name, "bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s",
                         "frac": None, "traffic": None}
 
-    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        bs = 8
-        sec, cores = cpu_reference_step_time(bs, N_SAMPLES, 2, 1)
-        cpu_baseline = {"value": bs / sec, "unit": "clips/s", "cores": cores, "kind": "port",
-                        "sample": f"oracle train step on {bs} of the 64 clips (10 s @32 kHz), median of 2 after 1 warm-up"}
+    # ---- baselines (rank 0, N=1 only): the reference on the host cores and under stock torch.cuda on this GPU
+    cpu_baseline, gpu_base = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and name != "clap_infer":
+        del wl
+        torch.cuda.empty_cache()
+        clips_s = min(REF_SAMPLE_CLIPS, B)
+        v, sec, cores, rkind, _ = cpu_reference_rate(name, clips_s, 2, 1)
+        cpu_baseline = {"value": v, "unit": "clips/s", "cores": cores, "kind": rkind,
+                        "sample": f"{'reference modules (oracle/_ref)' if rkind == 'reference' else 'oracle port'}: "
+                                  f"{'train step' if kind == 'train' else 'eval forward'} on {clips_s} of the {B} clips "
+                                  f"(10 s @32 kHz), fp32, mean of 2 after 1 warm-up"}
+        if not args.no_gpu_baseline:
+            gpu_base = gpu_baseline(name, B)
 
     if rank == 0:
-        clips = B * world * args.steps
-        value = clips / (ms * 1e-3)
         line = {
-            "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": WORKLOAD.format(B=B),
-                       "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": "per-step working set (>5 GB of activations) is far larger than the 126 MB L2",
-                       "cuda_graph": ts.use_graph, "dropout": True,
-                       "waveform_dtype": "f16" if args.wav_fp16 else "f32"},
-            "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "vs_baseline": None, "dtype": precision, "data": "synthetic",
+            "config": config_dict(name, B, world),
+            "details": {"cuda_graph": not args.no_graph, "dropout": kind == "train",
+                        "waveform_dtype": "f16" if args.wav_fp16 else "f32", "bench_config": name},
+            "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d_d2h[0],
+                    "d2h_bytes_per_step": h2d_d2h[1], "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
-            "clocks": clocks, "loss": last, "loss_resident": loss_dev,
-            "algorithmic_tflops": value * TRAIN_GFLOP_PER_CLIP / 1e3 / world,
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "result_e2e": last, "result_resident": res_resident,
+            "algorithmic_tflops": value * flops_per_clip / 1e3 / world,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_base,
         }
         print(json.dumps(line))
     if world > 1:

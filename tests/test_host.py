@@ -234,7 +234,12 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"] == base["metric"] and line["unit"] == "clips/s"
     assert line["higher_is_better"] is True and line["value"] > 0 and line["n_gpus"] == 1
     assert "configs[2]" in line["config"]["workload"]
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the line describes what was run: exactly the requested steps, on a stated sample of the batch, on no GPU
+    assert line["steps"] == 1 and line["warmup"] == 0 and line["gpus_used"] == 0 and line["clips_per_step"] == 8
+    assert abs(line["value"] - line["clips_per_step"] / (line["ms_per_step"] * 1e-3)) < 1e-6 * line["value"]
+    staged = os.path.isfile(os.path.join(root, "oracle", "_ref", "models", "audio_encoder.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged or os.path.isdir("/root/reference/models") else "port")
+    assert line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

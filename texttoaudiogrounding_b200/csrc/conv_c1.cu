@@ -302,15 +302,22 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
     constexpr int W = TW;
 
     for (int i = threadIdx.x; i < CO * 9; i += 256) s_dw[i] = 0.f;
-    // B fragments of the dgrad product: w[co][tap] as bf16, k = co, n = tap (second n-tile: tap 8 only)
-    uint32_t wb[4][2][2];
+    // B fragments of the dgrad product: w[co][tap], k = co, n = tap (second n-tile: tap 8 only).  The fp32 weights
+    // enter as bf16 hi + lo pairs (two MMAs): a once-rounded weight is a SYSTEMATIC error that does not average out
+    // over the 4 M pixels summed into the bn0 gradients (dgamma0 / dbeta0 cancel heavily: bn1 removes scale and shift)
+    uint32_t wb[4][2][2], wl[4][2][2];
+    auto lo_of = [](float v) { return v - __bfloat162float(__float2bfloat16_rn(v)); };
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
             const int co = ks * 16 + hf * 8 + 2 * t;
-            wb[ks][0][hf] = pack2(w[co * 9 + g], w[(co + 1) * 9 + g]);
-            wb[ks][1][hf] = g == 0 ? pack2(w[co * 9 + 8], w[(co + 1) * 9 + 8]) : 0u;
+            const float w0 = w[co * 9 + g], w1 = w[(co + 1) * 9 + g];
+            const float v0 = w[co * 9 + 8], v1 = w[(co + 1) * 9 + 8];
+            wb[ks][0][hf] = pack2(w0, w1);
+            wl[ks][0][hf] = pack2(lo_of(w0), lo_of(w1));
+            wb[ks][1][hf] = g == 0 ? pack2(v0, v1) : 0u;
+            wl[ks][1][hf] = g == 0 ? pack2(lo_of(v0), lo_of(v1)) : 0u;
         }
     float acc[8][4];
 #pragma unroll
@@ -384,6 +391,8 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
         for (int q = 0; q < 4; ++q) {
             mma16816(s0, a[q], wb[q][0][0], wb[q][0][1]);
             mma16816(s1, a[q], wb[q][1][0], wb[q][1][1]);
+            mma16816(s0, a[q], wl[q][0][0], wl[q][0][1]);
+            mma16816(s1, a[q], wl[q][1][0], wl[q][1][1]);
         }
         Srow[g * 9 + 2 * t] = s0[0];
         Srow[g * 9 + 2 * t + 1] = s0[1];

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from .. import engine
+from . import nn_ops
 from ..frontend_consts import hann_window, slaney_mel_fbanks
 from .base import LoadPretrainedMixin, merge_matched_keys
 
@@ -103,7 +104,7 @@ class _Cnn8RnnFunction(torch.autograd.Function):
         out, ectx = engine.encoder_forward(
             Wt, waveform, training=training, bn_training=module.bn0.training,
             dropout=module.dropout_enabled, seed=seed, dtype=module.compute_dtype, save=save,
-            stages=module._stages)
+            seed_dev=nn_ops.SEED_DEV, stages=module._stages)
         ctx.module, ctx.ectx, ctx.Wt = module, ectx, Wt
         return out
 

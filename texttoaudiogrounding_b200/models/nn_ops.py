@@ -11,6 +11,9 @@ from .. import ops
 from ..ops import call
 
 _SEEDS = itertools.count(0x5EED)
+# device-side addend of every dropout seed (a 1-element int64/uint64 CUDA tensor, or None).  A graph-replayed train step
+# points it at its step counter so that replays draw fresh masks although the host seeds are frozen in the graph.
+SEED_DEV = None
 
 
 def next_seed() -> int:
@@ -112,7 +115,7 @@ class _MhaCoreFunction(torch.autograd.Function):
         Lk = k.shape[1]
         out = torch.empty_like(q)
         probs = torch.empty(B, heads, Lq, Lk, device=q.device, dtype=torch.float32)
-        call("tag_mha_core_fwd", q, k, v, key_len, out, probs, B, Lq, Lk, E, heads, float(dropout_p), seed, None)
+        call("tag_mha_core_fwd", q, k, v, key_len, out, probs, B, Lq, Lk, E, heads, float(dropout_p), seed, SEED_DEV)
         ctx.save_for_backward(q, k, v, probs, key_len)
         ctx.cfg = (heads, float(dropout_p), seed)
         return out
@@ -125,7 +128,7 @@ class _MhaCoreFunction(torch.autograd.Function):
         Lk = k.shape[1]
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         call("tag_mha_core_bwd", d_out.contiguous(), q, k, v, probs, key_len, dq, dk, dv, B, Lq, Lk, E, heads, p, seed,
-             None)
+             SEED_DEV)
         return dq, dk, dv, None, None, None, None
 
 
@@ -229,7 +232,7 @@ class _LnLinearSigmoidFunction(torch.autograd.Function):
         prob = torch.empty(R, device=audio.device, dtype=torch.float32)
         stat = torch.empty(R, 2, device=audio.device, dtype=torch.float32)
         call("tag_ln_linear_sigmoid_fwd", audio, attn_out, gamma, beta, w, bias, prob, stat, R, E, float(eps),
-             float(dropout_p), seed, None)
+             float(dropout_p), seed, SEED_DEV)
         ctx.save_for_backward(audio, attn_out, gamma, beta, w, prob, stat)
         ctx.cfg = (float(dropout_p), seed)
         return prob
@@ -243,7 +246,7 @@ class _LnLinearSigmoidFunction(torch.autograd.Function):
         d_gamma, d_beta, d_w = torch.zeros_like(gamma), torch.zeros_like(beta), torch.zeros_like(w)
         d_bias = torch.zeros(1, device=audio.device, dtype=torch.float32)
         call("tag_ln_linear_sigmoid_bwd", d_prob.contiguous(), prob, audio, attn_out, gamma, beta, w, stat, d_audio,
-             d_attn, d_gamma, d_beta, d_w, d_bias, R, E, p, seed, None)
+             d_attn, d_gamma, d_beta, d_w, d_bias, R, E, p, seed, SEED_DEV)
         return d_audio, d_attn, d_gamma, d_beta, d_w, d_bias, None, None, None
 
 

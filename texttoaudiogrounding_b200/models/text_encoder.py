@@ -156,7 +156,7 @@ class _TextAssembleFunction(torch.autograd.Function):
         B, N = tokens.shape
         V, E = emb.shape
         out = torch.empty(B, N + 1, E, device=emb.device, dtype=torch.float32)
-        call("tag_text_assemble_fwd", tokens, emb, cls, pe, out, B, N, E, V, float(dropout_p), seed, None)
+        call("tag_text_assemble_fwd", tokens, emb, cls, pe, out, B, N, E, V, float(dropout_p), seed, nn_ops.SEED_DEV)
         ctx.save_for_backward(tokens)
         ctx.cfg = (V, E, float(dropout_p), seed)
         return out
@@ -168,7 +168,7 @@ class _TextAssembleFunction(torch.autograd.Function):
         B, N = tokens.shape
         d_emb = torch.zeros(V, E, device=d_out.device, dtype=torch.float32)
         d_cls = torch.zeros(1, 1, E, device=d_out.device, dtype=torch.float32)
-        call("tag_text_assemble_bwd", tokens, d_out.contiguous(), d_emb, d_cls, B, N, E, V, p, seed, None)
+        call("tag_text_assemble_bwd", tokens, d_out.contiguous(), d_emb, d_cls, B, N, E, V, p, seed, nn_ops.SEED_DEV)
         return d_emb, d_cls, None, None, None, None
 
 

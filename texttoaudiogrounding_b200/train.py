@@ -692,3 +692,176 @@ class AlignFusedTrainStep(FusedTrainStep):
             call("tag_embed_mean_bwd", text, text_len, d_seq, ew.grad, rows, N, D, V)
         engine.encoder_backward(self.Wt, ectx, d_emb.contiguous(), self.G, side_stream=self.side_stream)
         self.sim = sim
+
+
+class AutogradTrainStep:
+    """The same production plumbing — flat fp32 parameter / gradient / Adam buffers, ONE all-reduce of the flat
+    gradient bucket, fused clip_grad_norm_ + Adam, CUDA-graph replay — around ANY of the mirrored model graphs,
+    with forward and backward driven by autograd (every node is one of this package's C-ABI autograd Functions).
+    This is how the configurations FusedTrainStep does not hard-code train at full speed: the attention-type heads of
+    BASELINE.json configs[3] (SelfAttention + CrossAttentionGating / CrossAttention), add_proj, upsample, ...
+
+    ``forward_fn(model, batch) -> loss`` is called with the static device batch; the default is Runner.forward +
+    ``loss_fn`` (run_strong.py:92-120, 139-141).  Every tensor of ``batch`` — lengths included — is kept on the device
+    so that the captured region contains no host->device copy."""
+
+    def __init__(self, model: nn.Module, loss_fn=None, forward_fn=None, lr: float = 1e-3, betas=(0.9, 0.999),
+                 eps: float = 1e-8, max_grad_norm: float = 1.0, process_group=None, use_graph: bool = True):
+        self.model = model
+        self.loss_fn = loss_fn or FrameBceLoss()
+        self.forward_fn = forward_fn or (lambda m, b: self.loss_fn(runner_forward(m, b, self.device, training=True)))
+        self.betas, self.eps, self.max_grad_norm = betas, eps, max_grad_norm
+        self.pg = process_group
+        self.world, self.rank = 1, 0
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
+        self.use_graph = use_graph
+        self.device = next(model.parameters()).device
+        params = [p for p in model.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in params)
+        dev = self.device
+        self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.n_params = n
+        off = 0
+        for p in params:
+            k = p.numel()
+            if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
+                co, ci, kh, kw = p.shape          # conv weight: memory stays [Cout][kh][kw][Cin]
+                pv = self.flat_p[off:off + k].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+                gv = self.flat_g[off:off + k].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+            else:
+                pv = self.flat_p[off:off + k].view(p.shape)
+                gv = self.flat_g[off:off + k].view(p.shape)
+            pv.copy_(p.data)
+            p.data = pv
+            p.grad = gv                          # autograd accumulates in place into the bucket
+            off += k
+        self._params = params
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.norm_out = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.loss_out = torch.zeros((), device=dev, dtype=torch.float32)
+        self.lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
+        self._lr = float(lr)
+        if self.world > 1:
+            src = torch.distributed.get_global_rank(self.pg, 0) if self.pg is not None else 0
+            for t in [self.flat_p] + [b for b in model.buffers()]:
+                torch.distributed.broadcast(t, src=src, group=self.pg)
+        self._graphs = OrderedDict()
+        self._seen = {}
+        self._graph_pool = None
+        self._static = None
+
+    MAX_GRAPHS = 8
+    lr = FusedTrainStep.lr
+    set_lr = FusedTrainStep.set_lr
+
+    def _fwd_bwd(self, s):
+        from .models import nn_ops
+        self.flat_g.zero_()
+        prev, nn_ops.SEED_DEV = nn_ops.SEED_DEV, self.step_dev
+        try:
+            loss = self.forward_fn(self.model, {k: v for k, v in s.items() if k != "key"})
+            loss.backward()
+        finally:
+            nn_ops.SEED_DEV = prev
+        for p in self._params:                    # a parameter the graph did not reach keeps its zero slice
+            assert p.grad is not None and p.grad.data_ptr() >= self.flat_g.data_ptr()
+        self.loss_out.copy_(loss.detach())
+
+    def _optim(self):
+        self.sumsq.zero_()
+        call("tag_sumsq", self.flat_g, self.n_params, self.sumsq)
+        call("tag_clip_adam", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_params,
+             self.sumsq, self.step_dev, 1.0 / self.world, float(self.max_grad_norm), float(self._lr), self.lr_dev,
+             float(self.betas[0]), float(self.betas[1]), float(self.eps), self.norm_out)
+
+    def _allreduce(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.pg)
+
+    @staticmethod
+    def _items(batch: Dict):
+        items = {k: torch.as_tensor(v) for k, v in batch.items() if not isinstance(v, (str, bool, list)) or
+                 (isinstance(v, list) and v and isinstance(v[0], (int, float)))}
+        key = tuple((k, tuple(t.shape), t.dtype) for k, t in sorted(items.items()))
+        return items, key
+
+    def _alloc(self, items, key):
+        d = {k: torch.empty(t.shape, device=self.device, dtype=t.dtype) for k, t in items.items()}
+        d["key"] = key
+        return d
+
+    def prefetch(self, batch: Dict) -> None:
+        """Start the host->device copy of ``batch`` on a copy stream (see FusedTrainStep.prefetch)."""
+        items, key = self._items(batch)
+        if getattr(self, "_staging", None) is None or self._staging["key"] != key:
+            self._staging = self._alloc(items, key)
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._staging_free = torch.cuda.Event()
+            self._staging_ready = torch.cuda.Event()
+            self._staging_free.record()
+        self._copy_stream.wait_event(self._staging_free)
+        with torch.cuda.stream(self._copy_stream):
+            for k, t in items.items():
+                self._staging[k].copy_(t, non_blocking=True)
+            self._staging_ready.record()
+        self._prefetched = batch
+
+    def _prepare_static(self, batch: Dict):
+        staged = getattr(self, "_prefetched", None) is batch and getattr(self, "_staging", None) is not None
+        if staged:
+            items, key = {k: v for k, v in self._staging.items() if k != "key"}, self._staging["key"]
+        else:
+            items, key = self._items(batch)
+        if self._static is None or self._static["key"] != key:
+            entry = self._graphs.get(key)
+            self._static = entry["static"] if entry is not None else self._alloc(items, key)
+        if staged:
+            torch.cuda.current_stream().wait_event(self._staging_ready)
+        for k, t in items.items():
+            self._static[k].copy_(t, non_blocking=True)
+        if staged:
+            self._staging_free.record()
+            self._prefetched = None
+        return self._static
+
+    _loss_slots = None
+    step_async = FusedTrainStep.step_async
+
+    def step(self, batch: Optional[Dict]) -> torch.Tensor:
+        """One train step; returns the device scalar holding this step's loss.  ``batch=None`` re-uses the inputs
+        already resident in the static device buffers."""
+        s = self._static if batch is None else self._prepare_static(batch)
+        key = s["key"]
+        seen = self._seen[key] = self._seen.get(key, 0) + 1
+        if not self.use_graph or seen == 1:
+            self._fwd_bwd(s)
+            self._allreduce()
+            self._optim()
+            return self.loss_out
+        entry = self._graphs.get(key)
+        if entry is None:
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            torch.cuda.synchronize()
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1, pool=self._graph_pool):
+                self._fwd_bwd(s)
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, pool=self._graph_pool):
+                self._optim()
+            entry = self._graphs[key] = {"fwd_bwd": g1, "optim": g2, "static": s}
+            while len(self._graphs) > self.MAX_GRAPHS:
+                old, _ = self._graphs.popitem(last=False)
+                self._seen.pop(old, None)
+        else:
+            self._graphs.move_to_end(key)
+        entry["fwd_bwd"].replay()
+        self._allreduce()
+        entry["optim"].replay()
+        return self.loss_out
