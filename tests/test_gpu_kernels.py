@@ -152,13 +152,13 @@ def test_conv_c1_fwd_bwd():
 @pytest.mark.parametrize("B,H", [(2, 11), (3, 37), (1, 16)])
 def test_conv_c1_bwd_bf16_mma(B, H):
     """bf16 Cin=1 backward (mma.sync kernel): dy, x, w rounded to bf16, fp32 accumulation — compare with
-    fp32 autograd on the same rounded operands (tiles of 16 rows: ragged last tile, halo rows)."""
+    fp32 autograd on the same rounded dy / x and the fp32 weights (tiles of 16 rows: ragged last tile, halo rows)."""
     ops = _ops()
     W = 64
     bf = torch.bfloat16
     x = torch.randn(B, 1, H, W, generator=g(17)).to(bf).float().requires_grad_(True)
     w32 = torch.randn(64, 1, 3, 3, generator=g(18)) * 0.2
-    w = w32.to(bf).float().requires_grad_(True)
+    w = w32.clone().requires_grad_(True)
     y = F.conv2d(x, w, padding=1)
     dy = torch.randn(y.shape, generator=g(19)).to(bf).float()
     y.backward(dy)
@@ -166,7 +166,8 @@ def test_conv_c1_bwd_bf16_mma(B, H):
     dx = torch.empty(B, H, W, device="cuda")
     ops.call("tag_conv_c1_bwd", dy.permute(0, 2, 3, 1).contiguous().cuda().to(bf), x.detach().reshape(B, H, W).cuda().to(bf),
              w32.reshape(64, 9).cuda(), 1, dw, dx, B, H, W)
-    # dw uses the bf16 operands exactly (fp32 accumulate); dx uses bf16(w)
+    # dw uses the bf16 operands exactly (fp32 accumulate; independent of w); dx uses the fp32 weights as bf16 hi + lo
+    # pairs (two MMAs), i.e. w to 16 mantissa bits
     assert rel_err(dw.cpu().reshape(64, 1, 3, 3), w.grad) < 1e-4
     assert rel_err(dx.cpu().reshape(B, 1, H, W), x.grad) < 1e-4
 

@@ -755,6 +755,7 @@ class AutogradTrainStep:
         self._seen = {}
         self._graph_pool = None
         self._static = None
+        self._cap_stream = None
 
     MAX_GRAPHS = 8
     lr = FusedTrainStep.lr
@@ -839,8 +840,22 @@ class AutogradTrainStep:
         s = self._static if batch is None else self._prepare_static(batch)
         key = s["key"]
         seen = self._seen[key] = self._seen.get(key, 0) + 1
-        if not self.use_graph or seen == 1:
+        if not self.use_graph:
             self._fwd_bwd(s)
+            self._allreduce()
+            self._optim()
+            return self.loss_out
+        if self._cap_stream is None:
+            self._cap_stream = torch.cuda.Stream(self.device)
+        if seen == 1:
+            # autograd binds every AccumulateGrad node to the stream its parameter was first used on, and a node that
+            # lives on the legacy default stream cannot run inside a capture: the eager first step of a shape already
+            # runs on the stream the graphs are captured on
+            cur = torch.cuda.current_stream()
+            self._cap_stream.wait_stream(cur)
+            with torch.cuda.stream(self._cap_stream):
+                self._fwd_bwd(s)
+            cur.wait_stream(self._cap_stream)
             self._allreduce()
             self._optim()
             return self.loss_out
@@ -850,7 +865,7 @@ class AutogradTrainStep:
                 self._graph_pool = torch.cuda.graph_pool_handle()
             torch.cuda.synchronize()
             g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1, pool=self._graph_pool):
+            with torch.cuda.graph(g1, pool=self._graph_pool, stream=self._cap_stream):
                 self._fwd_bwd(s)
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2, pool=self._graph_pool):
