@@ -66,6 +66,12 @@ def main():
         m = build(ns, variant).eval()
         with torch.no_grad():
             o = m(inputs())
+            # the yardstick for the bf16 mode: the same reference forward under torch.autocast(bfloat16)
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                oa = m(inputs())
+        out[f"eval_frame_sim_autocast/{variant}"] = oa["frame_sim"].float().numpy()
+        print(variant, "reference autocast-bf16 vs fp32 frame_sim max abs",
+              (oa["frame_sim"].float() - o["frame_sim"]).abs().max().item())
         out[f"text/{variant}"] = batch["text"].numpy()
         out[f"eval_frame_sim/{variant}"] = o["frame_sim"].numpy()
         out[f"eval_length/{variant}"] = np.asarray(o["length"])

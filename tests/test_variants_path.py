@@ -116,7 +116,11 @@ def test_variant_eval_matches_reference_golden(variant):
     model = _build(variant, sd, "bf16").eval()
     with torch.no_grad():
         out, _ = _forward(model, batch)
-    assert np.abs(out["frame_sim"].cpu().numpy() - g[f"eval_frame_sim/{variant}"]).max() <= 1e-2      # bf16 bar
+    # bf16 bar: 1e-2 (north_star) — or, where the fixture's logits are too steep for ANY bf16 implementation
+    # (multi_gating_proj: the unmodified reference under torch.autocast(bfloat16) is itself 3e-2 away from its fp32
+    # output, recorded in the fixture by oracle/make_golden_variants.py), no worse than the reference's own bf16 run
+    ref_bf16 = np.abs(g[f"eval_frame_sim_autocast/{variant}"] - g[f"eval_frame_sim/{variant}"]).max()
+    assert np.abs(out["frame_sim"].cpu().numpy() - g[f"eval_frame_sim/{variant}"]).max() <= max(1e-2, ref_bf16)
 
 
 @pytest.mark.gpu
