@@ -96,6 +96,10 @@ int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, dou
                          int W, int Cin, int Cout, const void* bn_y, const float* bn_scale,
                          const float* bn_shift, const float* bn_mean, const float* bn_invstd,
                          cudaStream_t stream);
+/* Scheduling knob of tag_conv_tc_fwd_halo (same results either way): 1 (default) = layers whose weights stream
+ * (Cin >= 128) run on CTA PAIRS — a 2-CTA cluster computes a 256-pixel tile with cta_group::2 tcgen05 MMAs, each CTA
+ * loading half of every weight tile; 0 = one CTA per 128-pixel tile everywhere. */
+int tag_conv_halo_set_pair_mode(int mode);
 /* its weight operand: bf16 tap-major [9][Cout][Cin] (flip_transpose=0) or, for dgrad,
  * [9][Cin][Cout] of the 180-degree rotated kernel (flip_transpose=1), from the fp32 master. */
 int tag_weight_prep_tapmajor_bf16(const float* w, void* out, int Co, int Ci, int flip_transpose,

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Micro-benchmark of the dense tcgen05 kernels on the model's layer shapes (B = 64, 10 s clips).
-Usage: python scripts/bench_conv.py [fwd|wgrad] — prints ms and TFLOP/s per layer (CUDA events, L2 flushed)."""
+Usage: python scripts/bench_conv.py [fwd|dgrad|wgrad] — prints ms and TFLOP/s per layer (CUDA events, L2 flushed)."""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -36,6 +36,18 @@ def main(which):
             for label, stats in (("stats", st), ("nostats", None)):
                 ms = timeit(lambda: ops.conv_fwd(x, w, y, None, False, stats, B, H, W, Cin, Cout, 9))
                 print(f"fwd {H}x{W} {Cin}->{Cout} {label}: {ms:.3f} ms {flops / ms / 1e9:.0f} TFLOP/s")
+        elif which == "dgrad":
+            # the halo kernel as dgrad: input dy [.., Cout], output [.., Cin]; with the fused ReLU + BN-backward reduce
+            # when the layer is a block's conv2 (Cin == Cout)
+            dy = torch.randn(B, H, W, Cout, device="cuda").bfloat16()
+            wt = ops.prep_weight_t(w32, Cout, Cin, 9, torch.bfloat16, W)
+            dx = torch.empty(B, H, W, Cin, device="cuda", dtype=torch.bfloat16)
+            red = torch.zeros(2 * Cin, device="cuda", dtype=torch.float64)
+            aux = [torch.rand(Cin, device="cuda") + 0.5 for _ in range(4)]
+            fuse = (x, *aux) if Cin == Cout else None
+            ms = timeit(lambda: ops.conv_fwd(dy, wt, dx, None, False, red if fuse else None, B, H, W, Cout, Cin, 9,
+                                             bn_fuse=fuse))
+            print(f"dgrad {H}x{W} {Cout}->{Cin} {'bn_fuse' if fuse else 'plain'}: {ms:.3f} ms {flops / ms / 1e9:.0f} TFLOP/s")
         else:
             dy = torch.randn(B, H, W, Cout, device="cuda").bfloat16()
             dw = torch.zeros(Cout, 3, 3, Cin, device="cuda")

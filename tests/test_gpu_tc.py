@@ -15,6 +15,17 @@ def g(seed=0):
     return torch.Generator().manual_seed(seed)
 
 
+@pytest.fixture
+def halo_mode(request):
+    """halo kernel scheduling: True = default (CTA pairs with cta_group::2 MMAs where the weights stream),
+    "single" = one CTA per tile everywhere, False = the plain (no halo re-use) kernel."""
+    from texttoaudiogrounding_b200 import _lib
+    mode = request.param
+    _lib.lib().tag_conv_halo_set_pair_mode(0 if mode == "single" else 1)
+    yield bool(mode)
+    _lib.lib().tag_conv_halo_set_pair_mode(1)
+
+
 def _bf(x):
     return x.bfloat16().float()
 
@@ -29,12 +40,15 @@ SHAPES = [
     (3, 50, 8, 256, 512),     # block 4 conv1 (two N tiles)
     (2, 33, 8, 512, 512),     # block 4 conv2
     (40, 50, 8, 256, 512),    # > 148 tiles: persistent loop + both TMEM stages
+    (1, 16, 8, 256, 256),     # ONE tile: the second CTA of a pair computes a padding tile
+    (3, 40, 16, 128, 64),     # block-2 conv1 dgrad shape (N = 64, weights stream), odd tile count
 ]
 
 
-@pytest.mark.parametrize("halo", [True, False])
+@pytest.mark.parametrize("halo_mode", [True, "single", False], indirect=True)
 @pytest.mark.parametrize("B,H,W,Cin,Cout", SHAPES)
-def test_tc_conv3x3_fwd(B, H, W, Cin, Cout, halo):
+def test_tc_conv3x3_fwd(B, H, W, Cin, Cout, halo_mode):
+    halo = halo_mode
     from texttoaudiogrounding_b200 import ops
     x = _bf(torch.randn(B, Cin, H, W, generator=g(1)))
     w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g(2)) * (1.0 / (3 * Cin ** 0.5)))
@@ -58,9 +72,10 @@ def test_tc_conv3x3_fwd(B, H, W, Cin, Cout, halo):
     assert rel_err(yb.float(), ref) < 6e-3
 
 
-@pytest.mark.parametrize("halo", [True, False])
+@pytest.mark.parametrize("halo_mode", [True, "single", False], indirect=True)
 @pytest.mark.parametrize("B,H,W,Cin,Cout", SHAPES[:7])
-def test_tc_conv3x3_dgrad_and_wgrad(B, H, W, Cin, Cout, halo):
+def test_tc_conv3x3_dgrad_and_wgrad(B, H, W, Cin, Cout, halo_mode):
+    halo = halo_mode
     from texttoaudiogrounding_b200 import ops
     x = _bf(torch.randn(B, Cin, H, W, generator=g(3))).cuda().requires_grad_(True)
     w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g(4)) * (1.0 / (3 * Cin ** 0.5))).cuda().requires_grad_(True)
@@ -163,8 +178,9 @@ def test_bigru_bf16_tensor_core_variant_close_to_oracle(B, T):
     assert torch.equal(hp[:, 1:], out[:, :-1, :256].bfloat16()) and float(hp[:, 0].float().abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("B,H,W,C", [(2, 21, 16, 128), (3, 9, 64, 64), (2, 17, 8, 512)])
-def test_halo_dgrad_with_fused_bn_relu_backward_reduce(B, H, W, C):
+@pytest.mark.parametrize("halo_mode", [True, "single"], indirect=True)
+@pytest.mark.parametrize("B,H,W,C", [(2, 21, 16, 128), (3, 9, 64, 64), (2, 17, 8, 512), (1, 16, 8, 256)])
+def test_halo_dgrad_with_fused_bn_relu_backward_reduce(B, H, W, C, halo_mode):
     """dgrad epilogue fusion: ReLU gate + (dbeta, dgamma) reduction == separate mode-0 pass."""
     from texttoaudiogrounding_b200 import ops
     dy = _bf(torch.randn(B, H, W, C, generator=g(30))).cuda().bfloat16()

@@ -9,12 +9,11 @@
 // = consecutive image rows).  A traffic drops from 144 KB to 54 KB per tile and slab; the weight
 // tiles stream through their own ring.  Same warp roles / TMEM double buffering / epilogue as
 // conv_tc_fwd_kernel.
-#include "tc_common.cuh"
+#include "halo_epilogue.cuh"
 #include <cstdlib>
 
 namespace {
 
-constexpr int TILE_H = 16, TILE_W = 8;
 constexpr int A_SUB_BYTES = (TILE_H + 2) * TILE_W * 128;      // 18432
 
 // TPS = taps per weight stage: for narrow tiles (BLOCK_N <= 128) the three vertical taps of one
@@ -202,170 +201,9 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-        // ===================== epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., column half w/4
-        int it = 0;
-        int cur_n_tile = -1;
-        constexpr int CPW = BLOCK_N / 64;            // 32-column chunks per warp
-        // Per-channel statistics: a thread owns one pixel row of the tile (its TMEM lane) and 32 columns per chunk.
-        // Reducing over the 32 rows of every tile costs a 31-shuffle butterfly per chunk and quantity — that, not the
-        // MMAs, paced the narrow layers.  Instead the butterfly is cut after STAGES stages (none for BLOCK_N = 64) and
-        // the partial sums (64 registers in total) keep accumulating across tiles; the remaining stages run once per
-        // flush.  The lane -> column mapping of a butterfly stage is fixed, so accumulating in between is exact.
-        constexpr int STAGES = CPW == 1 ? 0 : (CPW == 2 ? 1 : 2);
-        constexpr int KEEP = 32 >> STAGES;
-        float run_s[CPW][KEEP], run_q[CPW][KEEP];
-#pragma unroll
-        for (int i = 0; i < CPW; ++i)
-#pragma unroll
-            for (int k = 0; k < KEEP; ++k) { run_s[i][k] = 0.f; run_q[i][k] = 0.f; }
-        auto flush_stats = [&](int n_tile) {
-            float fs[CPW], fq[CPW];
-#pragma unroll
-            for (int i = 0; i < CPW; ++i) {
-                fs[i] = warp_transpose_tail<KEEP>(run_s[i], lane);
-                fq[i] = warp_transpose_tail<KEEP>(run_q[i], lane);
-#pragma unroll
-                for (int k = 0; k < KEEP; ++k) { run_s[i][k] = 0.f; run_q[i][k] = 0.f; }
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-#pragma unroll
-            for (int i = 0; i < CPW; ++i) {
-                t_buf[warp * BLOCK_N + i * 32 + lane] = fs[i];
-                t_buf[warp * BLOCK_N + BLOCK_N / 2 + i * 32 + lane] = fq[i];
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int i = threadIdx.x; i < BLOCK_N; i += 256) {
-                const int ch = i / (BLOCK_N / 2), local = i % (BLOCK_N / 2);
-                double ds = 0.0, dq = 0.0;
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    ds += t_buf[(ch * 4 + q4) * BLOCK_N + local];
-                    dq += t_buf[(ch * 4 + q4) * BLOCK_N + BLOCK_N / 2 + local];
-                }
-                atomicAdd(stats + n_tile * BLOCK_N + i, ds);
-                atomicAdd(stats + Cout + n_tile * BLOCK_N + i, dq);
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-        };
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            int n_tile, b, h0, w0;
-            decode(tile, n_tile, b, h0, w0);
-            if (stats != nullptr && cur_n_tile >= 0 && n_tile != cur_n_tile) flush_stats(cur_n_tile);
-            cur_n_tile = n_tile;
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            const int lq = warp & 3, chalf = warp >> 2;
-            const int row = lq * 32 + lane;
-            const int h = h0 + (row >> 3), w = w0 + (row & 7);
-            const bool valid = h < H;
-            const bool edge_tile = h0 + TILE_H > H;          // tile-uniform: some rows fall off the image
-            TO* yrow = y + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N;
-            // fused BN backward: the BN input of this row is prefetched one chunk ahead (the first chunk
-            // before waiting for the accumulator)
-            const bf16* yin_row = bn_y != nullptr ? bn_y + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N : nullptr;
-            uint4 ynext[4];
-            auto fetch_y = [&](int cc_) {
-                const bf16* p = yin_row + (chalf * CPW + cc_) * 32;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) ynext[j] = (valid && cc_ < CPW) ? ld16(p + 8 * j) : make_uint4(0u, 0u, 0u, 0u);
-            };
-            if (bn_y != nullptr) fetch_y(0);
-            mbar_wait(tmem_full + 8 * acc, acc_phase);
-            tc_fence_after();
-#pragma unroll
-            for (int cc = 0; cc < CPW; ++cc) {
-                const int c = chalf * CPW + cc;
-                uint32_t r[32];
-                if (!(dbg & 2)) {
-                    tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + acc * BLOCK_N + c * 32, r);
-                    tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = 0;
-                }
-                if (cc == CPW - 1) {                     // accumulator drained: hand it back to the MMA warp now
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
-                }
-                float v[32];                             // the values as stored (rounded to TO, gated)
-                float q[32];                             // second statistic's factor: v (plain) or xhat (fused BN bwd)
-                const bool fused = bn_y != nullptr;
-                if (fused) {
-                    // fused "ReLU + BatchNorm backward, reduce pass": this kernel is the dgrad producing
-                    // d(relu(bn(y))); gate it with the ReLU mask recomputed from y and accumulate
-                    // dbeta = sum g and dgamma = sum g * xhat instead of the plain statistics
-                    const int cbase = n_tile * BLOCK_N + c * 32;
-                    uint4 yraw[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) yraw[j] = ynext[j];
-                    fetch_y(cc + 1);
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        float yv[4];
-                        unpack4<bf16>(yraw[j4 >> 1], j4 & 1, yv);
-                        const float4 sc = *reinterpret_cast<const float4*>(s_bnp + cbase + j4 * 4);
-                        const float4 sh = *reinterpret_cast<const float4*>(s_bnp + 512 + cbase + j4 * 4);
-                        const float4 xs = *reinterpret_cast<const float4*>(s_bnp + 1024 + cbase + j4 * 4);
-                        const float4 xo = *reinterpret_cast<const float4*>(s_bnp + 1536 + cbase + j4 * 4);
-                        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-                        const float xsv[4] = {xs.x, xs.y, xs.z, xs.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int j = j4 * 4 + e;
-                            const bool on = fmaf(yv[e], scv[e], shv[e]) > 0.f;
-                            r[j] = on ? r[j] : 0u;
-                            q[j] = fmaf(yv[e], xsv[e], xov[e]);
-                        }
-                    }
-                }
-                // round + pack first (one F2FP per pair), recover the rounded floats from the packed words
-                uint4 packed[sizeof(TO) == 2 ? 4 : 8];
-                if (sizeof(TO) == 2) {
-                    uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
-                        const uint32_t u = *reinterpret_cast<const uint32_t*>(&h2);
-                        pw[j >> 1] = u;
-                        v[j] = __uint_as_float(u << 16);
-                        v[j + 1] = __uint_as_float(u & 0xFFFF0000u);
-                    }
-                } else {
-                    uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { pw[j] = r[j]; v[j] = __uint_as_float(r[j]); }
-                }
-                if (stats != nullptr) {
-                    if (STAGES == 0) {
-                        if (valid) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                run_s[cc][j] += v[j];
-                                run_q[cc][j] = fmaf(v[j], fused ? q[j] : v[j], run_q[cc][j]);
-                            }
-                        }
-                    } else {
-                        if (edge_tile) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] : 0.f;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) q[j] = v[j] * (fused ? q[j] : v[j]);
-                        warp_transpose_head<STAGES>(v, lane);
-                        warp_transpose_head<STAGES>(q, lane);
-#pragma unroll
-                        for (int k = 0; k < KEEP; ++k) { run_s[cc][k] += v[k]; run_q[cc][k] += q[k]; }
-                    }
-                }
-                if (valid && !(dbg & 1)) {
-#pragma unroll
-                    for (int j = 0; j < (sizeof(TO) == 2 ? 4 : 8); ++j)
-                        st16(reinterpret_cast<uint8_t*>(yrow + c * 32) + 16 * j, packed[j]);
-                }
-            }
-        }
-        if (stats != nullptr && cur_n_tile >= 0) flush_stats(cur_n_tile);
+        halo_epilogue<BLOCK_N, TO>(tmem_base, tmem_full, t_buf, s_bnp, y, stats, B, H, W, Cout, bn_y, dbg,
+                                   (int)blockIdx.x, (int)gridDim.x, total_tiles, decode,
+                                   [&](int acc) { mbar_arrive(tmem_empty + 8 * acc); });
     }
     tc_fence_before();
     __syncthreads();
@@ -473,6 +311,20 @@ extern "C" int tag_weight_prep_tapmajor_x3(const float* w, void* out, int Co, in
     return TAG_OK;
 }
 
+int tag_halo2_dispatch(const CUtensorMap& tx, const CUtensorMap& tw, void* y, int y_dtype, double* stats, int B, int H,
+                       int W, int Cin, int Cout, int block_n, const void* bn_y, const float* const* bnp,
+                       cudaStream_t stream);                 // conv_tc_halo2.cu
+
+namespace {
+int g_pair_mode = getenv("TAG_B200_NO_PAIR") ? 0 : 1;
+}
+
+// 0: every layer on the one-CTA-per-tile kernel; 1 (default): CTA pairs (cta_group::2) where the weights stream
+extern "C" int tag_conv_halo_set_pair_mode(int mode) {
+    g_pair_mode = mode;
+    return TAG_OK;
+}
+
 // 3x3 only, no bias / ReLU.  x: bf16 NHWC, W a multiple of 8; w: bf16 TAP-MAJOR [9][Cout][Cin]
 // (tag_weight_prep_tapmajor_bf16); y bf16 or fp32.
 extern "C" int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, double* stats, int B,
@@ -483,15 +335,21 @@ extern "C" int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y
     if (bn_y != nullptr && (Cout > 512 || stats == nullptr)) return TAG_ERR_BAD_ARG;
     const float* bnp[4] = {bn_scale, bn_shift, bn_mean, bn_invstd};
     const int block_n = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    const bool wres = Cin == 64 && Cout == block_n && block_n <= 128;
     CUtensorMap tx, tw;
     int rc = make_act_tmap(&tx, x, B, H, W, Cin, TILE_W, TILE_H + 2);
     if (rc != TAG_OK) return rc;
+    if (g_pair_mode != 0 && !wres) {
+        // weights stream (Cin >= 128): CTA pairs with cta_group::2 MMAs, each CTA loads half of every weight tile
+        rc = make_w3_tmap(&tw, w, Cout, Cin, block_n / 2, block_n == 256 ? 1 : 3);
+        if (rc != TAG_OK) return rc;
+        return tag_halo2_dispatch(tx, tw, y, y_dtype, stats, B, H, W, Cin, Cout, block_n, bn_y, bnp, stream);
+    }
     rc = make_w3_tmap(&tw, w, Cout, Cin, block_n, block_n == 256 ? 1 : 3);
     if (rc != TAG_OK) return rc;
 #define TAG_HALO(BN_, WR_)                                                                               \
     (y_dtype == TAG_DTYPE_BF16 ? launch_halo<BN_, bf16, WR_>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, bnp, stream)  \
                                : launch_halo<BN_, float, WR_>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, bnp, stream))
-    const bool wres = Cin == 64 && Cout == block_n && block_n <= 128;
     if (block_n == 256) return TAG_HALO(256, false);
     if (block_n == 128) return wres ? TAG_HALO(128, true) : TAG_HALO(128, false);
     return wres ? TAG_HALO(64, true) : TAG_HALO(64, false);

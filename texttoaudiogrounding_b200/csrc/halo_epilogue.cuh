@@ -1,0 +1,187 @@
+// Epilogue of the halo convolution kernels (conv_tc_halo.cu: one CTA per tile; conv_tc_halo2.cu: a CTA pair per
+// 256-pixel tile with cta_group::2 MMAs): 8 warps drain the fp32 accumulator of one 128-pixel x BLOCK_N tile from
+// TMEM, apply the optional fused "ReLU gate + BatchNorm backward reductions" (bn_y != nullptr), round to the storage
+// type, accumulate per-channel statistics in registers across tiles and store the tile.
+//   decode(tile, n_tile, b, h0, w0): tile -> output-channel tile, image, tile origin (b == B marks a padding tile)
+//   arrive_empty(acc): hand accumulator `acc` back to the MMA issuer (a local or a remote mbarrier arrive)
+#pragma once
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TILE_H = 16, TILE_W = 8;
+
+template <int BLOCK_N, typename TO, typename Decode, typename ArriveEmpty>
+__device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_full, float* t_buf, const float* s_bnp,
+                                              TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W,
+                                              int Cout, const bf16* __restrict__ bn_y, int dbg, int first_tile,
+                                              int tile_stride, int total_tiles, Decode decode,
+                                              ArriveEmpty arrive_empty) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ===================== epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., column half w/4
+    int it = 0;
+    int cur_n_tile = -1;
+    constexpr int CPW = BLOCK_N / 64;            // 32-column chunks per warp
+    // Per-channel statistics: a thread owns one pixel row of the tile (its TMEM lane) and 32 columns per chunk.
+    // Reducing over the 32 rows of every tile costs a 31-shuffle butterfly per chunk and quantity — that, not the
+    // MMAs, paced the narrow layers.  Instead the butterfly is cut after STAGES stages (none for BLOCK_N = 64) and
+    // the partial sums (64 registers in total) keep accumulating across tiles; the remaining stages run once per
+    // flush.  The lane -> column mapping of a butterfly stage is fixed, so accumulating in between is exact.
+    constexpr int STAGES = CPW == 1 ? 0 : (CPW == 2 ? 1 : 2);
+    constexpr int KEEP = 32 >> STAGES;
+    float run_s[CPW][KEEP], run_q[CPW][KEEP];
+#pragma unroll
+    for (int i = 0; i < CPW; ++i)
+#pragma unroll
+        for (int k = 0; k < KEEP; ++k) { run_s[i][k] = 0.f; run_q[i][k] = 0.f; }
+    auto flush_stats = [&](int n_tile) {
+        float fs[CPW], fq[CPW];
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) {
+            fs[i] = warp_transpose_tail<KEEP>(run_s[i], lane);
+            fq[i] = warp_transpose_tail<KEEP>(run_q[i], lane);
+#pragma unroll
+            for (int k = 0; k < KEEP; ++k) { run_s[i][k] = 0.f; run_q[i][k] = 0.f; }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) {
+            t_buf[warp * BLOCK_N + i * 32 + lane] = fs[i];
+            t_buf[warp * BLOCK_N + BLOCK_N / 2 + i * 32 + lane] = fq[i];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = threadIdx.x; i < BLOCK_N; i += 256) {
+            const int ch = i / (BLOCK_N / 2), local = i % (BLOCK_N / 2);
+            double ds = 0.0, dq = 0.0;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                ds += t_buf[(ch * 4 + q4) * BLOCK_N + local];
+                dq += t_buf[(ch * 4 + q4) * BLOCK_N + BLOCK_N / 2 + local];
+            }
+            atomicAdd(stats + n_tile * BLOCK_N + i, ds);
+            atomicAdd(stats + Cout + n_tile * BLOCK_N + i, dq);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
+        int n_tile, b, h0, w0;
+        decode(tile, n_tile, b, h0, w0);
+        if (stats != nullptr && cur_n_tile >= 0 && n_tile != cur_n_tile) flush_stats(cur_n_tile);
+        cur_n_tile = n_tile;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int lq = warp & 3, chalf = warp >> 2;
+        const int row = lq * 32 + lane;
+        const int h = h0 + (row >> 3), w = w0 + (row & 7);
+        const bool valid = h < H && b < B;
+        const bool edge_tile = h0 + TILE_H > H || b >= B;   // tile-uniform: some rows fall off the image
+        TO* yrow = y + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N;
+        // fused BN backward: the BN input of this row is prefetched one chunk ahead (the first chunk
+        // before waiting for the accumulator)
+        const bf16* yin_row = bn_y != nullptr ? bn_y + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N : nullptr;
+        uint4 ynext[4];
+        auto fetch_y = [&](int cc_) {
+            const bf16* p = yin_row + (chalf * CPW + cc_) * 32;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ynext[j] = (valid && cc_ < CPW) ? ld16(p + 8 * j) : make_uint4(0u, 0u, 0u, 0u);
+        };
+        if (bn_y != nullptr) fetch_y(0);
+        mbar_wait(tmem_full + 8 * acc, acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < CPW; ++cc) {
+            const int c = chalf * CPW + cc;
+            uint32_t r[32];
+            if (!(dbg & 2)) {
+                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + acc * BLOCK_N + c * 32, r);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0;
+            }
+            if (cc == CPW - 1) {                     // accumulator drained: hand it back to the MMA warp now
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive_empty(acc);
+            }
+            float v[32];                             // the values as stored (rounded to TO, gated)
+            float q[32];                             // second statistic's factor: v (plain) or xhat (fused BN bwd)
+            const bool fused = bn_y != nullptr;
+            if (fused) {
+                // fused "ReLU + BatchNorm backward, reduce pass": this kernel is the dgrad producing
+                // d(relu(bn(y))); gate it with the ReLU mask recomputed from y and accumulate
+                // dbeta = sum g and dgamma = sum g * xhat instead of the plain statistics
+                const int cbase = n_tile * BLOCK_N + c * 32;
+                uint4 yraw[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) yraw[j] = ynext[j];
+                fetch_y(cc + 1);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float yv[4];
+                    unpack4<bf16>(yraw[j4 >> 1], j4 & 1, yv);
+                    const float4 sc = *reinterpret_cast<const float4*>(s_bnp + cbase + j4 * 4);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_bnp + 512 + cbase + j4 * 4);
+                    const float4 xs = *reinterpret_cast<const float4*>(s_bnp + 1024 + cbase + j4 * 4);
+                    const float4 xo = *reinterpret_cast<const float4*>(s_bnp + 1536 + cbase + j4 * 4);
+                    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                    const float xsv[4] = {xs.x, xs.y, xs.z, xs.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = j4 * 4 + e;
+                        const bool on = fmaf(yv[e], scv[e], shv[e]) > 0.f;
+                        r[j] = on ? r[j] : 0u;
+                        q[j] = fmaf(yv[e], xsv[e], xov[e]);
+                    }
+                }
+            }
+            // round + pack first (one F2FP per pair), recover the rounded floats from the packed words
+            uint4 packed[sizeof(TO) == 2 ? 4 : 8];
+            if (sizeof(TO) == 2) {
+                uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+                    const uint32_t u = *reinterpret_cast<const uint32_t*>(&h2);
+                    pw[j >> 1] = u;
+                    v[j] = __uint_as_float(u << 16);
+                    v[j + 1] = __uint_as_float(u & 0xFFFF0000u);
+                }
+            } else {
+                uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { pw[j] = r[j]; v[j] = __uint_as_float(r[j]); }
+            }
+            if (stats != nullptr) {
+                if (STAGES == 0) {
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            run_s[cc][j] += v[j];
+                            run_q[cc][j] = fmaf(v[j], fused ? q[j] : v[j], run_q[cc][j]);
+                        }
+                    }
+                } else {
+                    if (edge_tile) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) q[j] = v[j] * (fused ? q[j] : v[j]);
+                    warp_transpose_head<STAGES>(v, lane);
+                    warp_transpose_head<STAGES>(q, lane);
+#pragma unroll
+                    for (int k = 0; k < KEEP; ++k) { run_s[cc][k] += v[k]; run_q[cc][k] += q[k]; }
+                }
+            }
+            if (valid && !(dbg & 1)) {
+#pragma unroll
+                for (int j = 0; j < (sizeof(TO) == 2 ? 4 : 8); ++j)
+                    st16(reinterpret_cast<uint8_t*>(yrow + c * 32) + 16 * j, packed[j]);
+            }
+        }
+    }
+    if (stats != nullptr && cur_n_tile >= 0) flush_stats(cur_n_tile);
+}
+
+}  // namespace
