@@ -69,6 +69,23 @@ int tag_conv_c1_fwd(const void* x, const float* w, void* y, int dtype, double* s
                     int W, cudaStream_t stream);
 int tag_conv_c1_bwd(const void* dy, const void* x, const float* w, int dtype, float* dw, float* dx,
                     int B, int H, int W, cudaStream_t stream);
+/* conv_block1.conv1 + bn1 + ReLU as ONE pass (models/panns.py:49 for Cin = 1, audio_encoder.py:202): the BatchNorm batch
+ * statistics of a Cin = 1 convolution follow from 54 second-order moments of its 16 MB input (mom: double[54], written
+ * here), so the raw convolution output is never stored:
+ *   tag_c1_moments -> tag_c1_stats_from_moments (stats: double[128] = sum y | sum y^2, the tag_bn_finalize input)
+ *   -> tag_bn_finalize -> tag_conv_c1_fwd_act (y = relu(scale * conv(x, w) + shift)).
+ * Backward: tag_bn_act_domain_params(gamma, beta) gives the (scale, shift, mean, invstd) quadruple [4][C] with which the
+ * fused reduce of tag_conv_tc_fwd_halo reads the saved ACTIVATION as its bn_y; tag_conv_c1_bwd_bn then takes the gated
+ * gradient g, recomputes conv(x, w), applies the BatchNorm backward (red = the fused reduce's double[128]) and produces
+ * dw / dx — autograd of conv2d + batch_norm + relu without the intermediate tensors. */
+int tag_c1_moments(const void* x, int dtype, int B, int H, int W, double* mom, cudaStream_t stream);
+int tag_c1_stats_from_moments(const double* mom, const float* w, double* stats, cudaStream_t stream);
+int tag_conv_c1_fwd_act(const void* x, const float* w, const float* scale, const float* shift, void* y, int dtype,
+                        int B, int H, int W, cudaStream_t stream);
+int tag_bn_act_domain_params(const float* gamma, const float* beta, int C, float* out, cudaStream_t stream);
+int tag_conv_c1_bwd_bn(const void* g, const void* x, const float* w, const float* scale, const float* shift,
+                       const float* mean, const float* invstd, const double* red, int bn_training, float* dw, float* dx, int B,
+                       int H, int W, cudaStream_t stream);
 int tag_conv_fwd(const void* x, int x_dtype, const float* w, void* y, int y_dtype, const float* bias,
                  int relu, double* stats, int B, int H, int W, int Cin, int Cout, int taps,
                  cudaStream_t stream);

@@ -172,6 +172,67 @@ def test_conv_c1_bwd_bf16_mma(B, H):
     assert rel_err(dx.cpu().reshape(B, 1, H, W), x.grad) < 1e-4
 
 
+@pytest.mark.parametrize("B,H", [(2, 11), (3, 37), (1, 16)])
+def test_c1_one_pass_layer_statistics_forward_and_backward(B, H):
+    """conv_block1.conv1 + bn1 + relu without the raw convolution output in HBM (Cin = 1):
+    statistics from the 54 input moments == statistics of the convolution output; the one-pass forward ==
+    relu(bn(conv)); the fused backward (g gated by the ReLU, BN backward applied on the recomputed conv output) ==
+    autograd of conv2d -> batch_norm -> relu, in train and eval BatchNorm mode."""
+    ops = _ops()
+    W, C = 64, 64
+    bf = torch.bfloat16
+    x = torch.randn(B, 1, H, W, generator=g(41)).to(bf).float()
+    w = torch.randn(C, 1, 3, 3, generator=g(42)) * 0.3
+    gamma = torch.rand(C, generator=g(43)) + 0.5
+    gamma[3] = -gamma[3]                                        # a negative scale
+    beta = torch.randn(C, generator=g(44)) * 0.3
+    xd = x.reshape(B, H, W).cuda().to(bf)
+    wd = w.reshape(C, 9).cuda()
+    # ---- statistics from moments
+    mom = torch.empty(54, device="cuda", dtype=torch.float64)
+    ops.call("tag_c1_moments", xd, 1, B, H, W, mom)
+    stats = torch.empty(2 * C, device="cuda", dtype=torch.float64)
+    ops.call("tag_c1_stats_from_moments", mom, wd, stats)
+    y = F.conv2d(x.double(), w.double(), padding=1)
+    np.testing.assert_allclose(stats[:C].cpu().numpy(), y.sum((0, 2, 3)).numpy(), rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(stats[C:].cpu().numpy(), y.pow(2).sum((0, 2, 3)).numpy(), rtol=1e-5)
+    for training in (True, False):
+        xr = x.clone().requires_grad_(True)
+        wr = w.clone().requires_grad_(True)
+        yr = F.conv2d(xr, wr, padding=1)
+        rm, rv = torch.randn(C, generator=g(45)) * 0.2, torch.rand(C, generator=g(46)) + 0.5
+        if training:
+            mean, var = yr.detach().mean((0, 2, 3)), yr.detach().var((0, 2, 3), unbiased=False)
+        else:
+            mean, var = rm, rv
+        invstd = (var + 1e-5).rsqrt()
+        a = F.relu(F.batch_norm(yr, None if training else rm, None if training else rv, gamma, beta, training, 0.1, 1e-5))
+        da = torch.randn(a.shape, generator=g(47)).to(bf).float()
+        a.backward(da)
+        scale, shift = gamma * invstd, beta - mean * gamma * invstd
+        # ---- forward
+        ad = torch.empty(B, H, W, C, device="cuda", dtype=bf)
+        ops.call("tag_conv_c1_fwd_act", xd, wd, scale.cuda(), shift.cuda(), ad, 1, B, H, W)
+        assert rel_err(ad.float().cpu().permute(0, 3, 1, 2), a.detach()) < 4e-3
+        # ---- backward: the gated gradient and the two reductions as the fused dgrad epilogue delivers them
+        gate = (a.detach() > 0).float()
+        gg = (da * gate)
+        xhat = (yr.detach() - mean.view(1, C, 1, 1)) * invstd.view(1, C, 1, 1)
+        red = torch.cat([gg.double().sum((0, 2, 3)), (gg * xhat).double().sum((0, 2, 3))]).cuda()
+        dw = torch.zeros(C, 9, device="cuda")
+        dx = torch.empty(B, H, W, device="cuda")
+        ops.call("tag_conv_c1_bwd_bn", gg.permute(0, 2, 3, 1).contiguous().cuda().to(bf), xd, wd, scale.cuda(),
+                 shift.cuda(), mean.cuda(), invstd.cuda(), red, int(training), dw, dx, B, H, W)
+        # dy1 is rounded to bf16 before the two products (as the unfused path stores it)
+        assert rel_err(dw.cpu().reshape(C, 1, 3, 3), wr.grad) < 6e-3, training
+        assert rel_err(dx.cpu().reshape(B, 1, H, W), xr.grad) < 6e-3, training
+    # ---- activation-domain BatchNorm parameters: gate a > 0, xhat = (a - beta) / gamma
+    out = torch.empty(4, C, device="cuda")
+    ops.call("tag_bn_act_domain_params", gamma.cuda(), beta.cuda(), C, out)
+    assert torch.equal(out[0].cpu(), torch.ones(C)) and torch.equal(out[1].cpu(), torch.zeros(C))
+    assert torch.equal(out[2].cpu(), beta) and torch.allclose(out[3].cpu(), 1.0 / gamma, rtol=1e-6)
+
+
 @pytest.mark.parametrize("ph,pw,H", [(2, 2, 9), (1, 2, 6), (2, 2, 8)])
 def test_bn_relu_pool_fwd_bwd_matches_torch_autograd(ph, pw, H):
     ops = _ops()

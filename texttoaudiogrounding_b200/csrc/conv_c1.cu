@@ -30,10 +30,13 @@ __device__ __forceinline__ void load_x_tile(float (*xs)[XS_W], const T* x, int b
     }
 }
 
-template <typename T>
+// ACT: the BatchNorm scale / shift of the layer are already known (statistics from tag_c1_moments, or running statistics
+// in eval mode) and the kernel writes relu(scale * conv + shift) directly: the raw convolution output never exists in HBM.
+template <typename T, bool ACT>
 __global__ void __launch_bounds__(256)
 conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
-                   double* __restrict__ stats, int B, int H, int W) {
+                   double* __restrict__ stats, int B, int H, int W, const float* __restrict__ bn_scale,
+                   const float* __restrict__ bn_shift) {
     __shared__ float xs[TH + 2][XS_W];
     __shared__ float s_sum[CO], s_sq[CO];
     const int tiles_h = (H + TH - 1) / TH;
@@ -44,9 +47,13 @@ conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __re
     for (int c = 0; c < 8; ++c)
 #pragma unroll
         for (int t = 0; t < 9; ++t) wr[c][t] = __ldg(w + (cg * 8 + c) * 9 + t);
-    float cs[8], cq[8];
+    float cs[8], cq[8], bsc[8], bsh[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { cs[c] = 0.f; cq[c] = 0.f; }
+    for (int c = 0; c < 8; ++c) {
+        cs[c] = 0.f; cq[c] = 0.f;
+        bsc[c] = ACT ? __ldg(bn_scale + cg * 8 + c) : 1.f;
+        bsh[c] = ACT ? __ldg(bn_shift + cg * 8 + c) : 0.f;
+    }
     // persistent over tiles: the per-channel statistics stay in registers and are flushed ONCE per CTA (one
     // flush per tile meant ~1 M double atomics on 8 cache lines, which serialise in L2)
     // the halo tile of the NEXT tile is fetched into registers before this tile's arithmetic and committed to shared
@@ -95,15 +102,15 @@ conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __re
             float a = 0.f;
 #pragma unroll
             for (int t = 0; t < 9; ++t) a = fmaf(xn[t], wr[c][t], a);
+            if (ACT) a = fmaxf(fmaf(a, bsc[c], bsh[c]), 0.f);
             a = round_to<T>(a);
             o[c] = a;
-            cs[c] += a;
-            cq[c] += a * a;
+            if (!ACT) { cs[c] += a; cq[c] += a * a; }
         }
         store8<T>(y + (((long)b * H + h) * W + c0) * CO + cg * 8, o);
     }
     }
-    if (stats != nullptr) {
+    if (!ACT && stats != nullptr) {
         // lanes with equal (lane & 7) share the channel group: reduce over lane bits 3,4
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -267,6 +274,7 @@ constexpr int MROWS = MTH + 2;
 constexpr int MNST = 3;                       // cp.async stages per warp
 constexpr int MXS_W = 68;                     // bf16 halo row: 66 used
 constexpr int MMA_SMEM = 8 * MNST * 2048 + MROWS * 64 * 9 * 4 + MROWS * MXS_W * 2 + CO * 9 * 4;
+constexpr int MMA_SMEM_FUSE = 8 * MNST * 2048 + MROWS * 64 * 9 * 4 + (MROWS + 2) * MXS_W * 2 + CO * 9 * 4 + 8 * CO * 4;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -288,20 +296,68 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(256, 2)
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+}
+
+// FUSE_BN: `dy` is g = d(relu(bn1(y))) already gated by the ReLU mask (the fused epilogue of the conv2 dgrad), and the
+// kernel applies the BatchNorm backward itself before the two products:
+//     dy1 = A[c] * g + Bc[c] * y + C[c],   y = conv(x, w) RECOMPUTED here (one more thin MMA: 16 pixels x 9 taps x 64),
+//     A = gamma * invstd,  Bc = -A * dgamma_mean * invstd,  C = -A * dbeta_mean + A * dgamma_mean * mean * invstd
+// (tag_bn_relu_pool_bwd mode 1), so neither the raw convolution output nor dy1 ever exists in HBM.  The transform runs on
+// the A fragments in registers (the accumulator layout of y = the A layout of g); the wgrad B fragments are their 8x8
+// transposes (movmatrix) instead of ldmatrix.trans of the untransformed shared-memory unit.
+template <bool FUSE_BN>
+__global__ void __launch_bounds__(256, FUSE_BN ? 1 : 2)
 conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ w,
-                       float* __restrict__ dw, float* __restrict__ dx, int B, int H) {
+                       float* __restrict__ dw, float* __restrict__ dx, int B, int H,
+                       const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                       const float* __restrict__ bn_mean, const float* __restrict__ bn_invstd,
+                       const double* __restrict__ bn_red, float inv_count, int bn_training) {
+    constexpr int XOFF = FUSE_BN ? 2 : 1;                 // the recomputation needs one more halo row of x each side
+    constexpr int XROWS = MROWS + 2 * (XOFF - 1);
     extern __shared__ __align__(128) uint8_t msm[];
     uint8_t* stage = msm;                                                     // [8 warps][MNST][2048]
     float* S = reinterpret_cast<float*>(msm + 8 * MNST * 2048);               // [MROWS][64][9]
-    uint16_t* xs = reinterpret_cast<uint16_t*>(S + MROWS * 64 * 9);           // [MROWS][MXS_W] bf16 bits
-    float* s_dw = reinterpret_cast<float*>(xs + MROWS * MXS_W);               // [64][9]
+    uint16_t* xs = reinterpret_cast<uint16_t*>(S + MROWS * 64 * 9);           // [XROWS][MXS_W] bf16 bits
+    float* s_dw = reinterpret_cast<float*>(xs + XROWS * MXS_W);               // [64][9]
+    float* s_bn = s_dw + CO * 9;                                              // FUSE_BN: [8][64] per-channel constants
     const int tiles_h = (H + MTH - 1) / MTH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     constexpr int W = TW;
 
     for (int i = threadIdx.x; i < CO * 9; i += 256) s_dw[i] = 0.f;
+    uint32_t wyh[8][2], wyl[8][2];                        // FUSE_BN: B fragments of y = xcol * w^T (k = tap, n = channel)
+    if (FUSE_BN) {
+        if (threadIdx.x < CO) {
+            const int c = threadIdx.x;
+            const float sc = bn_scale[c], mu = bn_mean[c], is = bn_invstd[c];
+            const float dbe = bn_training ? (float)bn_red[c] * inv_count : 0.f;
+            const float dga = bn_training ? (float)bn_red[CO + c] * inv_count : 0.f;
+            const float sh = bn_shift[c];
+            s_bn[c] = sc;                                     // forward affine: a = relu(sc * y + sh)
+            s_bn[CO + c] = sh;
+            s_bn[2 * CO + c] = sc != 0.f ? is / sc : 0.f;     // 1 / gamma
+            s_bn[3 * CO + c] = sh + mu * sc;                  // beta
+            s_bn[4 * CO + c] = is;                            // xhat = is * y - mu * is
+            s_bn[5 * CO + c] = -mu * is;
+            s_bn[6 * CO + c] = sc * dbe;                      // dy1 = sc * g - sc * dbe - sc * dga * xhat
+            s_bn[7 * CO + c] = sc * dga;
+        }
+        auto lo_y = [](float v) { return v - __bfloat162float(__float2bfloat16_rn(v)); };
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const float* wc = w + (n * 8 + g) * 9;
+            const float w0 = wc[2 * t], w1 = wc[2 * t + 1], w8 = wc[8];
+            wyh[n][0] = pack2(w0, w1);
+            wyl[n][0] = pack2(lo_y(w0), lo_y(w1));
+            wyh[n][1] = t == 0 ? pack2(w8, 0.f) : 0u;
+            wyl[n][1] = t == 0 ? pack2(lo_y(w8), 0.f) : 0u;
+        }
+    }
     // B fragments of the dgrad product: w[co][tap], k = co, n = tap (second n-tile: tap 8 only).  The fp32 weights
     // enter as bf16 hi + lo pairs (two MMAs): a once-rounded weight is a SYSTEMATIC error that does not average out
     // over the 4 M pixels summed into the bn0 gradients (dgamma0 / dbeta0 cancel heavily: bn1 removes scale and shift)
@@ -330,9 +386,9 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
     for (int tile = blockIdx.x; tile < B * tiles_h; tile += gridDim.x) {
     const int b = tile / tiles_h, h0 = (tile % tiles_h) * MTH;
     __syncthreads();                                      // previous tile's dx phase is done with S / xs
-    for (int i = threadIdx.x; i < MROWS * MXS_W; i += 256) {
+    for (int i = threadIdx.x; i < XROWS * MXS_W; i += 256) {
         const int r = i / MXS_W, c = i - r * MXS_W;
-        const int h = h0 - 1 + r, wc = c - 1;
+        const int h = h0 - XOFF + r, wc = c - 1;
         uint16_t v = 0;
         if (c < 66 && h >= 0 && h < H && wc >= 0 && wc < W)
             v = reinterpret_cast<const uint16_t*>(x)[((long)b * H + h) * W + wc];
@@ -384,8 +440,64 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
         }
         const uint32_t sbase = my_stage + (i % MNST) * 2048 + lrow * 128;
         uint32_t a[4][4];
+        uint32_t alo[FUSE_BN ? 4 : 1][4];                 // FUSE_BN: low halves of dy1 (see below)
 #pragma unroll
         for (int q = 0; q < 4; ++q) ldsm_x4(a[q], sbase + (((2 * q + lchk) ^ (lrow & 7)) << 4));
+        if (FUSE_BN) {
+            // y[16 pixels][64] = xcol[16][9 -> 16] * w^T: A rows = the unit's pixels, k = taps (x from the halo tile)
+            uint32_t ay[4];
+            {
+                auto xat = [&](int m, int tap) -> uint32_t {
+                    return xs[(r + tap / 3 - 2 + XOFF) * MXS_W + c0 + m + tap % 3];
+                };
+                ay[0] = xat(g, 2 * t) | (xat(g, 2 * t + 1) << 16);
+                ay[1] = xat(g + 8, 2 * t) | (xat(g + 8, 2 * t + 1) << 16);
+                ay[2] = t == 0 ? xat(g, 8) : 0u;
+                ay[3] = t == 0 ? xat(g + 8, 8) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int n = 2 * q + hf;
+                    float yv[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma16816(yv, ay, wyh[n][0], wyh[n][1]);
+                    mma16816(yv, ay, wyl[n][0], wyl[n][1]);
+                    const int ch = 16 * q + 8 * hf + 2 * t;
+                    float2 cst[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) cst[i] = *reinterpret_cast<const float2*>(s_bn + i * CO + ch);
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {                 // rr = 0: pixel g, rr = 1: pixel g + 8
+                        const uint32_t u = a[q][2 * hf + rr];
+                        const float gv[2] = {__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u)};
+                        float dv[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float yy = yv[2 * rr + e];
+                            const float sc = e ? cst[0].y : cst[0].x, sh = e ? cst[1].y : cst[1].x;
+                            const float ig = e ? cst[2].y : cst[2].x, be = e ? cst[3].y : cst[3].x;
+                            const float xs_ = e ? cst[4].y : cst[4].x, xo_ = e ? cst[5].y : cst[5].x;
+                            const float am = e ? cst[6].y : cst[6].x, ax_ = e ? cst[7].y : cst[7].x;
+                            // Where the ReLU gate is open the fused reduce of the conv2 dgrad saw xhat through the SAVED
+                            // activation, (bf16(a) - beta) / gamma; the apply must use that same value, or dy1 keeps a
+                            // component along xhat of size (sum g (xhat' - xhat)) / N on EVERY pixel of the channel — a
+                            // coherent error in dw (sum xhat * x is the large y-x correlation).  Gate closed: exact xhat.
+                            const float ar = round_to<bf16>(fmaxf(fmaf(yy, sc, sh), 0.f));
+                            const float xh = ar > 0.f ? (ar - be) * ig : fmaf(yy, xs_, xo_);
+                            dv[e] = fmaf(sc, gv[e], -fmaf(ax_, xh, am));
+                        }
+                        const float d0 = dv[0], d1 = dv[1];
+                        // dy1 exists in fp32 only here: the dx product takes it as bf16 hi + lo (dx feeds the bn0
+                        // gradients, sums over 4 M pixels that cancel to a few percent of their terms — a second bf16
+                        // rounding of every term is visible there); so does the (cheap) weight-gradient product
+                        const uint32_t hi = pack2(d0, d1);
+                        a[q][2 * hf + rr] = hi;
+                        alo[q][2 * hf + rr] = pack2(d0 - __uint_as_float(hi << 16), d1 - __uint_as_float(hi & 0xFFFF0000u));
+                    }
+                }
+            }
+        }
         float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -393,6 +505,10 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
             mma16816(s1, a[q], wb[q][1][0], wb[q][1][1]);
             mma16816(s0, a[q], wl[q][0][0], wl[q][0][1]);
             mma16816(s1, a[q], wl[q][1][0], wl[q][1][1]);
+            if (FUSE_BN) {
+                mma16816(s0, alo[q], wb[q][0][0], wb[q][0][1]);
+                mma16816(s1, alo[q], wb[q][1][0], wb[q][1][1]);
+            }
         }
         Srow[g * 9 + 2 * t] = s0[0];
         Srow[g * 9 + 2 * t + 1] = s0[1];
@@ -403,20 +519,31 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
             // A fragments of the wgrad product: rows = taps, k = the unit's 16 pixels; x[h + dh][c + dw] from the halo tile
             uint32_t ax[4];
             {
-                const int dh = g / 3, dwv = g - dh * 3;                       // tap g (g <= 7): xs row r - 1 + dh, col c + dwv
-                const uint16_t* xr = xs + (r - 1 + dh) * MXS_W + c0 + dwv + 2 * t;
+                const int dh = g / 3, dwv = g - dh * 3;                       // tap g (g <= 7): x row h - 1 + dh, col c + dwv
+                const uint16_t* xr = xs + (r - 2 + XOFF + dh) * MXS_W + c0 + dwv + 2 * t;
                 ax[0] = (uint32_t)xr[0] | ((uint32_t)xr[1] << 16);
                 ax[2] = (uint32_t)xr[8] | ((uint32_t)xr[9] << 16);
-                const uint16_t* x8 = xs + (r + 1) * MXS_W + c0 + 2 + 2 * t;  // tap 8 = (dh, dw) = (+1, +1)
+                const uint16_t* x8 = xs + (r + XOFF) * MXS_W + c0 + 2 + 2 * t;  // tap 8 = (dh, dw) = (+1, +1)
                 ax[1] = g == 0 ? ((uint32_t)x8[0] | ((uint32_t)x8[1] << 16)) : 0u;
                 ax[3] = g == 0 ? ((uint32_t)x8[8] | ((uint32_t)x8[9] << 16)) : 0u;
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 uint32_t bt[4];
-                ldsm_x4_trans(bt, sbase + (((2 * q + lchk) ^ (lrow & 7)) << 4));
+                if (FUSE_BN) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bt[j] = movmatrix_trans(a[q][j]);
+                } else {
+                    ldsm_x4_trans(bt, sbase + (((2 * q + lchk) ^ (lrow & 7)) << 4));
+                }
                 mma16816(acc[2 * q], ax, bt[0], bt[1]);
                 mma16816(acc[2 * q + 1], ax, bt[2], bt[3]);
+                if (FUSE_BN) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bt[j] = movmatrix_trans(alo[q][j]);
+                    mma16816(acc[2 * q], ax, bt[0], bt[1]);
+                    mma16816(acc[2 * q + 1], ax, bt[2], bt[3]);
+                }
             }
         }
         __syncwarp();
@@ -455,7 +582,167 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
     for (int i = threadIdx.x; i < CO * 9; i += 256) atomicAdd(dw + i, s_dw[i]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// BatchNorm statistics of the Cin = 1 convolution WITHOUT running it: y[p, co] = sum_k w[co][k] x[p + d_k], hence
+//   sum_p y[p, co]   = sum_k w[co][k] * M1[k],            M1[k]     = sum_p x[p + d_k]
+//   sum_p y[p, co]^2 = sum_{k,k'} w[co][k] w[co][k'] * M2[k][k'],  M2[k][k'] = sum_p x[p + d_k] x[p + d_k']
+// over all output pixels p (zero padding).  The 9 + 45 moments of the 16 MB input cost one pass over it; the layer can
+// then write relu(bn(conv)) in a single kernel (conv_c1_fwd_kernel<ACT>).  mom: [45 upper-triangular M2 | 9 M1] doubles.
+constexpr int N_MOM = 54;
+
+// W == 64 (the model's mel axis): a thread owns one column and walks MOM_ROWS rows with a rolling 3x3 window, so every
+// input element is loaded three times (coalesced 128-byte rows) instead of nine, with no index divisions.
+constexpr int MOM_ROWS = 16;
+template <typename T>
+__global__ void __launch_bounds__(256)
+c1_moments_w64_kernel(const T* __restrict__ x, int B, int H, double* __restrict__ mom) {
+    constexpr int W = 64;
+    __shared__ float s_m[N_MOM];
+    if (threadIdx.x < N_MOM) s_m[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int chunks = (H + 4 * MOM_ROWS - 1) / (4 * MOM_ROWS);
+    const int b = blockIdx.x / chunks;
+    const int h_begin = (blockIdx.x % chunks) * 4 * MOM_ROWS + (threadIdx.x >> 6) * MOM_ROWS;
+    const int wq = threadIdx.x & 63;
+    const T* xb = x + (long)b * H * W;
+    auto load_row = [&](int hh, float (&r)[3]) {
+        const bool ok = hh >= 0 && hh < H;
+        const T* p = xb + (long)hh * W + wq;
+        r[0] = (ok && wq > 0) ? to_f<T>(p[-1]) : 0.f;
+        r[1] = ok ? to_f<T>(p[0]) : 0.f;
+        r[2] = (ok && wq < W - 1) ? to_f<T>(p[1]) : 0.f;
+    };
+    float m[N_MOM];
+#pragma unroll
+    for (int i = 0; i < N_MOM; ++i) m[i] = 0.f;
+    float xn[9];
+    {
+        float r0[3], r1[3];
+        load_row(h_begin - 1, r0);
+        load_row(h_begin, r1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { xn[k] = 0.f; xn[3 + k] = r0[k]; xn[6 + k] = r1[k]; }
+    }
+#pragma unroll 2
+    for (int h = h_begin; h < h_begin + MOM_ROWS; ++h) {
+        float r2[3];
+        load_row(h + 1, r2);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { xn[k] = xn[3 + k]; xn[3 + k] = xn[6 + k]; xn[6 + k] = r2[k]; }
+        if (h < H) {
+            int idx = 0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+#pragma unroll
+                for (int k2 = k; k2 < 9; ++k2) { m[idx] = fmaf(xn[k], xn[k2], m[idx]); ++idx; }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) m[45 + k] += xn[k];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N_MOM; ++i) {
+        const float v = warp_sum(m[i]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_m[i], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < N_MOM) atomicAdd(mom + threadIdx.x, (double)s_m[threadIdx.x]);
+}
+
+// stats[co] = sum y, stats[64 + co] = sum y^2 (the layout tag_bn_finalize reads) from the moments, in double
+__global__ void c1_stats_from_moments_kernel(const double* __restrict__ mom, const float* __restrict__ w,
+                                             double* __restrict__ stats) {
+    const int co = threadIdx.x;
+    if (co >= CO) return;
+    double wk[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wk[k] = (double)w[co * 9 + k];
+    double s1 = 0.0, s2 = 0.0;
+    int idx = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        s1 += wk[k] * mom[45 + k];
+#pragma unroll
+        for (int k2 = k; k2 < 9; ++k2) { s2 += (k2 == k ? 1.0 : 2.0) * wk[k] * wk[k2] * mom[idx]; ++idx; }
+    }
+    stats[co] = s1;
+    stats[CO + co] = s2;
+}
+
+// BatchNorm parameters in the ACTIVATION domain: with a = relu(gamma * xhat + beta) saved instead of the BN input, the
+// ReLU gate is a > 0 and xhat = (a - beta) / gamma wherever the gate is open.  Writes the (scale, shift, mean, invstd)
+// quadruple that makes a fused "ReLU + BN backward reduce" epilogue (tag_conv_tc_fwd_halo bn_y = a) compute exactly that:
+// gate fma(a, 1, 0) > 0, xhat = (a - beta) * (1 / gamma).  gamma == 0 (no information about xhat in a) yields xhat = 0.
+__global__ void bn_act_domain_params_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, int C,
+                                            float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float gm = gamma[c];
+    out[c] = 1.f;
+    out[C + c] = 0.f;
+    out[2 * C + c] = beta[c];
+    out[3 * C + c] = gm != 0.f ? 1.f / gm : 0.f;
+}
+
 }  // namespace
+
+extern "C" int tag_c1_moments(const void* x, int dtype, int B, int H, int W, double* mom, cudaStream_t stream) {
+    // the Cin = 1 layer only exists on the 64-bin mel axis (tag_conv_c1_* require W == 64)
+    if (B <= 0 || H <= 0 || W != 64) return TAG_ERR_BAD_ARG;
+    cudaError_t e = cudaMemsetAsync(mom, 0, N_MOM * sizeof(double), stream);
+    if (e != cudaSuccess) return (int)e;
+    {
+        const int blocks64 = B * ((H + 4 * MOM_ROWS - 1) / (4 * MOM_ROWS));
+        if (dtype == TAG_DTYPE_F32) c1_moments_w64_kernel<float><<<blocks64, 256, 0, stream>>>((const float*)x, B, H, mom);
+        else c1_moments_w64_kernel<bf16><<<blocks64, 256, 0, stream>>>((const bf16*)x, B, H, mom);
+    }
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_c1_stats_from_moments(const double* mom, const float* w, double* stats, cudaStream_t stream) {
+    c1_stats_from_moments_kernel<<<1, 64, 0, stream>>>(mom, w, stats);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_bn_act_domain_params(const float* gamma, const float* beta, int C, float* out, cudaStream_t stream) {
+    if (C <= 0) return TAG_ERR_BAD_ARG;
+    bn_act_domain_params_kernel<<<(C + 127) / 128, 128, 0, stream>>>(gamma, beta, C, out);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_conv_c1_fwd_act(const void* x, const float* w, const float* scale, const float* shift, void* y,
+                                   int dtype, int B, int H, int W, cudaStream_t stream) {
+    if (W != TW || B <= 0 || H <= 0) return TAG_ERR_BAD_ARG;
+    int blocks = B * ((H + TH - 1) / TH);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (dtype == TAG_DTYPE_F32)
+        conv_c1_fwd_kernel<float, true><<<blocks, 256, 0, stream>>>((const float*)x, w, (float*)y, nullptr, B, H, W, scale, shift);
+    else
+        conv_c1_fwd_kernel<bf16, true><<<blocks, 256, 0, stream>>>((const bf16*)x, w, (bf16*)y, nullptr, B, H, W, scale, shift);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_conv_c1_bwd_bn(const void* g, const void* x, const float* w, const float* scale, const float* shift,
+                                  const float* mean, const float* invstd, const double* red, int bn_training, float* dw, float* dx, int B,
+                                  int H, int W, cudaStream_t stream) {
+    if (W != TW || B <= 0 || H <= 0) return TAG_ERR_BAD_ARG;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_c1_bwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MMA_SMEM_FUSE);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    int mblocks = B * ((H + MTH - 1) / MTH);
+    if (mblocks > 148) mblocks = 148;
+    const float inv_count = 1.0f / (float)((double)B * H * W);
+    conv_c1_bwd_mma_kernel<true><<<mblocks, 256, MMA_SMEM_FUSE, stream>>>((const bf16*)g, (const bf16*)x, w, dw, dx, B, H, scale,
+                                                                          shift, mean, invstd, red, inv_count, bn_training);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
 
 extern "C" int tag_conv_c1_fwd(const void* x, const float* w, void* y, int dtype, double* stats, int B,
                                int H, int W, cudaStream_t stream) {
@@ -463,9 +750,9 @@ extern "C" int tag_conv_c1_fwd(const void* x, const float* w, void* y, int dtype
     int blocks = B * ((H + TH - 1) / TH);
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (dtype == TAG_DTYPE_F32)
-        conv_c1_fwd_kernel<float><<<blocks, 256, 0, stream>>>((const float*)x, w, (float*)y, stats, B, H, W);
+        conv_c1_fwd_kernel<float, false><<<blocks, 256, 0, stream>>>((const float*)x, w, (float*)y, stats, B, H, W, nullptr, nullptr);
     else
-        conv_c1_fwd_kernel<bf16><<<blocks, 256, 0, stream>>>((const bf16*)x, w, (bf16*)y, stats, B, H, W);
+        conv_c1_fwd_kernel<bf16, false><<<blocks, 256, 0, stream>>>((const bf16*)x, w, (bf16*)y, stats, B, H, W, nullptr, nullptr);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }
@@ -481,13 +768,14 @@ extern "C" int tag_conv_c1_bwd(const void* dy, const void* x, const float* w, in
     } else {
         static bool attr_set = false;
         if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(conv_c1_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MMA_SMEM);
+            cudaError_t e = cudaFuncSetAttribute(conv_c1_bwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MMA_SMEM);
             if (e != cudaSuccess) return (int)e;
             attr_set = true;
         }
         int mblocks = B * ((H + MTH - 1) / MTH);
         if (mblocks > 148 * 2) mblocks = 148 * 2;
-        conv_c1_bwd_mma_kernel<<<mblocks, 256, MMA_SMEM, stream>>>((const bf16*)dy, (const bf16*)x, w, dw, dx, B, H);
+        conv_c1_bwd_mma_kernel<false><<<mblocks, 256, MMA_SMEM, stream>>>((const bf16*)dy, (const bf16*)x, w, dw, dx, B, H,
+                                                                          nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0);
     }
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;

@@ -82,6 +82,7 @@ class EncoderCtx:
     f: torch.Tensor = None
     out: torch.Tensor = None
     gates: torch.Tensor = None
+    c1_fused: bool = False                          # block 1: y[0] is None, a[0] = relu(bn1(conv1)) in one pass
 
 
 def _seed_for(seed: int, layer: int) -> int:
@@ -175,19 +176,36 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
     # ---- conv blocks
     x = x0
     H, W = T0, N_MELS
+    # the one-pass Cin = 1 layer: its backward (tag_conv_c1_bwd_bn) exists for bf16 and needs the fused reduce of the
+    # halo dgrad kernel
+    c1_fused = ops.USE_C1_FUSE and (not save or (dtype == torch.bfloat16 and ops.USE_TC and ops.USE_HALO))
+    if save:
+        ctx.c1_fused = c1_fused
     for blk, ((cin, cout), (ph, pw)) in enumerate(zip(CHANNELS, POOLS)):
         count = B * H * W
         # conv1
-        y1 = torch.empty(B, H, W, cout, **act)
         st1 = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if bn_training else None
-        if cin == 1:
-            call("tag_conv_c1_fwd", x, Wt.conv[0], y1, ops.dt(y1), st1, B, H, W)
-        else:
-            ops.conv_fwd(x, _operand(Wt, ("f", 2 * blk), lambda: fwd_operand(Wt.conv[2 * blk], W)), y1, None, False, st1, B, H, W, cin, cout, 9)
         aux1 = bn_aux(cout)
-        finalize(st1, count, cout, 1 + 2 * blk, aux1)
-        a1 = torch.empty(B, H, W, cout, **act)
-        ops.scale_shift_act(y1, a1, aux1[0], aux1[1], cout, relu=True)
+        if cin == 1 and c1_fused:
+            # Cin = 1: the batch statistics of conv1's output follow from 54 moments of its 16 MB input, so the layer
+            # writes relu(bn1(conv1(x))) in ONE pass; the raw output y1 is never stored (backward recomputes it)
+            if bn_training:
+                mom = torch.empty(54, device=dev, dtype=torch.float64)
+                call("tag_c1_moments", x, ops.dt(x), B, H, W, mom)
+                call("tag_c1_stats_from_moments", mom, Wt.conv[0], st1)
+            finalize(st1, count, cout, 1, aux1)
+            y1 = None
+            a1 = torch.empty(B, H, W, cout, **act)
+            call("tag_conv_c1_fwd_act", x, Wt.conv[0], aux1[0], aux1[1], a1, ops.dt(a1), B, H, W)
+        else:
+            y1 = torch.empty(B, H, W, cout, **act)
+            if cin == 1:
+                call("tag_conv_c1_fwd", x, Wt.conv[0], y1, ops.dt(y1), st1, B, H, W)
+            else:
+                ops.conv_fwd(x, _operand(Wt, ("f", 2 * blk), lambda: fwd_operand(Wt.conv[2 * blk], W)), y1, None, False, st1, B, H, W, cin, cout, 9)
+            finalize(st1, count, cout, 1 + 2 * blk, aux1)
+            a1 = torch.empty(B, H, W, cout, **act)
+            ops.scale_shift_act(y1, a1, aux1[0], aux1[1], cout, relu=True)
         # conv2
         y2 = torch.empty(B, H, W, cout, **act)
         st2 = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if bn_training else None
@@ -335,6 +353,28 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         w2t = _operand(Wt, ("t", 2 * blk + 1), lambda: ops.prep_weight_t(Wt.conv[2 * blk + 1], cout, cout, 9, dtype, W))
         da1 = torch.empty_like(a1)
         red1 = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
+        if cin == 1 and ctx.c1_fused:
+            # the BN input y1 was never stored: the fused reduce reads the saved activation a1 = relu(gamma * xhat + beta)
+            # instead (gate a1 > 0, xhat = (a1 - beta) / gamma where the gate is open)
+            g1, b1 = Wt.bn[1][0], Wt.bn[1][1]
+            actp = torch.empty(4, cout, **f32)
+            call("tag_bn_act_domain_params", g1, b1, cout, actp)
+            ops.conv_fwd(dy2, w2t, da1, None, False, red1, B, H, W, cout, cout, 9,
+                         bn_fuse=(a1, actp[0], actp[1], actp[2], actp[3]))
+            del dy2
+            dg, dbt = G.bn[1]
+            call("tag_bn_param_grads", red1, cout, dg, dbt)
+            # conv1 backward with the BatchNorm backward applied on the fly (y1 recomputed from x0)
+            dx0 = torch.empty(B, H, W, **f32)
+            call("tag_conv_c1_bwd_bn", da1, ctx.x0, Wt.conv[0], aux1[0], aux1[1], aux1[2], aux1[3], red1, bn_tr, G.conv[0], dx0,
+                 B, H, W)
+            del da1
+            red0 = torch.zeros(2 * N_MELS, device=dev, dtype=torch.float64)
+            aux0 = ctx.bn_aux[0]
+            call("tag_bn_bwd_reduce_f32", dx0, ctx.db, aux0[2], aux0[3], B * H, N_MELS, red0)
+            dg, dbt = G.bn[0]
+            call("tag_bn_param_grads", red0, N_MELS, dg, dbt)
+            continue
         if ops.can_fuse_bn_bwd(w2t, y1):
             # dgrad with the ReLU gate and the BN-backward reductions of bn1 fused into its epilogue
             ops.conv_fwd(dy2, w2t, da1, None, False, red1, B, H, W, cout, cout, 9,

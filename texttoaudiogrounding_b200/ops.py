@@ -46,6 +46,7 @@ def call(name: str, *args) -> None:
 
 USE_TC = os.environ.get("TAG_B200_NO_TC", "0") != "1"
 USE_HALO = os.environ.get("TAG_B200_NO_HALO", "0") != "1"
+USE_C1_FUSE = os.environ.get("TAG_B200_NO_C1_FUSE", "0") != "1"      # conv_block1.conv1 + bn1 + relu in one pass
 
 
 def tc_eligible(W: int, Cin: int, Cout: int) -> bool:
