@@ -83,8 +83,8 @@ int tag_c1_stats_from_moments(const double* mom, const float* w, double* stats, 
 int tag_conv_c1_fwd_act(const void* x, const float* w, const float* scale, const float* shift, void* y, int dtype,
                         int B, int H, int W, cudaStream_t stream);
 int tag_bn_act_domain_params(const float* gamma, const float* beta, int C, float* out, cudaStream_t stream);
-int tag_conv_c1_bwd_bn(const void* g, const void* x, const float* w, const float* scale, const float* shift,
-                       const float* mean, const float* invstd, const double* red, int bn_training, float* dw, float* dx, int B,
+int tag_conv_c1_bwd_bn(const void* g, const void* x, const float* w, const float* scale, const float* mean,
+                       const float* invstd, const double* red, int bn_training, float* dw, float* dx, int B,
                        int H, int W, cudaStream_t stream);
 int tag_conv_fwd(const void* x, int x_dtype, const float* w, void* y, int y_dtype, const float* bias,
                  int relu, double* stats, int B, int H, int W, int Cin, int Cout, int taps,

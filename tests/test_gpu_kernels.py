@@ -222,7 +222,7 @@ def test_c1_one_pass_layer_statistics_forward_and_backward(B, H):
         dw = torch.zeros(C, 9, device="cuda")
         dx = torch.empty(B, H, W, device="cuda")
         ops.call("tag_conv_c1_bwd_bn", gg.permute(0, 2, 3, 1).contiguous().cuda().to(bf), xd, wd, scale.cuda(),
-                 shift.cuda(), mean.cuda(), invstd.cuda(), red, int(training), dw, dx, B, H, W)
+                 mean.cuda(), invstd.cuda(), red, int(training), dw, dx, B, H, W)
         # dy1 is rounded to bf16 before the two products (as the unfused path stores it)
         assert rel_err(dw.cpu().reshape(C, 1, 3, 3), wr.grad) < 6e-3, training
         assert rel_err(dx.cpu().reshape(B, 1, H, W), xr.grad) < 6e-3, training

@@ -274,7 +274,7 @@ constexpr int MROWS = MTH + 2;
 constexpr int MNST = 3;                       // cp.async stages per warp
 constexpr int MXS_W = 68;                     // bf16 halo row: 66 used
 constexpr int MMA_SMEM = 8 * MNST * 2048 + MROWS * 64 * 9 * 4 + MROWS * MXS_W * 2 + CO * 9 * 4;
-constexpr int MMA_SMEM_FUSE = 8 * MNST * 2048 + MROWS * 64 * 9 * 4 + (MROWS + 2) * MXS_W * 2 + CO * 9 * 4 + 8 * CO * 4;
+constexpr int MMA_SMEM_FUSE = 8 * MNST * 2048 + MROWS * 64 * 9 * 4 + (MROWS + 2) * MXS_W * 2 + CO * 9 * 4 + 3 * CO * 4;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -313,9 +313,9 @@ template <bool FUSE_BN>
 __global__ void __launch_bounds__(256, FUSE_BN ? 1 : 2)
 conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ w,
                        float* __restrict__ dw, float* __restrict__ dx, int B, int H,
-                       const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
-                       const float* __restrict__ bn_mean, const float* __restrict__ bn_invstd,
-                       const double* __restrict__ bn_red, float inv_count, int bn_training) {
+                       const float* __restrict__ bn_scale, const float* __restrict__ bn_mean,
+                       const float* __restrict__ bn_invstd, const double* __restrict__ bn_red, float inv_count,
+                       int bn_training) {
     constexpr int XOFF = FUSE_BN ? 2 : 1;                 // the recomputation needs one more halo row of x each side
     constexpr int XROWS = MROWS + 2 * (XOFF - 1);
     extern __shared__ __align__(128) uint8_t msm[];
@@ -323,7 +323,7 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
     float* S = reinterpret_cast<float*>(msm + 8 * MNST * 2048);               // [MROWS][64][9]
     uint16_t* xs = reinterpret_cast<uint16_t*>(S + MROWS * 64 * 9);           // [XROWS][MXS_W] bf16 bits
     float* s_dw = reinterpret_cast<float*>(xs + XROWS * MXS_W);               // [64][9]
-    float* s_bn = s_dw + CO * 9;                                              // FUSE_BN: [8][64] per-channel constants
+    float* s_bn = s_dw + CO * 9;                                              // FUSE_BN: [3][64] = A | Bc | C
     const int tiles_h = (H + MTH - 1) / MTH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -337,15 +337,9 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
             const float sc = bn_scale[c], mu = bn_mean[c], is = bn_invstd[c];
             const float dbe = bn_training ? (float)bn_red[c] * inv_count : 0.f;
             const float dga = bn_training ? (float)bn_red[CO + c] * inv_count : 0.f;
-            const float sh = bn_shift[c];
-            s_bn[c] = sc;                                     // forward affine: a = relu(sc * y + sh)
-            s_bn[CO + c] = sh;
-            s_bn[2 * CO + c] = sc != 0.f ? is / sc : 0.f;     // 1 / gamma
-            s_bn[3 * CO + c] = sh + mu * sc;                  // beta
-            s_bn[4 * CO + c] = is;                            // xhat = is * y - mu * is
-            s_bn[5 * CO + c] = -mu * is;
-            s_bn[6 * CO + c] = sc * dbe;                      // dy1 = sc * g - sc * dbe - sc * dga * xhat
-            s_bn[7 * CO + c] = sc * dga;
+            s_bn[c] = sc;
+            s_bn[CO + c] = -sc * dga * is;
+            s_bn[2 * CO + c] = -sc * dbe + sc * dga * mu * is;
         }
         auto lo_y = [](float v) { return v - __bfloat162float(__float2bfloat16_rn(v)); };
 #pragma unroll
@@ -440,7 +434,6 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
         }
         const uint32_t sbase = my_stage + (i % MNST) * 2048 + lrow * 128;
         uint32_t a[4][4];
-        uint32_t alo[FUSE_BN ? 4 : 1][4];                 // FUSE_BN: low halves of dy1 (see below)
 #pragma unroll
         for (int q = 0; q < 4; ++q) ldsm_x4(a[q], sbase + (((2 * q + lchk) ^ (lrow & 7)) << 4));
         if (FUSE_BN) {
@@ -464,36 +457,16 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
                     mma16816(yv, ay, wyh[n][0], wyh[n][1]);
                     mma16816(yv, ay, wyl[n][0], wyl[n][1]);
                     const int ch = 16 * q + 8 * hf + 2 * t;
-                    float2 cst[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) cst[i] = *reinterpret_cast<const float2*>(s_bn + i * CO + ch);
+                    const float2 cA = *reinterpret_cast<const float2*>(s_bn + ch);
+                    const float2 cB = *reinterpret_cast<const float2*>(s_bn + CO + ch);
+                    const float2 cC = *reinterpret_cast<const float2*>(s_bn + 2 * CO + ch);
 #pragma unroll
                     for (int rr = 0; rr < 2; ++rr) {                 // rr = 0: pixel g, rr = 1: pixel g + 8
                         const uint32_t u = a[q][2 * hf + rr];
-                        const float gv[2] = {__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u)};
-                        float dv[2];
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const float yy = yv[2 * rr + e];
-                            const float sc = e ? cst[0].y : cst[0].x, sh = e ? cst[1].y : cst[1].x;
-                            const float ig = e ? cst[2].y : cst[2].x, be = e ? cst[3].y : cst[3].x;
-                            const float xs_ = e ? cst[4].y : cst[4].x, xo_ = e ? cst[5].y : cst[5].x;
-                            const float am = e ? cst[6].y : cst[6].x, ax_ = e ? cst[7].y : cst[7].x;
-                            // Where the ReLU gate is open the fused reduce of the conv2 dgrad saw xhat through the SAVED
-                            // activation, (bf16(a) - beta) / gamma; the apply must use that same value, or dy1 keeps a
-                            // component along xhat of size (sum g (xhat' - xhat)) / N on EVERY pixel of the channel — a
-                            // coherent error in dw (sum xhat * x is the large y-x correlation).  Gate closed: exact xhat.
-                            const float ar = round_to<bf16>(fmaxf(fmaf(yy, sc, sh), 0.f));
-                            const float xh = ar > 0.f ? (ar - be) * ig : fmaf(yy, xs_, xo_);
-                            dv[e] = fmaf(sc, gv[e], -fmaf(ax_, xh, am));
-                        }
-                        const float d0 = dv[0], d1 = dv[1];
-                        // dy1 exists in fp32 only here: the dx product takes it as bf16 hi + lo (dx feeds the bn0
-                        // gradients, sums over 4 M pixels that cancel to a few percent of their terms — a second bf16
-                        // rounding of every term is visible there); so does the (cheap) weight-gradient product
-                        const uint32_t hi = pack2(d0, d1);
-                        a[q][2 * hf + rr] = hi;
-                        alo[q][2 * hf + rr] = pack2(d0 - __uint_as_float(hi << 16), d1 - __uint_as_float(hi & 0xFFFF0000u));
+                        const float g0 = __uint_as_float(u << 16), g1 = __uint_as_float(u & 0xFFFF0000u);
+                        const float d0 = fmaf(cA.x, g0, fmaf(cB.x, yv[2 * rr], cC.x));
+                        const float d1 = fmaf(cA.y, g1, fmaf(cB.y, yv[2 * rr + 1], cC.y));
+                        a[q][2 * hf + rr] = pack2(d0, d1);
                     }
                 }
             }
@@ -505,10 +478,6 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
             mma16816(s1, a[q], wb[q][1][0], wb[q][1][1]);
             mma16816(s0, a[q], wl[q][0][0], wl[q][0][1]);
             mma16816(s1, a[q], wl[q][1][0], wl[q][1][1]);
-            if (FUSE_BN) {
-                mma16816(s0, alo[q], wb[q][0][0], wb[q][0][1]);
-                mma16816(s1, alo[q], wb[q][1][0], wb[q][1][1]);
-            }
         }
         Srow[g * 9 + 2 * t] = s0[0];
         Srow[g * 9 + 2 * t + 1] = s0[1];
@@ -538,12 +507,6 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
                 }
                 mma16816(acc[2 * q], ax, bt[0], bt[1]);
                 mma16816(acc[2 * q + 1], ax, bt[2], bt[3]);
-                if (FUSE_BN) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) bt[j] = movmatrix_trans(alo[q][j]);
-                    mma16816(acc[2 * q], ax, bt[0], bt[1]);
-                    mma16816(acc[2 * q + 1], ax, bt[2], bt[3]);
-                }
             }
         }
         __syncwarp();
@@ -589,6 +552,21 @@ conv_c1_bwd_mma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, 
 // over all output pixels p (zero padding).  The 9 + 45 moments of the 16 MB input cost one pass over it; the layer can
 // then write relu(bn(conv)) in a single kernel (conv_c1_fwd_kernel<ACT>).  mom: [45 upper-triangular M2 | 9 M1] doubles.
 constexpr int N_MOM = 54;
+
+// After the call lane l holds the sum over the 32 lanes of a[l] (butterfly transpose-reduce, 31 shuffles).
+__device__ __forceinline__ float c1_transpose_sum(float (&a)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? a[i] : a[i + off];
+            const float keep = upper ? a[i + off] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return a[0];
+}
 
 // W == 64 (the model's mel axis): a thread owns one column and walks MOM_ROWS rows with a rolling 3x3 window, so every
 // input element is loaded three times (coalesced 128-byte rows) instead of nine, with no index divisions.
@@ -639,11 +617,15 @@ c1_moments_w64_kernel(const T* __restrict__ x, int B, int H, double* __restrict_
             for (int k = 0; k < 9; ++k) m[45 + k] += xn[k];
         }
     }
+    // 54 sums over the warp as two 32-wide butterfly transpose-reductions (62 shuffles instead of 270): afterwards lane l
+    // holds the warp totals of moments l and 32 + l
+    float lo32[32], hi32[32];
 #pragma unroll
-    for (int i = 0; i < N_MOM; ++i) {
-        const float v = warp_sum(m[i]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&s_m[i], v);
-    }
+    for (int i = 0; i < 32; ++i) { lo32[i] = m[i]; hi32[i] = 32 + i < N_MOM ? m[32 + i] : 0.f; }
+    const int lane = threadIdx.x & 31;
+    const float t0 = c1_transpose_sum(lo32, lane), t1 = c1_transpose_sum(hi32, lane);
+    atomicAdd(&s_m[lane], t0);
+    if (32 + lane < N_MOM) atomicAdd(&s_m[32 + lane], t1);
     __syncthreads();
     if (threadIdx.x < N_MOM) atomicAdd(mom + threadIdx.x, (double)s_m[threadIdx.x]);
 }
@@ -725,8 +707,8 @@ extern "C" int tag_conv_c1_fwd_act(const void* x, const float* w, const float* s
     return TAG_OK;
 }
 
-extern "C" int tag_conv_c1_bwd_bn(const void* g, const void* x, const float* w, const float* scale, const float* shift,
-                                  const float* mean, const float* invstd, const double* red, int bn_training, float* dw, float* dx, int B,
+extern "C" int tag_conv_c1_bwd_bn(const void* g, const void* x, const float* w, const float* scale, const float* mean,
+                                  const float* invstd, const double* red, int bn_training, float* dw, float* dx, int B,
                                   int H, int W, cudaStream_t stream) {
     if (W != TW || B <= 0 || H <= 0) return TAG_ERR_BAD_ARG;
     static bool attr_set = false;
@@ -739,7 +721,7 @@ extern "C" int tag_conv_c1_bwd_bn(const void* g, const void* x, const float* w, 
     if (mblocks > 148) mblocks = 148;
     const float inv_count = 1.0f / (float)((double)B * H * W);
     conv_c1_bwd_mma_kernel<true><<<mblocks, 256, MMA_SMEM_FUSE, stream>>>((const bf16*)g, (const bf16*)x, w, dw, dx, B, H, scale,
-                                                                          shift, mean, invstd, red, inv_count, bn_training);
+                                                                          mean, invstd, red, inv_count, bn_training);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }
@@ -775,7 +757,7 @@ extern "C" int tag_conv_c1_bwd(const void* dy, const void* x, const float* w, in
         int mblocks = B * ((H + MTH - 1) / MTH);
         if (mblocks > 148 * 2) mblocks = 148 * 2;
         conv_c1_bwd_mma_kernel<false><<<mblocks, 256, MMA_SMEM, stream>>>((const bf16*)dy, (const bf16*)x, w, dw, dx, B, H,
-                                                                          nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0);
+                                                                          nullptr, nullptr, nullptr, nullptr, 0.f, 0);
     }
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;

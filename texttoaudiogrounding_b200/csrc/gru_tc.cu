@@ -1,12 +1,17 @@
-// BiGRU recurrence, bf16 tensor-core variant (compute dtype bf16): same cluster decomposition as
-// gru.cu (8 CTAs x 32 hidden units, 8 sequences per cluster, DSMEM exchange, one cluster barrier
-// per step) but the per-step product with W_hh runs on mma.sync.m16n8k16 with the CTA's W_hh
-// slice held in REGISTERS as A fragments for all T steps (48 registers per thread), so a step
-// costs 12 MMAs per warp instead of ~800 FFMAs, and the exchanged state is bf16 rows of 64 B.
-// The hidden state itself, the gates and all gradients stay fp32.
+// BiGRU recurrence, bf16 tensor-core variant (compute dtype bf16): a cluster of 8 CTAs per (direction, 8 sequences),
+// CTA c owning hidden units 32 c .. 32 c + 31.  The per-step product with W_hh runs on mma.sync.m16n8k16 with the CTA's
+// W_hh slice held in REGISTERS as A fragments for all T steps (48 registers per thread); the hidden state, the gates and
+// all gradients stay fp32; what crosses CTAs is bf16, as 16-byte `st.async` pieces that complete on the receiver's
+// mbarrier (no cluster barrier, no fence in the loop).
+//   forward : every CTA needs the whole new state: it ships its 32 units x 8 sequences to all 8 CTAs (256 pieces arrive
+//             per CTA and step), each CTA multiplies its 96 gate rows with the full state (K split over the 8 warps).
+//   backward: a CTA multiplies its OWN 96 gate-gradient rows with its rows of W_hh for all 256 units and ships the eight
+//             8 x 32 partial products to their owners (256 pieces per CTA and step instead of 768 gate-gradient pieces).
+// Measured (scripts/gru_timing.py, B = 64, T = 250): the hand-off costs ~2 ns per arriving piece, so the piece count sets
+// the step time: 1.50 -> 1.17 us / step forward, 2.0 -> 1.19 us / step backward against the cluster-barrier version.
 //
-// (tcgen05 needs M >= 64 and pays a TMEM round trip per step; for a 96 x 8 x 256 product on the
-// critical path of a 250-step recurrence the register-resident mma.sync form has lower latency.)
+// (tcgen05 needs M >= 64 and pays a TMEM round trip per step; for a 96 x 8 x 256 product on the critical path of a
+// 250-step recurrence the register-resident mma.sync form has lower latency.)
 //
 // Replaces the cuDNN RNN behind nn.GRU (reference models/audio_encoder.py:141,217).
 #include "common.cuh"
@@ -22,7 +27,6 @@ constexpr int JS = HID / NCTA;        // 32
 constexpr int BS = 8;
 constexpr int G3 = 3 * HID;           // 768
 constexpr int HPAD = HID + 8;         // bf16 row stride of the exchanged hidden state
-constexpr int GPAD = G3 + 8;          // bf16 row stride of the exchanged gate gradients
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
@@ -35,26 +39,82 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float fast_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 2.0f / (1.0f + __expf(-2.0f * x)) - 1.0f; }
 
-struct FwdSmem {
-    bf16 h[2][BS][HPAD];              // double-buffered hidden state, [b][k]
-    float part[8][BS][100];           // per-warp partial gate pre-activations, [warp][b][row (96) + pad]
+// ---------------------------------------------------------------------------------------------
+// Barrier-free hand-off.  An exchange through plain DSMEM stores needs one cluster barrier per step: arrive.release has
+// to drain every earlier store of the thread (the HBM stores of the previous step included) and the barrier itself costs
+// ~400 cycles.  Here every 16-byte piece of a state row travels as ONE `st.async` that carries its own completion: the
+// store lands in the peer's shared memory and adds 16 to the transaction count of the peer's mbarrier for that step.
+// A CTA waits on its LOCAL mbarrier until all 8 producers (itself included) have delivered the step's bytes — no
+// cluster barrier, no fence, and the HBM stores are never ordered against anything.  Buffers and barriers alternate
+// between two slots: a CTA can only be one step ahead of the slowest peer (it needs that peer's bytes to advance), so
+// slot s & 1 is never overwritten while someone still reads it.
+__device__ __forceinline__ void g_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void g_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 22)) __trap();           // a lost hand-off must not hang the GPU
+    }
+}
+__device__ __forceinline__ uint32_t g_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async16(uint32_t cluster_addr, const uint4& v, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_bar) : "memory");
+}
+
+// sigmoid / tanh on the hardware tanh (MUFU.TANH, 2^-11 relative error): the IEEE divisions of the formulas above were
+// ~350 of the ~1900 cycles of a step, and the state crosses CTAs in bf16 (2^-9) anyway.
+__device__ __forceinline__ float hw_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float hw_sigmoid(float x) { return fmaf(0.5f, hw_tanh(0.5f * x), 0.5f); }
+
+#ifdef TAG_GRU_TIMING
+__device__ long long g_gru_timing[64 * 8];
+#define GRU_T(slot) do { if (tid == 32 && cta == 1 && slice == 0 && dir == 0 && step >= 16 && step < 80) \
+        g_gru_timing[(step - 16) * 8 + (slot)] = clock64(); } while (0)
+#define GRU_MARK(row) do { if (tid == 32 && cta == 1 && slice == 0 && dir == 0) g_gru_timing[(row) * 8 + 7] = clock64(); } while (0)
+#else
+#define GRU_T(slot) do { } while (0)
+#define GRU_MARK(row) do { } while (0)
+#endif
+
+struct FwdSmemA {
+    bf16 h[2][BS][HPAD];              // receive buffers: hidden state of all 256 units, [slot][b][k]
+    float part[8][BS][100];           // per-warp partial gate pre-activations
+    bf16 stage[BS][JS];               // this CTA's 32 new units per sequence (64 B rows), source of the st.async pieces
+    unsigned long long bar[2];
 };
 
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(256, 1)
-gru_fwd_tc_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
-                  float* __restrict__ out, float* __restrict__ gates, int B, int T) {
-    __shared__ __align__(16) FwdSmem s;
+gru_fwd_tc_async_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
+                        float* __restrict__ out, float* __restrict__ gates, int B, int T) {
+    __shared__ __align__(16) FwdSmemA s;
     cg::cluster_group cluster = cg::this_cluster();
     const int cta = (int)cluster.block_rank();
     const int slice = blockIdx.y, dir = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* W = w_hh + (long)dir * G3 * HID;
     const float* bh = b_hh + dir * G3;
+    constexpr uint32_t STEP_BYTES = NCTA * BS * JS * 2;          // 4096: every producer delivers 8 rows of 64 B
 
-    // ---- A fragments: rows (g, j) of this CTA, k in [32 warp, 32 warp + 32)
     uint32_t afrag[6][2][4];
 #pragma unroll
     for (int mt = 0; mt < 6; ++mt) {
@@ -62,8 +122,8 @@ gru_fwd_tc_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, 
         for (int kt = 0; kt < 2; ++kt) {
             const int k0 = warp * 32 + kt * 16 + (lane & 3) * 2;
 #pragma unroll
-            for (int hr = 0; hr < 2; ++hr) {            // rows lane/4 and lane/4 + 8 of the M tile
-                const int rl = mt * 16 + (lane >> 2) + hr * 8;      // local row = g*32 + j
+            for (int hr = 0; hr < 2; ++hr) {
+                const int rl = mt * 16 + (lane >> 2) + hr * 8;
                 const int grow = (rl >> 5) * HID + cta * JS + (rl & 31);
                 const float* wr = W + (long)grow * HID;
                 afrag[mt][kt][hr] = pack_bf16(wr[k0], wr[k0 + 1]);
@@ -72,19 +132,26 @@ gru_fwd_tc_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, 
         }
     }
     for (int i = tid; i < 2 * BS * HPAD; i += 256) (&s.h[0][0][0])[i] = __float2bfloat16_rn(0.f);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s.bar[0]);
+    if (tid == 0) {
+        g_mbar_init(bar0, 1); g_mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        g_mbar_expect_tx(bar0, STEP_BYTES);                      // slot 0 receives h_2, slot 1 receives h_1
+        g_mbar_expect_tx(bar0 + 8, STEP_BYTES);
+    }
     cluster.sync();
 
-    // finalisation role: hidden unit jg, sequence bl
     const int jg = cta * JS + lane;
     const int bl = warp;
     const int bglob = slice * BS + bl;
     const bool b_ok = bglob < B;
     const float bias_r = bh[jg], bias_z = bh[HID + jg], bias_n = bh[2 * HID + jg];
-    bf16* peer_h[NCTA];
-#pragma unroll
-    for (int r = 0; r < NCTA; ++r) peer_h[r] = cluster.map_shared_rank(&s.h[0][0][0], r);
+    // lane l delivers piece (l & 3) of this warp's 64-byte row to peer l >> 2
+    const uint32_t peer = lane >> 2, piece = lane & 3;
+    const uint32_t h_local = (uint32_t)__cvta_generic_to_shared(&s.h[0][0][0]);
+    const uint32_t peer_h = g_mapa(h_local, peer) + (uint32_t)((bl * HPAD + cta * JS + piece * 8) * 2);
+    const uint32_t peer_bar = g_mapa(bar0, peer);
 
-    // input projections are fetched two steps ahead (their L2/HBM latency is off the critical path)
     auto fetch_gi = [&](int step, float (&g3)[3]) {
         g3[0] = g3[1] = g3[2] = 0.f;
         if (b_ok && step < T) {
@@ -97,12 +164,18 @@ gru_fwd_tc_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, 
     fetch_gi(0, gi_cur);
     fetch_gi(1, gi_nxt);
     float hprev = 0.f;
-    int cur = 0;
     for (int step = 0; step < T; ++step) {
         const int t = dir == 0 ? step : T - 1 - step;
+        const int cur = step & 1, nxt = cur ^ 1;
+        GRU_T(0);
         fetch_gi(step + 2, gi_nn);
+        if (step > 0) {
+            // h_step: slot cur, its (step - 1) / 2-th use
+            g_mbar_wait(bar0 + 8 * cur, (uint32_t)(((step - 1) >> 1) & 1));
+            if (tid == 0) g_mbar_expect_tx(bar0 + 8 * cur, STEP_BYTES);      // re-arm for h_{step + 2}
+        }
+        GRU_T(1);
         const float gi_r = gi_cur[0], gi_z = gi_cur[1], gi_n = gi_cur[2];
-        // ---- partial product on the tensor cores
         uint32_t bfrag[2][2];
 #pragma unroll
         for (int kt = 0; kt < 2; ++kt) {
@@ -121,7 +194,9 @@ gru_fwd_tc_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, 
             s.part[warp][c0][r0 + 8] = d[2];
             s.part[warp][c0 + 1][r0 + 8] = d[3];
         }
+        GRU_T(2);
         __syncthreads();
+        GRU_T(3);
         float gh_r = bias_r, gh_z = bias_z, gh_n = bias_n;
 #pragma unroll
         for (int wv = 0; wv < 8; ++wv) {
@@ -129,19 +204,20 @@ gru_fwd_tc_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, 
             gh_z += s.part[wv][bl][JS + lane];
             gh_n += s.part[wv][bl][2 * JS + lane];
         }
-        const float r = fast_sigmoid(gi_r + gh_r);
-        const float z = fast_sigmoid(gi_z + gh_z);
-        const float n = fast_tanh(gi_n + r * gh_n);
+        GRU_T(4);
+        const float r = hw_sigmoid(gi_r + gh_r);
+        const float z = hw_sigmoid(gi_z + gh_z);
+        const float n = hw_tanh(gi_n + r * gh_n);
         const float hnew = (1.f - z) * n + z * hprev;
         hprev = hnew;
-        const int nxt = cur ^ 1;
-        const int off = (nxt * BS + bl) * HPAD + jg;
-        const bf16 hb = __float2bfloat16_rn(hnew);
-#pragma unroll
-        for (int rnk = 0; rnk < NCTA; ++rnk) peer_h[rnk][off] = hb;
-        // arrive first, then issue the HBM stores: the release of the NEXT arrive waits for them,
-        // a whole step later, instead of this one
-        auto token = cluster.barrier_arrive();
+        if (step + 1 < T) {
+            s.stage[bl][lane] = __float2bfloat16_rn(hnew);
+            __syncwarp();
+            const uint4 v = *reinterpret_cast<const uint4*>(&s.stage[bl][piece * 8]);
+            GRU_T(5);
+            st_async16(peer_h + (uint32_t)(nxt * BS * HPAD * 2), v, peer_bar + 8 * nxt);
+        }
+        GRU_T(6);
         if (b_ok) {
             out[((long)bglob * T + t) * (2 * HID) + dir * HID + jg] = hnew;
             if (gates != nullptr) {
@@ -151,76 +227,111 @@ gru_fwd_tc_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, 
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) { gi_cur[i] = gi_nxt[i]; gi_nxt[i] = gi_nn[i]; }
-        cluster.barrier_wait(std::move(token));
-        cur = nxt;
     }
+    cluster.sync();                   // no CTA retires while a peer may still deliver into it
 }
 
-struct BwdSmem {
-    bf16 dgh[2][BS][GPAD];            // double-buffered gathered gate gradients, [b][row]
-    float part[8][BS][36];            // [warp][b][k_local (32) + pad]
+// ---------------------------------------------------------------------------------------------
+// Backward with the PRODUCT exchanged instead of its operand.  The hand-off costs ~2 ns per st.async at the receiving
+// CTA (measured: 256 pieces / step -> 0.55 us, 512 -> 1.1 us, scripts/gru_timing.py), and shipping
+// every CTA's 96 gate-gradient rows to all 8 CTAs would be 768 pieces per CTA and step: 1.5 us.  Here a CTA keeps its
+// gate gradients local and multiplies them with ITS 96 rows of W_hh for ALL 256 hidden units (warp w: units 32 w .. + 31,
+// 12 MMAs, the same count as before); the result is one eighth of dh_prev for everybody, and warp w's 8 x 32 block goes
+// to CTA w alone as 32 bf16 pieces.  A CTA receives 8 x 32 = 256 pieces per step (one third), sums the 8 partial blocks
+// in fp32 and adds the direct term.
+constexpr int GPL = 112;              // local gate-gradient row stride (96 rows + pad: 224 B, sequences skew by 24 banks)
+constexpr int SPL = 40;               // staging row stride (80 B: conflict-free 2-byte scatter, 16-byte aligned pieces)
+struct BwdSmemP {
+    bf16 dgl[BS][GPL];                // this CTA's gate gradients of the current step, [b][g * 32 + j]: the B operand
+    bf16 recv[2][NCTA][BS][JS];       // partial dh_prev blocks, [slot][source CTA][b][k local]
+    bf16 stage[8][BS][SPL];           // per warp: its outgoing 8 x 32 block
+    unsigned long long bar[2];
 };
 
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(256, 1)
-gru_bwd_tc_kernel(const float* __restrict__ d_out, const float* __restrict__ out, const float* __restrict__ gates,
-                  const float* __restrict__ w_hh, bf16* __restrict__ dgi, bf16* __restrict__ dgh_out,
-                  bf16* __restrict__ hprev_out, int B, int T) {
-    __shared__ __align__(16) BwdSmem s;
+gru_bwd_tc_prod_kernel(const float* __restrict__ d_out, const float* __restrict__ out, const float* __restrict__ gates,
+                       const float* __restrict__ w_hh, bf16* __restrict__ dgi, bf16* __restrict__ dgh_out,
+                       bf16* __restrict__ hprev_out, int B, int T) {
+    __shared__ __align__(16) BwdSmemP s;
     cg::cluster_group cluster = cg::this_cluster();
     const int cta = (int)cluster.block_rank();
     const int slice = blockIdx.y, dir = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = lane & 3, rho = lane >> 2;
     const float* W = w_hh + (long)dir * G3 * HID;
+    constexpr uint32_t STEP_BYTES = NCTA * BS * JS * 2;          // 4096
 
-    // ---- A fragments of W_hh^T: A[m = k_local][kk = row] = W_hh[row][32 cta + k_local];
-    //      this warp owns rows [96 warp, 96 warp + 96) = 6 K tiles, both M tiles.
+    // A[m = kk][kdim = r] = W_hh[global row of local row r][32 warp + kk]; local row r = 32 g + j <-> global g * 256 + 32 cta + j.
+    // The k order inside an MMA is permuted (fragment column 2c + e <-> r = 16 kt + 4c + e, column 2c + 8 + e <-> r = 16 kt
+    // + 4c + 2 + e) so that a B fragment is ONE 8-byte shared-memory load.
     uint32_t afrag[2][6][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
         for (int kt = 0; kt < 6; ++kt) {
-            const int row0 = warp * 96 + kt * 16 + (lane & 3) * 2;
 #pragma unroll
             for (int hr = 0; hr < 2; ++hr) {
-                const int kcol = cta * JS + mt * 16 + (lane >> 2) + hr * 8;
-                afrag[mt][kt][hr] = pack_bf16(W[(long)row0 * HID + kcol], W[(long)(row0 + 1) * HID + kcol]);
-                afrag[mt][kt][hr + 2] = pack_bf16(W[(long)(row0 + 8) * HID + kcol], W[(long)(row0 + 9) * HID + kcol]);
+                const int kcol = warp * 32 + mt * 16 + rho + hr * 8;
+                float wv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int r = kt * 16 + 4 * c + e;
+                    wv[e] = W[(long)((r >> 5) * HID + cta * JS + (r & 31)) * HID + kcol];
+                }
+                afrag[mt][kt][hr] = pack_bf16(wv[0], wv[1]);
+                afrag[mt][kt][hr + 2] = pack_bf16(wv[2], wv[3]);
             }
         }
     }
-    for (int i = tid; i < 2 * BS * GPAD; i += 256) (&s.dgh[0][0][0])[i] = __float2bfloat16_rn(0.f);
+    for (int i = tid; i < BS * GPL; i += 256) (&s.dgl[0][0])[i] = __float2bfloat16_rn(0.f);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s.bar[0]);
+    if (tid == 0) {
+        g_mbar_init(bar0, 1); g_mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        g_mbar_expect_tx(bar0, STEP_BYTES);
+        g_mbar_expect_tx(bar0 + 8, STEP_BYTES);
+    }
     cluster.sync();
 
     const int jg = cta * JS + lane;
     const int bl = warp;
     const int bglob = slice * BS + bl;
     const bool b_ok = bglob < B;
-    bf16* peer[NCTA];
-#pragma unroll
-    for (int r = 0; r < NCTA; ++r) peer[r] = cluster.map_shared_rank(&s.dgh[0][0][0], r);
+    // outgoing: lane l delivers piece (l & 3) of sequence l >> 2 of this warp's block to CTA `warp`
+    const int pseq = lane >> 2, ppiece = lane & 3;
+    const uint32_t recv_local = (uint32_t)__cvta_generic_to_shared(&s.recv[0][0][0][0]);
+    const uint32_t dst_recv = g_mapa(recv_local, (uint32_t)warp) + (uint32_t)(((cta * BS + pseq) * JS + ppiece * 8) * 2);
+    const uint32_t dst_bar = g_mapa(bar0, (uint32_t)warp);
 
-    // software pipeline: the operands of step s+1 are fetched while step s runs its product
-    float p_r = 0.f, p_z = 0.f, p_n = 0.f, p_hn = 0.f, p_do = 0.f, p_hp = 0.f;
-    auto fetch = [&](int step) {
+    // per-step operands, fetched TWO steps ahead into alternating register sets (the loop body is instantiated twice)
+    const long t_stride = dir == 0 ? -1 : 1;                     // the backward pass walks time in reverse
+    const int t_first = dir == 0 ? T - 1 : 0;
+    const long bt0 = (long)bglob * T + t_first;
+    const float* gates_p = gates + (bt0 * 2 + dir) * 4 * HID + jg;
+    const float* dout_p = d_out + bt0 * (2 * HID) + dir * HID + jg;
+    const float* outp_p = out + bt0 * (2 * HID) + dir * HID + jg;             // out[t]; the previous state is out[t_prev]
+    bf16* dgi_p = dgi + bt0 * (2 * G3) + dir * G3 + jg;
+    bf16* dgh_p = dgh_out + ((long)dir * B * T + bt0) * G3 + jg;
+    bf16* hp_p = hprev_out + ((long)dir * B * T + bt0) * HID + jg;
+    struct Ops { float r, z, n, hn, dout, hprev; };
+    auto fetch = [&](int step, Ops& o) {
+        o.r = o.z = o.n = o.hn = o.dout = o.hprev = 0.f;
         if (!b_ok || step >= T) return;
-        const int t = dir == 0 ? T - 1 - step : step;
-        const int t_prev = dir == 0 ? t - 1 : t + 1;
-        const long bt = (long)bglob * T + t;
-        const float* gp = gates + (bt * 2 + dir) * 4 * HID;
-        p_r = __ldg(gp + jg); p_z = __ldg(gp + HID + jg); p_n = __ldg(gp + 2 * HID + jg); p_hn = __ldg(gp + 3 * HID + jg);
-        p_do = __ldg(d_out + bt * (2 * HID) + dir * HID + jg);
-        p_hp = (t_prev >= 0 && t_prev < T) ? __ldg(out + ((long)bglob * T + t_prev) * (2 * HID) + dir * HID + jg) : 0.f;
+        const long off = (long)step * t_stride;
+        const float* gp = gates_p + off * (8 * HID);
+        o.r = __ldg(gp); o.z = __ldg(gp + HID); o.n = __ldg(gp + 2 * HID); o.hn = __ldg(gp + 3 * HID);
+        o.dout = __ldg(dout_p + off * (2 * HID));
+        if (step + 1 < T) o.hprev = __ldg(outp_p + (off + t_stride) * (2 * HID));   // t_prev = t -+ 1 inside the sequence
     };
-    fetch(0);
-
     float dh = 0.f;
-    int cur = 0;
-    for (int step = 0; step < T; ++step) {
-        const int t = dir == 0 ? T - 1 - step : step;
+    auto do_step = [&](int step, Ops& ops) {
+        const int cur = step & 1;
+        const Ops o = ops;                        // this step's operands; the set is refilled for step + 2 right away
+        fetch(step + 2, ops);
         float g_r = 0.f, g_z = 0.f, g_n = 0.f, dh_direct = 0.f, s_dn = 0.f, s_hp = 0.f;
         if (b_ok) {
-            const float r = p_r, z = p_z, n = p_n, hn = p_hn, hprev = p_hp;
-            const float dht = dh + p_do;
+            const float r = o.r, z = o.z, n = o.n, hn = o.hn, hprev = o.hprev;
+            const float dht = dh + o.dout;
             const float dn_pre = dht * (1.f - z) * (1.f - n * n);
             const float dz_pre = dht * (hprev - n) * z * (1.f - z);
             const float dr_pre = dn_pre * hn * r * (1.f - r);
@@ -229,59 +340,66 @@ gru_bwd_tc_kernel(const float* __restrict__ d_out, const float* __restrict__ out
             dh_direct = dht * z;
         }
         const bf16 v_r = __float2bfloat16_rn(g_r), v_z = __float2bfloat16_rn(g_z), v_n = __float2bfloat16_rn(g_n);
-        {
-            const int o = (cur * BS + bl) * GPAD + jg;
-#pragma unroll
-            for (int rnk = 0; rnk < NCTA; ++rnk) {
-                peer[rnk][o] = v_r; peer[rnk][o + HID] = v_z; peer[rnk][o + 2 * HID] = v_n;
-            }
+        const bool exchange = step + 1 < T;       // the last step's dh_prev has no consumer
+        if (exchange) { s.dgl[bl][lane] = v_r; s.dgl[bl][JS + lane] = v_z; s.dgl[bl][2 * JS + lane] = v_n; }
+        if (b_ok) {
+            const long off = (long)step * t_stride;
+            bf16* gi_o = dgi_p + off * (2 * G3);
+            gi_o[0] = v_r; gi_o[HID] = v_z; gi_o[2 * HID] = __float2bfloat16_rn(s_dn);
+            bf16* gh_o = dgh_p + off * G3;
+            gh_o[0] = v_r; gh_o[HID] = v_z; gh_o[2 * HID] = v_n;
+            hp_p[off * HID] = __float2bfloat16_rn(s_hp);
         }
-        auto token = cluster.barrier_arrive();
-        if (b_ok) {          // HBM stores after the arrive (see the forward kernel)
-            const long bt = (long)bglob * T + t;
-            // bf16 outputs: they are operands of the tensor-core weight-gradient / dgrad GEMMs
-            bf16* gi_p = dgi + bt * (2 * G3) + dir * G3;
-            gi_p[jg] = v_r; gi_p[HID + jg] = v_z; gi_p[2 * HID + jg] = __float2bfloat16_rn(s_dn);
-            bf16* gh_p = dgh_out + ((long)dir * B * T + bt) * G3;
-            gh_p[jg] = v_r; gh_p[HID + jg] = v_z; gh_p[2 * HID + jg] = v_n;
-            hprev_out[((long)dir * B * T + bt) * HID + jg] = __float2bfloat16_rn(s_hp);
-        }
-        fetch(step + 1);
-        cluster.barrier_wait(std::move(token));
-        // dh_prev[b][k_local] = sum_row dgh[b][row] * W_hh[row][32 cta + k_local]
+        if (!exchange) return;
+        __syncthreads();                           // all 96 x 8 gate gradients of this CTA are in dgl
         float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+        const bf16* brow = &s.dgl[rho][4 * c];
 #pragma unroll
         for (int kt = 0; kt < 6; ++kt) {
-            const bf16* gp = &s.dgh[cur][lane >> 2][warp * 96 + kt * 16 + (lane & 3) * 2];
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(gp);
-            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(gp + 8);
-            mma_bf16_16816(d0, afrag[0][kt], b0, b1);
-            mma_bf16_16816(d1, afrag[1][kt], b0, b1);
+            const uint2 b = *reinterpret_cast<const uint2*>(brow + kt * 16);
+            mma_bf16_16816(d0, afrag[0][kt], b.x, b.y);
+            mma_bf16_16816(d1, afrag[1][kt], b.x, b.y);
         }
-        {
-            const int r0 = lane >> 2, c0 = (lane & 3) * 2;
-            s.part[warp][c0][r0] = d0[0];      s.part[warp][c0 + 1][r0] = d0[1];
-            s.part[warp][c0][r0 + 8] = d0[2];  s.part[warp][c0 + 1][r0 + 8] = d0[3];
-            s.part[warp][c0][16 + r0] = d1[0]; s.part[warp][c0 + 1][16 + r0] = d1[1];
-            s.part[warp][c0][24 + r0] = d1[2]; s.part[warp][c0 + 1][24 + r0] = d1[3];
+        {   // d0: units rho, rho + 8 (of this warp's 32), d1: 16 + rho, 24 + rho; sequences 2c, 2c + 1
+            bf16* st = &s.stage[warp][0][0];
+            st[(2 * c) * SPL + rho] = __float2bfloat16_rn(d0[0]);      st[(2 * c + 1) * SPL + rho] = __float2bfloat16_rn(d0[1]);
+            st[(2 * c) * SPL + rho + 8] = __float2bfloat16_rn(d0[2]);  st[(2 * c + 1) * SPL + rho + 8] = __float2bfloat16_rn(d0[3]);
+            st[(2 * c) * SPL + rho + 16] = __float2bfloat16_rn(d1[0]); st[(2 * c + 1) * SPL + rho + 16] = __float2bfloat16_rn(d1[1]);
+            st[(2 * c) * SPL + rho + 24] = __float2bfloat16_rn(d1[2]); st[(2 * c + 1) * SPL + rho + 24] = __float2bfloat16_rn(d1[3]);
         }
-        __syncthreads();
+        __syncwarp();
+        const uint4 v = *reinterpret_cast<const uint4*>(&s.stage[warp][pseq][ppiece * 8]);
+        st_async16(dst_recv + (uint32_t)(cur * NCTA * BS * JS * 2), v, dst_bar + 8 * cur);
+        g_mbar_wait(bar0 + 8 * cur, (uint32_t)((step >> 1) & 1));
+        if (tid == 0) g_mbar_expect_tx(bar0 + 8 * cur, STEP_BYTES);          // re-arm for step + 2
         float sum = dh_direct;
 #pragma unroll
-        for (int wv = 0; wv < 8; ++wv) sum += s.part[wv][bl][lane];
+        for (int src = 0; src < NCTA; ++src) sum += __bfloat162float(s.recv[cur][src][bl][lane]);
         dh = sum;
-        cur ^= 1;
-        // part[] is next written after the following cluster.sync(), which orders it after these reads
+    };
+    Ops oa, ob;
+    fetch(0, oa);
+    fetch(1, ob);
+    for (int step = 0; step < T; step += 2) {
+        do_step(step, oa);
+        if (step + 1 < T) do_step(step + 1, ob);
     }
+    cluster.sync();
 }
 
 }  // namespace
+
+#ifdef TAG_GRU_TIMING
+extern "C" int tag_gru_timing_read(long long* host64x8) {
+    return (int)cudaMemcpyFromSymbol(host64x8, g_gru_timing, sizeof(long long) * 64 * 8);
+}
+#endif
 
 extern "C" int tag_gru_fwd_bf16(const float* gi, const float* w_hh, const float* b_hh, float* out,
                                 float* gates, int B, int T, cudaStream_t stream) {
     if (B <= 0 || T <= 0) return TAG_ERR_BAD_ARG;
     dim3 grid(NCTA, (B + BS - 1) / BS, 2);
-    gru_fwd_tc_kernel<<<grid, 256, 0, stream>>>(gi, w_hh, b_hh, out, gates, B, T);
+    gru_fwd_tc_async_kernel<<<grid, 256, 0, stream>>>(gi, w_hh, b_hh, out, gates, B, T);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }
@@ -290,7 +408,7 @@ extern "C" int tag_gru_bwd_bf16(const float* d_out, const float* out, const floa
                                 void* dgi, void* dgh, void* hprev, int B, int T, cudaStream_t stream) {
     if (B <= 0 || T <= 0) return TAG_ERR_BAD_ARG;
     dim3 grid(NCTA, (B + BS - 1) / BS, 2);
-    gru_bwd_tc_kernel<<<grid, 256, 0, stream>>>(d_out, out, gates, w_hh, (bf16*)dgi, (bf16*)dgh, (bf16*)hprev, B, T);
+    gru_bwd_tc_prod_kernel<<<grid, 256, 0, stream>>>(d_out, out, gates, w_hh, (bf16*)dgi, (bf16*)dgh, (bf16*)hprev, B, T);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }

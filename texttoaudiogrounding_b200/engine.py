@@ -281,8 +281,10 @@ class _SideStream:
 
 
 def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G: EncoderGrads,
-                     side_stream: Optional[torch.cuda.Stream] = None) -> None:
-    """Backward of encoder_forward: accumulates parameter gradients into ``G``."""
+                     side_stream: Optional[torch.cuda.Stream] = None, on_block_done=None) -> None:
+    """Backward of encoder_forward: accumulates parameter gradients into ``G``.  ``on_block_done(blk)`` is called once the
+    kernels producing every gradient of conv block ``blk`` (3 .. 0) and of everything after it are queued — the hook the
+    data-parallel step uses to start the all-reduce of the finished part of the bucket under the remaining backward."""
     side = _SideStream(side_stream)
     dev = d_emb.device
     B, dtype = ctx.B, ctx.dtype
@@ -366,7 +368,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
             call("tag_bn_param_grads", red1, cout, dg, dbt)
             # conv1 backward with the BatchNorm backward applied on the fly (y1 recomputed from x0)
             dx0 = torch.empty(B, H, W, **f32)
-            call("tag_conv_c1_bwd_bn", da1, ctx.x0, Wt.conv[0], aux1[0], aux1[1], aux1[2], aux1[3], red1, bn_tr, G.conv[0], dx0,
+            call("tag_conv_c1_bwd_bn", da1, ctx.x0, Wt.conv[0], aux1[0], aux1[2], aux1[3], red1, bn_tr, G.conv[0], dx0,
                  B, H, W)
             del da1
             red0 = torch.zeros(2 * N_MELS, device=dev, dtype=torch.float64)
@@ -374,6 +376,8 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
             call("tag_bn_bwd_reduce_f32", dx0, ctx.db, aux0[2], aux0[3], B * H, N_MELS, red0)
             dg, dbt = G.bn[0]
             call("tag_bn_param_grads", red0, N_MELS, dg, dbt)
+            if on_block_done is not None:
+                on_block_done(blk)
             continue
         if ops.can_fuse_bn_bwd(w2t, y1):
             # dgrad with the ReLU gate and the BN-backward reductions of bn1 fused into its epilogue
@@ -408,4 +412,8 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
             dp = torch.empty_like(x_in)
             ops.conv_fwd(dy1, w1t, dp, None, False, None, B, H, W, cout, cin, 9)
         del dy1
+        if on_block_done is not None:
+            if blk == 2:
+                side.join()          # the hook may read the weight gradients queued on the side stream so far
+            on_block_done(blk)
     side.join()

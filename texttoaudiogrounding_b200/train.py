@@ -114,6 +114,15 @@ class FusedTrainStep:
         model.register_state_dict_pre_hook(lambda *a, **k: self.flush_counters())
         # weight-gradient GEMMs on a second stream (TAG_B200_OVERLAP=1)
         self.side_stream = torch.cuda.Stream(self.device) if os.environ.get("TAG_B200_OVERLAP", "0") == "1" else None
+        # Data parallel: the ONE logical all-reduce of the flat gradient bucket is issued as two calls so that 97 % of its
+        # bytes travel under the backward pass.  The bucket is ordered [BN affine | conv1_1 .. conv2_2 | conv3_1 .. rnn |
+        # embedding]: everything from conv_block3.conv1.weight on (8.5 M of 8.8 M floats) is final once block 3 has run its
+        # backward, ~2 ms before block 1 finishes; that tail is reduced on a communication stream forked INSIDE the captured
+        # region (NCCL collectives are graph-capturable), the 1 MB head on the main stream after the last kernel.
+        self._ar_split = self._views[18 + 4][0]
+        self._overlap_ar = self.world > 1 and os.environ.get("TAG_B200_NO_AR_OVERLAP", "0") != "1"
+        self._comm_stream = None
+        self._ar_done = None
 
     # ------------------------------------------------------------------ what this step computes
     def _check_model(self, model):
@@ -307,8 +316,36 @@ class FusedTrainStep:
         ws = torch.empty(B, Tp, device=emb.device, dtype=torch.float32)
         call("tag_dot_sigmoid_bwd", d_sim, sim, emb, seq, d_emb, d_seq, ws, B, Tp, D, self.scale)
         call("tag_embed_mean_bwd", text, text_len, d_seq, ew.grad, B, N, D, V)
-        engine.encoder_backward(self.Wt, ectx, d_emb, self.G, side_stream=self.side_stream)
+        engine.encoder_backward(self.Wt, ectx, d_emb, self.G, side_stream=self.side_stream,
+                                on_block_done=self._early_allreduce if self._overlap_ar else None)
+        if self._overlap_ar:
+            self._finish_allreduce()
         self.sim = sim
+
+    def _early_allreduce(self, blk: int) -> None:
+        """After conv block 3 (index 2): all-reduce flat_g[_ar_split:] on the communication stream."""
+        if blk != 2:
+            return
+        tail = self.flat_g[self._ar_split:]
+        if self.device.type != "cuda":
+            torch.distributed.all_reduce(tail, group=self.pg)
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record()
+        self._comm_stream.wait_event(ready)
+        with torch.cuda.stream(self._comm_stream):
+            torch.distributed.all_reduce(tail, group=self.pg)
+            self._ar_done = torch.cuda.Event()
+            self._ar_done.record()
+
+    def _finish_allreduce(self) -> None:
+        """The head of the bucket (BN affine gradients, blocks 1-2) after the last backward kernel; joins the tail."""
+        torch.distributed.all_reduce(self.flat_g[:self._ar_split], group=self.pg)
+        if self._ar_done is not None:
+            torch.cuda.current_stream().wait_event(self._ar_done)
+            self._ar_done = None
 
     def _optim(self):
         self.sumsq.zero_()
@@ -318,7 +355,8 @@ class FusedTrainStep:
              float(self.betas[0]), float(self.betas[1]), float(self.eps), self.norm_out)
 
     def _allreduce(self):
-        if self.world > 1:
+        """The whole bucket in one call — only when the step did not already reduce it under its backward pass."""
+        if self.world > 1 and not self._overlap_ar:
             torch.distributed.all_reduce(self.flat_g, group=self.pg)
 
     def _eager(self, s):
@@ -484,6 +522,7 @@ class WeakFusedTrainStep(FusedTrainStep):
         if model.pooling not in POOL_MODES:
             raise Exception(f"Unsupported pooling {model.pooling}")
         super().__init__(model, **kw)
+        self._overlap_ar = False          # this step's backward issues the bucket's all-reduce in one piece (_allreduce)
         self.pool_mode = POOL_MODES[model.pooling]
         self.frame_weight = frame_weight
         self.loss_clip = torch.zeros((), device=self.device, dtype=torch.float32)
@@ -598,6 +637,7 @@ class AlignFusedTrainStep(FusedTrainStep):
         from .models.align import AUDIO_POOL, TEXT_POOL
         from .models.audio_text_model import AudioTextAlignByWord
         super().__init__(model, **kw)
+        self._overlap_ar = False          # this step's backward issues the bucket's all-reduce in one piece (_allreduce)
         self.word_level = isinstance(model, AudioTextAlignByWord)
         self.a_mode = AUDIO_POOL[model.sim_pooling.audio_pool]
         self.t_mode = TEXT_POOL[model.sim_pooling.text_pool]
