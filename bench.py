@@ -587,7 +587,7 @@ def main():
     # ---- baselines (rank 0, N=1 only): the reference on the host cores and under stock torch.cuda on this GPU
     cpu_baseline, gpu_base = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and name != "clap_infer":
-        del wl
+        wl = None
         torch.cuda.empty_cache()
         clips_s = min(REF_SAMPLE_CLIPS, B)
         v, sec, cores, rkind, _ = cpu_reference_rate(name, clips_s, 2, 1)
@@ -617,6 +617,15 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        # the captured graphs hold NCCL kernels (the all-reduce runs inside the backward graph): release them BEFORE the
+        # communicator goes away, or ncclCommDestroy waits for ever
+        ts = getattr(wl, "ts", None)
+        if ts is not None and hasattr(ts, "close"):
+            ts.close()
+        wl = ts = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

@@ -316,9 +316,10 @@ class FusedTrainStep:
         ws = torch.empty(B, Tp, device=emb.device, dtype=torch.float32)
         call("tag_dot_sigmoid_bwd", d_sim, sim, emb, seq, d_emb, d_seq, ws, B, Tp, D, self.scale)
         call("tag_embed_mean_bwd", text, text_len, d_seq, ew.grad, B, N, D, V)
+        overlap = self._overlap_ar and self.world > 1       # (bench.py profiles one rank alone with world set to 1)
         engine.encoder_backward(self.Wt, ectx, d_emb, self.G, side_stream=self.side_stream,
-                                on_block_done=self._early_allreduce if self._overlap_ar else None)
-        if self._overlap_ar:
+                                on_block_done=self._early_allreduce if overlap else None)
+        if overlap:
             self._finish_allreduce()
         self.sim = sim
 
@@ -432,6 +433,15 @@ class FusedTrainStep:
             self._staging_free.record()
             self._prefetched = None
         return s
+
+    def close(self) -> None:
+        """Drop the captured CUDA graphs.  In data-parallel runs they contain NCCL kernels, so call this (or delete the
+        step object) before ``torch.distributed.destroy_process_group()``."""
+        self._graphs.clear()
+        self._seen.clear()
+        self._static = None
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
 
     def flush_counters(self) -> None:
         """Write the host-side step count into the BatchNorm ``num_batches_tracked`` buffers."""
