@@ -74,15 +74,15 @@ int tag_conv_c1_bwd(const void* dy, const void* x, const float* w, int dtype, fl
  * here), so the raw convolution output is never stored:
  *   tag_c1_moments -> tag_c1_stats_from_moments (stats: double[128] = sum y | sum y^2, the tag_bn_finalize input)
  *   -> tag_bn_finalize -> tag_conv_c1_fwd_act (y = relu(scale * conv(x, w) + shift)).
- * Backward: tag_bn_act_domain_params(gamma, beta) gives the (scale, shift, mean, invstd) quadruple [4][C] with which the
- * fused reduce of tag_conv_tc_fwd_halo reads the saved ACTIVATION as its bn_y; tag_conv_c1_bwd_bn then takes the gated
- * gradient g, recomputes conv(x, w), applies the BatchNorm backward (red = the fused reduce's double[128]) and produces
- * dw / dx — autograd of conv2d + batch_norm + relu without the intermediate tensors. */
+ * Backward: the fused reduce of tag_conv_tc_fwd_halo reads the saved ACTIVATION (bn_act) and tag_bn_red_act_to_xhat
+ * converts its sums (red[C + c] = sum g * a  ->  sum g * xhat = (sum g * a - beta * sum g) / gamma, in place);
+ * tag_conv_c1_bwd_bn then takes the gated gradient g, recomputes conv(x, w), applies the BatchNorm backward (red = those
+ * double[128]) and produces dw / dx — autograd of conv2d + batch_norm + relu without the intermediate tensors. */
 int tag_c1_moments(const void* x, int dtype, int B, int H, int W, double* mom, cudaStream_t stream);
 int tag_c1_stats_from_moments(const double* mom, const float* w, double* stats, cudaStream_t stream);
 int tag_conv_c1_fwd_act(const void* x, const float* w, const float* scale, const float* shift, void* y, int dtype,
                         int B, int H, int W, cudaStream_t stream);
-int tag_bn_act_domain_params(const float* gamma, const float* beta, int C, float* out, cudaStream_t stream);
+int tag_bn_red_act_to_xhat(double* red, const float* gamma, const float* beta, int C, cudaStream_t stream);
 int tag_conv_c1_bwd_bn(const void* g, const void* x, const float* w, const float* scale, const float* mean,
                        const float* invstd, const double* red, int bn_training, float* dw, float* dx, int B,
                        int H, int W, cudaStream_t stream);
@@ -106,13 +106,11 @@ int tag_conv_tc_wgrad64(const void* dy, const void* x, float* dw, int B, int H, 
                         cudaStream_t stream);
 /* 3x3 only: same result as tag_conv_tc_fwd(taps=9, no bias/relu) with the input halo tile re-used
  * across the three vertical taps (16x8-pixel output tiles; W must be a multiple of 8).
- * Optional fused ReLU+BatchNorm backward (dgrad use): with bn_y (the BN input, bf16 NHWC [B,H,W,Cout]) and
- * its per-channel scale/shift/mean/invstd, the output is gated by the ReLU mask and `stats` receives
- * dbeta = sum g and dgamma = sum g*xhat (the reduce pass of tag_bn_relu_pool_bwd, mode 0, no pooling). */
+ * Optional fused ReLU+BatchNorm backward (dgrad use): with bn_act = the SAVED ACTIVATION a = relu(bn(.)) of the layer
+ * whose output gradient this dgrad produces (bf16 NHWC [B,H,W,Cout]), the output is gated by a > 0 and `stats` receives
+ * sum g and sum g * a per channel (activation domain; tag_bn_red_act_to_xhat converts the second into dgamma). */
 int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, double* stats, int B, int H,
-                         int W, int Cin, int Cout, const void* bn_y, const float* bn_scale,
-                         const float* bn_shift, const float* bn_mean, const float* bn_invstd,
-                         cudaStream_t stream);
+                         int W, int Cin, int Cout, const void* bn_act, cudaStream_t stream);
 /* Scheduling knob of tag_conv_tc_fwd_halo (same results either way): 1 (default) = layers whose weights stream
  * (Cin >= 128) run on CTA PAIRS — a 2-CTA cluster computes a 256-pixel tile with cta_group::2 tcgen05 MMAs, each CTA
  * loading half of every weight tile; 0 = one CTA per 128-pixel tile everywhere. */

@@ -226,11 +226,10 @@ def test_c1_one_pass_layer_statistics_forward_and_backward(B, H):
         # dy1 is rounded to bf16 before the two products (as the unfused path stores it)
         assert rel_err(dw.cpu().reshape(C, 1, 3, 3), wr.grad) < 6e-3, training
         assert rel_err(dx.cpu().reshape(B, 1, H, W), xr.grad) < 6e-3, training
-    # ---- activation-domain BatchNorm parameters: gate a > 0, xhat = (a - beta) / gamma
-    out = torch.empty(4, C, device="cuda")
-    ops.call("tag_bn_act_domain_params", gamma.cuda(), beta.cuda(), C, out)
-    assert torch.equal(out[0].cpu(), torch.ones(C)) and torch.equal(out[1].cpu(), torch.zeros(C))
-    assert torch.equal(out[2].cpu(), beta) and torch.allclose(out[3].cpu(), 1.0 / gamma, rtol=1e-6)
+    # ---- activation-domain reductions -> dgamma: (sum g a - beta sum g) / gamma
+    red = torch.tensor([3.0, -2.0, 5.0, 7.0], dtype=torch.float64).cuda()        # C = 2: [sum g | sum g * a]
+    ops.call("tag_bn_red_act_to_xhat", red, torch.tensor([2.0, 0.0]).cuda(), torch.tensor([0.5, 1.0]).cuda(), 2)
+    assert red.cpu().tolist() == [3.0, -2.0, (5.0 - 0.5 * 3.0) / 2.0, 0.0]
 
 
 @pytest.mark.parametrize("ph,pw,H", [(2, 2, 9), (1, 2, 6), (2, 2, 8)])

@@ -123,6 +123,16 @@ template <> __device__ __forceinline__ void pack4<bf16>(uint4& raw, int sub, con
 }
 __device__ __forceinline__ uint4 ld16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void st16(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+// 256-bit global accesses (sm_100: LDG / STG .256): one instruction moves a whole 32-byte sector per lane, where two
+// 16-byte stores of a strided row pattern reach L2 as two half-filled sector writes
+__device__ __forceinline__ void st32(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ void ld32(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
 
 inline void tag_dropout_params(float p, uint32_t* thresh, float* keep_scale) {
     if (p <= 0.f) { *thresh = 0u; *keep_scale = 1.f; return; }

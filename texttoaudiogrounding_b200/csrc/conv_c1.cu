@@ -650,19 +650,17 @@ __global__ void c1_stats_from_moments_kernel(const double* __restrict__ mom, con
     stats[CO + co] = s2;
 }
 
-// BatchNorm parameters in the ACTIVATION domain: with a = relu(gamma * xhat + beta) saved instead of the BN input, the
-// ReLU gate is a > 0 and xhat = (a - beta) / gamma wherever the gate is open.  Writes the (scale, shift, mean, invstd)
-// quadruple that makes a fused "ReLU + BN backward reduce" epilogue (tag_conv_tc_fwd_halo bn_y = a) compute exactly that:
-// gate fma(a, 1, 0) > 0, xhat = (a - beta) * (1 / gamma).  gamma == 0 (no information about xhat in a) yields xhat = 0.
-__global__ void bn_act_domain_params_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, int C,
-                                            float* __restrict__ out) {
+// Reductions of the fused "ReLU gate + BatchNorm backward" epilogue (tag_conv_tc_fwd_halo with bn_act) are taken in the
+// ACTIVATION domain: red[c] = sum g, red[C + c] = sum g * a with a = relu(gamma * xhat + beta).  g is zero wherever the
+// gate is closed, and a = gamma * xhat + beta wherever it is open, so
+//     sum g * xhat = (sum g * a - beta * sum g) / gamma        (the dgamma of the layer; red[c] is already its dbeta).
+// gamma == 0 leaves no trace of xhat in a: the term is set to 0.
+__global__ void bn_red_act_to_xhat_kernel(double* __restrict__ red, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const float gm = gamma[c];
-    out[c] = 1.f;
-    out[C + c] = 0.f;
-    out[2 * C + c] = beta[c];
-    out[3 * C + c] = gm != 0.f ? 1.f / gm : 0.f;
+    const double gm = (double)gamma[c];
+    red[C + c] = gm != 0.0 ? (red[C + c] - (double)beta[c] * red[c]) / gm : 0.0;
 }
 
 }  // namespace
@@ -687,9 +685,9 @@ extern "C" int tag_c1_stats_from_moments(const double* mom, const float* w, doub
     return TAG_OK;
 }
 
-extern "C" int tag_bn_act_domain_params(const float* gamma, const float* beta, int C, float* out, cudaStream_t stream) {
+extern "C" int tag_bn_red_act_to_xhat(double* red, const float* gamma, const float* beta, int C, cudaStream_t stream) {
     if (C <= 0) return TAG_ERR_BAD_ARG;
-    bn_act_domain_params_kernel<<<(C + 127) / 128, 128, 0, stream>>>(gamma, beta, C, out);
+    bn_red_act_to_xhat_kernel<<<(C + 127) / 128, 128, 0, stream>>>(red, gamma, beta, C);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }

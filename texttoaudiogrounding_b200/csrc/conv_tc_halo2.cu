@@ -24,8 +24,7 @@ struct Halo2Smem {
     static constexpr int BAR_OFFSET = B_OFFSET + B_STAGES * B_HALF_BYTES;
     static constexpr int STATS_OFFSET = BAR_OFFSET + 512;
     static constexpr int TBUF_OFFSET = STATS_OFFSET + 2 * BLOCK_N * 4;
-    static constexpr int BNP_OFFSET = TBUF_OFFSET + 8 * BLOCK_N * 4;
-    static constexpr int TOTAL = BNP_OFFSET + 4 * 512 * 4 + 1024;
+    static constexpr int TOTAL = TBUF_OFFSET + 8 * BLOCK_N * 4 + 1024;
     static_assert(8 * (2 * A_STAGES + 2 * B_STAGES + 4) + 8 <= 512, "barrier block");
     static_assert(B_HALF_BYTES % 1024 == 0, "weight half tiles must keep the 1024 B swizzle alignment");
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
@@ -35,9 +34,7 @@ template <int BLOCK_N, typename TO, int A_STAGES, int B_STAGES, int TPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 conv_tc_fwd_halo2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                          TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W, int Cin, int Cout,
-                         const bf16* __restrict__ bn_y, const float* __restrict__ bn_scale,
-                         const float* __restrict__ bn_shift, const float* __restrict__ bn_mean,
-                         const float* __restrict__ bn_invstd, int dbg) {
+                         const bf16* __restrict__ bn_y, int dbg) {
     using L = Halo2Smem<BLOCK_N, A_STAGES, B_STAGES, TPS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -54,7 +51,6 @@ conv_tc_fwd_halo2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         reinterpret_cast<volatile uint32_t*>(base_ptr + L::BAR_OFFSET + 16 * A_STAGES + 16 * B_STAGES + 32);
     float* s_stats = reinterpret_cast<float*>(base_ptr + L::STATS_OFFSET);
     float* t_buf = reinterpret_cast<float*>(base_ptr + L::TBUF_OFFSET);
-    float* s_bnp = reinterpret_cast<float*>(base_ptr + L::BNP_OFFSET);     // [sc | sh | xs | xo] x Cout
 
     const int warp = threadIdx.x >> 5;
     const uint32_t rank = cluster_ctarank();                  // 0 = leader (issues the MMAs)
@@ -79,15 +75,6 @@ conv_tc_fwd_halo2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     if (warp == 9) tmem_alloc_2sm(tmem_slot, 512);
     if (threadIdx.x < 256)
         for (int i = threadIdx.x; i < 2 * BLOCK_N; i += 256) s_stats[i] = 0.f;
-    if (bn_y != nullptr) {
-        for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
-            const float is = bn_invstd[c];
-            s_bnp[c] = bn_scale[c];
-            s_bnp[512 + c] = bn_shift[c];
-            s_bnp[1024 + c] = is;
-            s_bnp[1536 + c] = -bn_mean[c] * is;
-        }
-    }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();               // barriers initialised and TMEM allocated in BOTH CTAs before any remote signal
@@ -179,7 +166,7 @@ conv_tc_fwd_halo2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         const uint32_t lead_tmem_empty = mapa_u32(tmem_empty, 0);
-        halo_epilogue<BLOCK_N, TO>(tmem_base, tmem_full, t_buf, s_bnp, y, stats, B, H, W, Cout, bn_y, dbg, pair, n_pairs,
+        halo_epilogue<BLOCK_N, TO>(tmem_base, tmem_full, t_buf, y, stats, B, H, W, Cout, bn_y, dbg, pair, n_pairs,
                                    total_tiles, decode,
                                    [&](int acc) { mbar_arrive_cluster(lead_tmem_empty + 8 * acc); });
     }
@@ -192,7 +179,7 @@ conv_tc_fwd_halo2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 
 template <int BLOCK_N, typename TO>
 int launch_halo2(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* stats, int B, int H, int W, int Cin,
-                 int Cout, const void* bn_y, const float* const* bnp, cudaStream_t stream) {
+                 int Cout, const void* bn_y, cudaStream_t stream) {
     constexpr int TPS = BLOCK_N == 256 ? 1 : 3;
     constexpr int A_STAGES = BLOCK_N == 256 ? 5 : (BLOCK_N == 128 ? 6 : 8);
     constexpr int B_STAGES = BLOCK_N == 256 ? 6 : (BLOCK_N == 128 ? 4 : 5);
@@ -209,8 +196,7 @@ int launch_halo2(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* 
     const int max_pairs = sm_count() / 2;
     const int grid = 2 * (total_pairs < max_pairs ? total_pairs : max_pairs);
     static int dbg = getenv("TAG_HALO_DBG") ? atoi(getenv("TAG_HALO_DBG")) : 0;
-    kern<<<grid, 384, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout, (const bf16*)bn_y, bnp[0], bnp[1],
-                                          bnp[2], bnp[3], dbg);
+    kern<<<grid, 384, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout, (const bf16*)bn_y, dbg);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }
@@ -220,11 +206,10 @@ int launch_halo2(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* 
 // CTA-pair launch of the halo convolution; called by tag_conv_tc_fwd_halo (conv_tc_halo.cu) for the layers whose weights
 // stream (Cin >= 128).  tw: tap-major weights [9][Cout][Cin] with box (64, block_n / 2, block_n == 256 ? 1 : 3).
 int tag_halo2_dispatch(const CUtensorMap& tx, const CUtensorMap& tw, void* y, int y_dtype, double* stats, int B, int H,
-                       int W, int Cin, int Cout, int block_n, const void* bn_y, const float* const* bnp,
-                       cudaStream_t stream) {
+                       int W, int Cin, int Cout, int block_n, const void* bn_y, cudaStream_t stream) {
 #define TAG_HALO2(BN_)                                                                                     \
-    (y_dtype == TAG_DTYPE_BF16 ? launch_halo2<BN_, bf16>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, bnp, stream) \
-                               : launch_halo2<BN_, float>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, bnp, stream))
+    (y_dtype == TAG_DTYPE_BF16 ? launch_halo2<BN_, bf16>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, stream) \
+                               : launch_halo2<BN_, float>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, stream))
     if (block_n == 256) return TAG_HALO2(256);
     if (block_n == 128) return TAG_HALO2(128);
     return TAG_HALO2(64);

@@ -1,6 +1,6 @@
 // Epilogue of the halo convolution kernels (conv_tc_halo.cu: one CTA per tile; conv_tc_halo2.cu: a CTA pair per
 // 256-pixel tile with cta_group::2 MMAs): 8 warps drain the fp32 accumulator of one 128-pixel x BLOCK_N tile from
-// TMEM, apply the optional fused "ReLU gate + BatchNorm backward reductions" (bn_y != nullptr), round to the storage
+// TMEM, apply the optional fused "ReLU gate + BatchNorm backward reductions" (bn_y = saved activation), round to the storage
 // type, accumulate per-channel statistics in registers across tiles and store the tile.
 //   decode(tile, n_tile, b, h0, w0): tile -> output-channel tile, image, tile origin (b == B marks a padding tile)
 //   arrive_empty(acc): hand accumulator `acc` back to the MMA issuer (a local or a remote mbarrier arrive)
@@ -12,7 +12,7 @@ namespace {
 constexpr int TILE_H = 16, TILE_W = 8;
 
 template <int BLOCK_N, typename TO, typename Decode, typename ArriveEmpty>
-__device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_full, float* t_buf, const float* s_bnp,
+__device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_full, float* t_buf,
                                               TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W,
                                               int Cout, const bf16* __restrict__ bn_y, int dbg, int first_tile,
                                               int tile_stride, int total_tiles, Decode decode,
@@ -83,7 +83,8 @@ __device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_
         auto fetch_y = [&](int cc_) {
             const bf16* p = yin_row + (chalf * CPW + cc_) * 32;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ynext[j] = (valid && cc_ < CPW) ? ld16(p + 8 * j) : make_uint4(0u, 0u, 0u, 0u);
+            for (int j = 0; j < 4; ++j) ynext[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (valid && cc_ < CPW) { ld32(p, ynext[0], ynext[1]); ld32(p + 16, ynext[2], ynext[3]); }
         };
         if (bn_y != nullptr) fetch_y(0);
         mbar_wait(tmem_full + 8 * acc, acc_phase);
@@ -105,13 +106,14 @@ __device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_
                 if (lane == 0) arrive_empty(acc);
             }
             float v[32];                             // the values as stored (rounded to TO, gated)
-            float q[32];                             // second statistic's factor: v (plain) or xhat (fused BN bwd)
+            float q[32];                             // second statistic's factor: v (plain) or the activation (fused BN bwd)
             const bool fused = bn_y != nullptr;
             if (fused) {
-                // fused "ReLU + BatchNorm backward, reduce pass": this kernel is the dgrad producing
-                // d(relu(bn(y))); gate it with the ReLU mask recomputed from y and accumulate
-                // dbeta = sum g and dgamma = sum g * xhat instead of the plain statistics
-                const int cbase = n_tile * BLOCK_N + c * 32;
+                // fused "ReLU + BatchNorm backward, reduce pass": this kernel is the dgrad producing d(relu(bn(.))).
+                // bn_y is the SAVED ACTIVATION a = relu(gamma * xhat + beta) of that layer: the ReLU gate is a > 0 and the
+                // two reductions are taken in the activation domain, sum g and sum g * a — no per-channel parameter is
+                // touched per element (32 LDS.128 per chunk paced the narrow layers); tag_bn_red_act_to_xhat turns them
+                // into dbeta = sum g, dgamma = sum g * xhat = (sum g * a - beta * sum g) / gamma afterwards.
                 uint4 yraw[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) yraw[j] = ynext[j];
@@ -120,18 +122,11 @@ __device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_
                 for (int j4 = 0; j4 < 8; ++j4) {
                     float yv[4];
                     unpack4<bf16>(yraw[j4 >> 1], j4 & 1, yv);
-                    const float4 sc = *reinterpret_cast<const float4*>(s_bnp + cbase + j4 * 4);
-                    const float4 sh = *reinterpret_cast<const float4*>(s_bnp + 512 + cbase + j4 * 4);
-                    const float4 xs = *reinterpret_cast<const float4*>(s_bnp + 1024 + cbase + j4 * 4);
-                    const float4 xo = *reinterpret_cast<const float4*>(s_bnp + 1536 + cbase + j4 * 4);
-                    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-                    const float xsv[4] = {xs.x, xs.y, xs.z, xs.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int j = j4 * 4 + e;
-                        const bool on = fmaf(yv[e], scv[e], shv[e]) > 0.f;
-                        r[j] = on ? r[j] : 0u;
-                        q[j] = fmaf(yv[e], xsv[e], xov[e]);
+                        r[j] = yv[e] > 0.f ? r[j] : 0u;
+                        q[j] = yv[e];
                     }
                 }
             }
@@ -176,8 +171,8 @@ __device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_
             }
             if (valid && !(dbg & 1)) {
 #pragma unroll
-                for (int j = 0; j < (sizeof(TO) == 2 ? 4 : 8); ++j)
-                    st16(reinterpret_cast<uint8_t*>(yrow + c * 32) + 16 * j, packed[j]);
+                for (int j = 0; j < (sizeof(TO) == 2 ? 4 : 8); j += 2)
+                    st32(reinterpret_cast<uint8_t*>(yrow + c * 32) + 16 * j, packed[j], packed[j + 1]);
             }
         }
     }

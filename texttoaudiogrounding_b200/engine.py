@@ -356,13 +356,9 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         da1 = torch.empty_like(a1)
         red1 = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
         if cin == 1 and ctx.c1_fused:
-            # the BN input y1 was never stored: the fused reduce reads the saved activation a1 = relu(gamma * xhat + beta)
-            # instead (gate a1 > 0, xhat = (a1 - beta) / gamma where the gate is open)
-            g1, b1 = Wt.bn[1][0], Wt.bn[1][1]
-            actp = torch.empty(4, cout, **f32)
-            call("tag_bn_act_domain_params", g1, b1, cout, actp)
-            ops.conv_fwd(dy2, w2t, da1, None, False, red1, B, H, W, cout, cout, 9,
-                         bn_fuse=(a1, actp[0], actp[1], actp[2], actp[3]))
+            # the BN input y1 was never stored; the fused reduce works on the saved activation a1 anyway
+            ops.conv_fwd(dy2, w2t, da1, None, False, red1, B, H, W, cout, cout, 9, bn_fuse=a1)
+            call("tag_bn_red_act_to_xhat", red1, Wt.bn[1][0], Wt.bn[1][1], cout)
             del dy2
             dg, dbt = G.bn[1]
             call("tag_bn_param_grads", red1, cout, dg, dbt)
@@ -379,10 +375,10 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
             if on_block_done is not None:
                 on_block_done(blk)
             continue
-        if ops.can_fuse_bn_bwd(w2t, y1):
-            # dgrad with the ReLU gate and the BN-backward reductions of bn1 fused into its epilogue
-            ops.conv_fwd(dy2, w2t, da1, None, False, red1, B, H, W, cout, cout, 9,
-                         bn_fuse=(y1, aux1[0], aux1[1], aux1[2], aux1[3]))
+        if ops.can_fuse_bn_bwd(w2t, a1):
+            # dgrad with the ReLU gate and the BN-backward reductions of bn1 fused into its epilogue (activation domain)
+            ops.conv_fwd(dy2, w2t, da1, None, False, red1, B, H, W, cout, cout, 9, bn_fuse=a1)
+            call("tag_bn_red_act_to_xhat", red1, Wt.bn[1 + 2 * blk][0], Wt.bn[1 + 2 * blk][1], cout)
         else:
             ops.conv_fwd(dy2, w2t, da1, None, False, None, B, H, W, cout, cout, 9)
             call("tag_bn_relu_pool_bwd", 0, y1, da1, None, ops.dt(y1), aux1[0], aux1[1], aux1[2], aux1[3], red1,

@@ -55,7 +55,8 @@ def tc_eligible(W: int, Cin: int, Cout: int) -> bool:
 
 def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps, bn_fuse=None):
     """Dispatch on the weight dtype: bf16 weights -> tcgen05 kernel, fp32 weights -> SIMT kernel.
-    ``bn_fuse`` = (bn_y, scale, shift, mean, invstd): fused ReLU+BN backward reduce (halo kernel only)."""
+    ``bn_fuse`` = the saved activation relu(bn(.)) of the layer this dgrad differentiates through: output gated by
+    a > 0, ``stats`` = (sum g | sum g * a) — the fused ReLU + BN-backward reduce of the halo kernel."""
     if getattr(w, "_tag_x3", False):
         # fp32 activations x split-bf16 weights: fp32-accurate product on the bf16 tensor cores (csrc/split.cu)
         if x.dtype != torch.float32 or y.dtype != torch.float32 or stats is not None or bn_fuse is not None:
@@ -64,7 +65,7 @@ def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps, bn_fuse=None)
         call("tag_split_bf16x3", x, xs, B * H * W, Cin, 0, 0)
         annotate(f"fwd M={B * H * W} N={Cout} K={taps * 3 * Cin}", 2.0 * B * H * W * Cout * taps * 3 * Cin)
         if taps == 9:
-            call("tag_conv_tc_fwd_halo", xs, w, y, dt(y), None, B, H, W, 3 * Cin, Cout, None, None, None, None, None)
+            call("tag_conv_tc_fwd_halo", xs, w, y, dt(y), None, B, H, W, 3 * Cin, Cout, None)
         else:
             call("tag_conv_tc_fwd", xs, w, y, dt(y), bias, int(relu), None, B, H, W, 3 * Cin, Cout, taps)
         return
@@ -75,8 +76,7 @@ def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps, bn_fuse=None)
         if getattr(w, "_tag_tapmajor", False):
             if taps != 9 or bias is not None or relu or W % 8 != 0:
                 raise _lib.TagError("tap-major weights are only valid for the 3x3 halo kernel")
-            f = bn_fuse or (None, None, None, None, None)
-            call("tag_conv_tc_fwd_halo", x, w, y, dt(y), stats, B, H, W, Cin, Cout, *f)
+            call("tag_conv_tc_fwd_halo", x, w, y, dt(y), stats, B, H, W, Cin, Cout, bn_fuse)
             return
         if bn_fuse is not None:
             raise _lib.TagError("bn_fuse needs the halo kernel")
@@ -87,8 +87,8 @@ def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps, bn_fuse=None)
         call("tag_conv_fwd", x, dt(x), w, y, dt(y), bias, int(relu), stats, B, H, W, Cin, Cout, taps)
 
 
-def can_fuse_bn_bwd(w, y) -> bool:
-    return bool(getattr(w, "_tag_tapmajor", False)) and y.dtype == torch.bfloat16
+def can_fuse_bn_bwd(w, act) -> bool:
+    return bool(getattr(w, "_tag_tapmajor", False)) and act.dtype == torch.bfloat16
 
 
 def conv_wgrad(dy, x, dw, B, H, W, Cin, Cout, taps, splits, tc=None):
