@@ -75,14 +75,15 @@ int tag_conv_c1_bwd(const void* dy, const void* x, const float* w, int dtype, fl
  *   tag_c1_moments -> tag_c1_stats_from_moments (stats: double[128] = sum y | sum y^2, the tag_bn_finalize input)
  *   -> tag_bn_finalize -> tag_conv_c1_fwd_act (y = relu(scale * conv(x, w) + shift)).
  * Backward: the fused reduce of tag_conv_tc_fwd_halo reads the saved ACTIVATION (bn_act) and tag_bn_red_act_to_xhat
- * converts its sums (red[C + c] = sum g * a  ->  sum g * xhat = (sum g * a - beta * sum g) / gamma, in place);
+ * converts its sums in place (red[c] *= sum_scale; red[C + c] = sum g * a -> sum g * xhat = (sum g * a - beta * sum g) / gamma);
  * tag_conv_c1_bwd_bn then takes the gated gradient g, recomputes conv(x, w), applies the BatchNorm backward (red = those
  * double[128]) and produces dw / dx — autograd of conv2d + batch_norm + relu without the intermediate tensors. */
 int tag_c1_moments(const void* x, int dtype, int B, int H, int W, double* mom, cudaStream_t stream);
 int tag_c1_stats_from_moments(const double* mom, const float* w, double* stats, cudaStream_t stream);
 int tag_conv_c1_fwd_act(const void* x, const float* w, const float* scale, const float* shift, void* y, int dtype,
                         int B, int H, int W, cudaStream_t stream);
-int tag_bn_red_act_to_xhat(double* red, const float* gamma, const float* beta, int C, cudaStream_t stream);
+int tag_bn_red_act_to_xhat(double* red, const float* gamma, const float* beta, int C, float sum_scale,
+                           cudaStream_t stream);
 int tag_conv_c1_bwd_bn(const void* g, const void* x, const float* w, const float* scale, const float* mean,
                        const float* invstd, const double* red, int bn_training, float* dw, float* dx, int B,
                        int H, int W, cudaStream_t stream);
@@ -106,11 +107,16 @@ int tag_conv_tc_wgrad64(const void* dy, const void* x, float* dw, int B, int H, 
                         cudaStream_t stream);
 /* 3x3 only: same result as tag_conv_tc_fwd(taps=9, no bias/relu) with the input halo tile re-used
  * across the three vertical taps (16x8-pixel output tiles; W must be a multiple of 8).
- * Optional fused ReLU+BatchNorm backward (dgrad use): with bn_act = the SAVED ACTIVATION a = relu(bn(.)) of the layer
- * whose output gradient this dgrad produces (bf16 NHWC [B,H,W,Cout]), the output is gated by a > 0 and `stats` receives
- * sum g and sum g * a per channel (activation domain; tag_bn_red_act_to_xhat converts the second into dgamma). */
+ * Optional fused BatchNorm-backward reductions in the epilogue (dgrad use; `stats` receives two sums per channel):
+ *   bn_act only        : this dgrad's output is d(relu(bn(.))), bn_act = that layer's SAVED ACTIVATION a (bf16 NHWC
+ *                        [B,H,W,Cout]): the output is gated by a > 0; stats = sum g | sum g * a.
+ *   bn_act + pool_cnt  : this dgrad's output is d(dropout(pool(relu(bn(.))))), bn_act = the saved POOLED output p of that
+ *                        layer, pool_cnt = its open-gate code (uint8, tag_bn_relu_pool_fwd): stats = sum dout * cnt |
+ *                        sum dout * p, i.e. the same two sums for the pooled layer (4 sum g / keep_scale | sum g * a)
+ *                        without a pass over its full-resolution input.
+ * tag_bn_red_act_to_xhat turns either pair into (dbeta, dgamma) (sum_scale = 1, or keep_scale / 4 for the pooled form). */
 int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, double* stats, int B, int H,
-                         int W, int Cin, int Cout, const void* bn_act, cudaStream_t stream);
+                         int W, int Cin, int Cout, const void* bn_act, const void* pool_cnt, cudaStream_t stream);
 /* Scheduling knob of tag_conv_tc_fwd_halo (same results either way): 1 (default) = layers whose weights stream
  * (Cin >= 128) run on CTA PAIRS — a 2-CTA cluster computes a 256-pixel tile with cta_group::2 tcgen05 MMAs, each CTA
  * loading half of every weight tile; 0 = one CTA per 128-pixel tile everywhere. */
@@ -125,7 +131,10 @@ int tag_weight_prep_tapmajor_x3(const float* w, void* out, int Co, int Ci, cudaS
 int tag_weight_flip_transpose_bf16(const float* w, void* wt, int Co, int Ci, int taps, cudaStream_t stream);
 
 /* ---- BN + ReLU + avg+max pool + dropout — models/panns.py:50-58, audio_encoder.py:202-211 */
-int tag_bn_relu_pool_fwd(const void* y, void* out, int dtype, const float* scale, const float* shift,
+/* cnt (optional, uint8 [B, H/ph, W/pw, C]): per output element 4 * (n / (ph pw) + [n > 0]), n = the number of window
+ * elements with an open ReLU gate, 0 if the element was dropped — with `out` itself all that the backward reductions of
+ * the layer need (see tag_conv_tc_fwd_halo, pool_cnt). */
+int tag_bn_relu_pool_fwd(const void* y, void* out, void* cnt, int dtype, const float* scale, const float* shift,
                          int B, int H, int W, int C, int ph, int pw, float dropout_p, uint64_t seed,
                          const uint64_t* seed_dev, cudaStream_t stream);
 int tag_bn_relu_pool_bwd(int mode, const void* y, const void* dout, void* dy, int dtype,

@@ -104,7 +104,7 @@ def main():
         Ho, Wo = H // ph, W // pw
         p = torch.empty(B, Ho, Wo, C, device=dev, dtype=bf)
         report(f"bn_relu_pool_fwd {H}x{W}x{C} pool{ph}{pw}",
-               timeit(lambda: call("tag_bn_relu_pool_fwd", y, p, ops.BF16, sc, sh, B, H, W, C, ph, pw, 0.2, 123, seed_dev)),
+               timeit(lambda: call("tag_bn_relu_pool_fwd", y, p, None, ops.BF16, sc, sh, B, H, W, C, ph, pw, 0.2, 123, seed_dev)),
                nb + p.numel() * 2)
         dp = torch.randn(B, Ho, Wo, C, device=dev).to(bf)
         red = torch.zeros(2 * C, device=dev, dtype=torch.float64)

@@ -228,8 +228,11 @@ def test_c1_one_pass_layer_statistics_forward_and_backward(B, H):
         assert rel_err(dx.cpu().reshape(B, 1, H, W), xr.grad) < 6e-3, training
     # ---- activation-domain reductions -> dgamma: (sum g a - beta sum g) / gamma
     red = torch.tensor([3.0, -2.0, 5.0, 7.0], dtype=torch.float64).cuda()        # C = 2: [sum g | sum g * a]
-    ops.call("tag_bn_red_act_to_xhat", red, torch.tensor([2.0, 0.0]).cuda(), torch.tensor([0.5, 1.0]).cuda(), 2)
+    ops.call("tag_bn_red_act_to_xhat", red, torch.tensor([2.0, 0.0]).cuda(), torch.tensor([0.5, 1.0]).cuda(), 2, 1.0)
     assert red.cpu().tolist() == [3.0, -2.0, (5.0 - 0.5 * 3.0) / 2.0, 0.0]
+    red = torch.tensor([3.0, -2.0, 5.0, 7.0], dtype=torch.float64).cuda()        # with a dropout keep scale on sum g
+    ops.call("tag_bn_red_act_to_xhat", red, torch.tensor([2.0, 4.0]).cuda(), torch.tensor([0.5, 1.0]).cuda(), 2, 1.25)
+    assert red.cpu().tolist() == [3.75, -2.5, (5.0 - 0.5 * 3.75) / 2.0, (7.0 + 2.5) / 4.0]
 
 
 @pytest.mark.parametrize("ph,pw,H", [(2, 2, 9), (1, 2, 6), (2, 2, 8)])
@@ -253,7 +256,7 @@ def test_bn_relu_pool_fwd_bwd_matches_torch_autograd(ph, pw, H):
     np.testing.assert_allclose(rv.cpu().numpy(), ref_rv.numpy(), rtol=1e-4)
     Ho, Wo = H // ph, W // pw
     pn = torch.empty(B, Ho, Wo, C, device="cuda")
-    ops.call("tag_bn_relu_pool_fwd", yn, pn, 0, aux[0], aux[1], B, H, W, C, ph, pw, 0.0, 0, None)
+    ops.call("tag_bn_relu_pool_fwd", yn, pn, None, 0, aux[0], aux[1], B, H, W, C, ph, pw, 0.0, 0, None)
     assert rel_err(pn.permute(0, 3, 1, 2).cpu(), p.detach()) < 1e-5
     dpn = dp.permute(0, 2, 3, 1).contiguous().cuda()
     red = torch.zeros(2 * C, device="cuda", dtype=torch.float64)

@@ -205,7 +205,7 @@ def test_halo_dgrad_with_fused_bn_relu_backward_reduce(B, H, W, C, halo_mode):
     g_f = torch.empty_like(da)
     red = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
     ops.conv_fwd(dy, wt, g_f, None, False, red, B, H, W, C, C, 9, bn_fuse=a1)
-    ops.call("tag_bn_red_act_to_xhat", red, gamma, beta, C)
+    ops.call("tag_bn_red_act_to_xhat", red, gamma, beta, C, 1.0)
     torch.cuda.synchronize()
     mask = a1.float() > 0
     assert torch.equal(g_f.float(), torch.where(mask, da.float(), torch.zeros_like(da.float())))
@@ -213,6 +213,49 @@ def test_halo_dgrad_with_fused_bn_relu_backward_reduce(B, H, W, C, halo_mode):
     # rounding (2^-9 of |a| / |gamma|)
     np.testing.assert_allclose(red[:C].cpu().numpy(), red_ref[:C].cpu().numpy(), rtol=2e-3, atol=2e-2)
     np.testing.assert_allclose(red[C:].cpu().numpy(), red_ref[C:].cpu().numpy(), rtol=1e-2, atol=0.3)
+
+
+@pytest.mark.parametrize("halo_mode", [True, "single"], indirect=True)
+@pytest.mark.parametrize("B,H,W,Cin,Cout,ph,pw,pdrop", [(2, 21, 16, 128, 256, 2, 2, 0.2), (3, 9, 32, 64, 128, 2, 2, 0.0),
+                                                        (2, 17, 8, 256, 512, 1, 2, 0.2), (1, 16, 8, 128, 128, 1, 2, 0.0)])
+def test_halo_dgrad_with_fused_pooled_bn_backward_reduce(B, H, W, Cin, Cout, ph, pw, pdrop, halo_mode):
+    """The bn2 backward reductions of a pooled block from (dout, pooled output, open-gate counts) in the epilogue of the
+    NEXT block's conv1 dgrad  ==  the stand-alone reduce pass over the full-resolution BatchNorm input (mode 0).
+    Geometry: previous block [B, Hp, Wp, Cin] at full resolution -> pooled [B, H, W, Cin] = input of this conv (Cin -> Cout)."""
+    from texttoaudiogrounding_b200 import ops
+    Hp, Wp = H * ph + (1 if ph == 2 else 0), W * pw            # an odd row that floor-mode pooling drops
+    y2 = _bf(torch.randn(B, Hp, Wp, Cin, generator=g(40))).cuda().bfloat16()
+    gamma = (torch.rand(Cin, generator=g(41)) + 0.5).cuda()
+    gamma[2] = -gamma[2]
+    beta = (torch.randn(Cin, generator=g(42)) * 0.3).cuda()
+    mean, invstd = (torch.randn(Cin, generator=g(43)) * 0.1).cuda(), (torch.rand(Cin, generator=g(44)) + 0.5).cuda()
+    scale, shift = gamma * invstd, beta - mean * gamma * invstd
+    seed = 1234
+    p = torch.empty(B, H, W, Cin, device="cuda", dtype=torch.bfloat16)
+    cnt = torch.empty(B, H, W, Cin, device="cuda", dtype=torch.uint8)
+    ops.call("tag_bn_relu_pool_fwd", y2, p, cnt, 1, scale, shift, B, Hp, Wp, Cin, ph, pw, pdrop, seed, None)
+    assert int(cnt.max()) <= 8 and set(torch.unique(cnt).tolist()) <= ({0, 5, 6, 7, 8} if ph == 2 else {0, 6, 8})
+    if pdrop > 0:
+        dropped = (p.float() == 0) & (cnt == 0)
+        assert 0.1 < dropped.float().mean().item() < 0.6        # dropped elements carry the code 0
+    # the conv whose dgrad produces d(pooled output)
+    dy = _bf(torch.randn(B, H, W, Cout, generator=g(45))).cuda().bfloat16()
+    w32 = (torch.randn(Cout, 3, 3, Cin, generator=g(46)) * (1.0 / (3 * Cin ** 0.5))).cuda()
+    wt = ops.prep_weight_t(w32, Cout, Cin, 9, torch.bfloat16, W)
+    dp = torch.empty(B, H, W, Cin, device="cuda", dtype=torch.bfloat16)
+    red = torch.zeros(2 * Cin, device="cuda", dtype=torch.float64)
+    ops.conv_fwd(dy, wt, dp, None, False, red, B, H, W, Cout, Cin, 9, bn_fuse=(p, cnt))
+    ops.call("tag_bn_red_act_to_xhat", red, gamma, beta, Cin, 0.25 / (1.0 - pdrop) if pdrop > 0 else 0.25)
+    dp_plain = torch.empty_like(dp)
+    ops.conv_fwd(dy, wt, dp_plain, None, False, None, B, H, W, Cout, Cin, 9)
+    assert torch.equal(dp, dp_plain)                            # no gating in this mode
+    red_ref = torch.zeros(2 * Cin, device="cuda", dtype=torch.float64)
+    ops.call("tag_bn_relu_pool_bwd", 0, y2, dp, None, 1, scale, shift, mean, invstd, red_ref, 1, B, Hp, Wp, Cin, ph, pw,
+             pdrop, seed, None)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(red[:Cin].cpu().numpy(), red_ref[:Cin].cpu().numpy(), rtol=2e-3, atol=2e-2)
+    # dgamma through the bf16 pooled output: 2^-9 of |dout * p| / |gamma| per window, a random walk over the windows
+    np.testing.assert_allclose(red[Cin:].cpu().numpy(), red_ref[Cin:].cpu().numpy(), rtol=1e-2, atol=1.0)
 
 
 def test_batched_weight_prep_equals_single_kernels():

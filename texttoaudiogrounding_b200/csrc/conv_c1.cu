@@ -755,12 +755,15 @@ __global__ void c1_stats_from_moments_kernel(const double* __restrict__ mom, con
 // gate is closed, and a = gamma * xhat + beta wherever it is open, so
 //     sum g * xhat = (sum g * a - beta * sum g) / gamma        (the dgamma of the layer; red[c] is already its dbeta).
 // gamma == 0 leaves no trace of xhat in a: the term is set to 0.
+// sum_scale: the pooled form of the reduce delivers sum g / keep_scale of the dropout (a constant), applied here first.
 __global__ void bn_red_act_to_xhat_kernel(double* __restrict__ red, const float* __restrict__ gamma,
-                                          const float* __restrict__ beta, int C) {
+                                          const float* __restrict__ beta, int C, float sum_scale) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double gm = (double)gamma[c];
-    red[C + c] = gm != 0.0 ? (red[C + c] - (double)beta[c] * red[c]) / gm : 0.0;
+    const double sg = red[c] * (double)sum_scale;
+    red[c] = sg;
+    red[C + c] = gm != 0.0 ? (red[C + c] - (double)beta[c] * sg) / gm : 0.0;
 }
 
 }  // namespace
@@ -785,9 +788,10 @@ extern "C" int tag_c1_stats_from_moments(const double* mom, const float* w, doub
     return TAG_OK;
 }
 
-extern "C" int tag_bn_red_act_to_xhat(double* red, const float* gamma, const float* beta, int C, cudaStream_t stream) {
+extern "C" int tag_bn_red_act_to_xhat(double* red, const float* gamma, const float* beta, int C, float sum_scale,
+                                      cudaStream_t stream) {
     if (C <= 0) return TAG_ERR_BAD_ARG;
-    bn_red_act_to_xhat_kernel<<<(C + 127) / 128, 128, 0, stream>>>(red, gamma, beta, C);
+    bn_red_act_to_xhat_kernel<<<(C + 127) / 128, 128, 0, stream>>>(red, gamma, beta, C, sum_scale);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }

@@ -41,7 +41,7 @@ template <int BLOCK_N, typename TO, int B_STAGES, int TPS, bool WRES>
 __global__ void __launch_bounds__(384, 1)
 conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W, int Cin, int Cout,
-                        const bf16* __restrict__ bn_y, int dbg) {
+                        const bf16* __restrict__ bn_y, const uint8_t* __restrict__ pool_cnt, int dbg) {
     using L = HaloSmem<BLOCK_N, B_STAGES, TPS, WRES>;
     constexpr int A_STAGES = L::A_STAGES;
     constexpr bool TWO_ISSUERS = WRES && BLOCK_N == 64 && A_STAGES == 6;      // see the MMA issuer section
@@ -188,7 +188,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-        halo_epilogue<BLOCK_N, TO>(tmem_base, tmem_full, t_buf, y, stats, B, H, W, Cout, bn_y, dbg,
+        halo_epilogue<BLOCK_N, TO>(tmem_base, tmem_full, t_buf, y, stats, B, H, W, Cout, bn_y, pool_cnt, dbg,
                                    (int)blockIdx.x, (int)gridDim.x, total_tiles, decode,
                                    [&](int acc) { mbar_arrive(tmem_empty + 8 * acc); });
     }
@@ -200,7 +200,7 @@ conv_tc_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 
 template <int BLOCK_N, typename TO, bool WRES>
 int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* stats, int B, int H, int W,
-                int Cin, int Cout, const void* bn_y, cudaStream_t stream) {
+                int Cin, int Cout, const void* bn_y, const void* pool_cnt, cudaStream_t stream) {
     constexpr int TPS = BLOCK_N == 256 ? 1 : 3;
     constexpr int B_STAGES = WRES ? 3 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 3 : 5));
     using L = HaloSmem<BLOCK_N, B_STAGES, TPS, WRES>;
@@ -214,7 +214,7 @@ int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* s
     const int total_tiles = B * ((H + TILE_H - 1) / TILE_H) * (W / TILE_W) * (Cout / BLOCK_N);
     const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
     static int dbg = getenv("TAG_HALO_DBG") ? atoi(getenv("TAG_HALO_DBG")) : 0;
-    kern<<<grid, 384, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout, (const bf16*)bn_y, dbg);
+    kern<<<grid, 384, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout, (const bf16*)bn_y, (const uint8_t*)pool_cnt, dbg);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }
@@ -298,7 +298,7 @@ extern "C" int tag_weight_prep_tapmajor_x3(const float* w, void* out, int Co, in
 }
 
 int tag_halo2_dispatch(const CUtensorMap& tx, const CUtensorMap& tw, void* y, int y_dtype, double* stats, int B, int H,
-                       int W, int Cin, int Cout, int block_n, const void* bn_y,
+                       int W, int Cin, int Cout, int block_n, const void* bn_y, const void* pool_cnt,
                        cudaStream_t stream);                 // conv_tc_halo2.cu
 
 namespace {
@@ -314,8 +314,10 @@ extern "C" int tag_conv_halo_set_pair_mode(int mode) {
 // 3x3 only, no bias / ReLU.  x: bf16 NHWC, W a multiple of 8; w: bf16 TAP-MAJOR [9][Cout][Cin]
 // (tag_weight_prep_tapmajor_bf16); y bf16 or fp32.
 extern "C" int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, double* stats, int B,
-                                    int H, int W, int Cin, int Cout, const void* bn_act, cudaStream_t stream) {
+                                    int H, int W, int Cin, int Cout, const void* bn_act, const void* pool_cnt,
+                                    cudaStream_t stream) {
     const void* bn_y = bn_act;
+    if (pool_cnt != nullptr && bn_act == nullptr) return TAG_ERR_BAD_ARG;
     if (Cin % 64 != 0 || Cout % 64 != 0 || W % TILE_W != 0 || B <= 0 || H <= 0) return TAG_ERR_BAD_ARG;
     if (bn_y != nullptr && stats == nullptr) return TAG_ERR_BAD_ARG;
     const int block_n = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
@@ -327,13 +329,13 @@ extern "C" int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y
         // weights stream (Cin >= 128): CTA pairs with cta_group::2 MMAs, each CTA loads half of every weight tile
         rc = make_w3_tmap(&tw, w, Cout, Cin, block_n / 2, block_n == 256 ? 1 : 3);
         if (rc != TAG_OK) return rc;
-        return tag_halo2_dispatch(tx, tw, y, y_dtype, stats, B, H, W, Cin, Cout, block_n, bn_y, stream);
+        return tag_halo2_dispatch(tx, tw, y, y_dtype, stats, B, H, W, Cin, Cout, block_n, bn_y, pool_cnt, stream);
     }
     rc = make_w3_tmap(&tw, w, Cout, Cin, block_n, block_n == 256 ? 1 : 3);
     if (rc != TAG_OK) return rc;
 #define TAG_HALO(BN_, WR_)                                                                               \
-    (y_dtype == TAG_DTYPE_BF16 ? launch_halo<BN_, bf16, WR_>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, stream)  \
-                               : launch_halo<BN_, float, WR_>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, stream))
+    (y_dtype == TAG_DTYPE_BF16 ? launch_halo<BN_, bf16, WR_>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, pool_cnt, stream)  \
+                               : launch_halo<BN_, float, WR_>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, pool_cnt, stream))
     if (block_n == 256) return TAG_HALO(256, false);
     if (block_n == 128) return wres ? TAG_HALO(128, true) : TAG_HALO(128, false);
     return wres ? TAG_HALO(64, true) : TAG_HALO(64, false);

@@ -34,7 +34,7 @@ template <int BLOCK_N, typename TO, int A_STAGES, int B_STAGES, int TPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 conv_tc_fwd_halo2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                          TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W, int Cin, int Cout,
-                         const bf16* __restrict__ bn_y, int dbg) {
+                         const bf16* __restrict__ bn_y, const uint8_t* __restrict__ pool_cnt, int dbg) {
     using L = Halo2Smem<BLOCK_N, A_STAGES, B_STAGES, TPS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -166,7 +166,7 @@ conv_tc_fwd_halo2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         const uint32_t lead_tmem_empty = mapa_u32(tmem_empty, 0);
-        halo_epilogue<BLOCK_N, TO>(tmem_base, tmem_full, t_buf, y, stats, B, H, W, Cout, bn_y, dbg, pair, n_pairs,
+        halo_epilogue<BLOCK_N, TO>(tmem_base, tmem_full, t_buf, y, stats, B, H, W, Cout, bn_y, pool_cnt, dbg, pair, n_pairs,
                                    total_tiles, decode,
                                    [&](int acc) { mbar_arrive_cluster(lead_tmem_empty + 8 * acc); });
     }
@@ -179,7 +179,7 @@ conv_tc_fwd_halo2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 
 template <int BLOCK_N, typename TO>
 int launch_halo2(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* stats, int B, int H, int W, int Cin,
-                 int Cout, const void* bn_y, cudaStream_t stream) {
+                 int Cout, const void* bn_y, const void* pool_cnt, cudaStream_t stream) {
     constexpr int TPS = BLOCK_N == 256 ? 1 : 3;
     constexpr int A_STAGES = BLOCK_N == 256 ? 5 : (BLOCK_N == 128 ? 6 : 8);
     constexpr int B_STAGES = BLOCK_N == 256 ? 6 : (BLOCK_N == 128 ? 4 : 5);
@@ -196,7 +196,7 @@ int launch_halo2(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* 
     const int max_pairs = sm_count() / 2;
     const int grid = 2 * (total_pairs < max_pairs ? total_pairs : max_pairs);
     static int dbg = getenv("TAG_HALO_DBG") ? atoi(getenv("TAG_HALO_DBG")) : 0;
-    kern<<<grid, 384, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout, (const bf16*)bn_y, dbg);
+    kern<<<grid, 384, L::TOTAL, stream>>>(tx, tw, (TO*)y, stats, B, H, W, Cin, Cout, (const bf16*)bn_y, (const uint8_t*)pool_cnt, dbg);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }
@@ -206,10 +206,10 @@ int launch_halo2(const CUtensorMap& tx, const CUtensorMap& tw, void* y, double* 
 // CTA-pair launch of the halo convolution; called by tag_conv_tc_fwd_halo (conv_tc_halo.cu) for the layers whose weights
 // stream (Cin >= 128).  tw: tap-major weights [9][Cout][Cin] with box (64, block_n / 2, block_n == 256 ? 1 : 3).
 int tag_halo2_dispatch(const CUtensorMap& tx, const CUtensorMap& tw, void* y, int y_dtype, double* stats, int B, int H,
-                       int W, int Cin, int Cout, int block_n, const void* bn_y, cudaStream_t stream) {
+                       int W, int Cin, int Cout, int block_n, const void* bn_y, const void* pool_cnt, cudaStream_t stream) {
 #define TAG_HALO2(BN_)                                                                                     \
-    (y_dtype == TAG_DTYPE_BF16 ? launch_halo2<BN_, bf16>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, stream) \
-                               : launch_halo2<BN_, float>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, stream))
+    (y_dtype == TAG_DTYPE_BF16 ? launch_halo2<BN_, bf16>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, pool_cnt, stream) \
+                               : launch_halo2<BN_, float>(tx, tw, y, stats, B, H, W, Cin, Cout, bn_y, pool_cnt, stream))
     if (block_n == 256) return TAG_HALO2(256);
     if (block_n == 128) return TAG_HALO2(128);
     return TAG_HALO2(64);

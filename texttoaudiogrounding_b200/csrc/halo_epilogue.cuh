@@ -2,6 +2,13 @@
 // 256-pixel tile with cta_group::2 MMAs): 8 warps drain the fp32 accumulator of one 128-pixel x BLOCK_N tile from
 // TMEM, apply the optional fused "ReLU gate + BatchNorm backward reductions" (bn_y = saved activation), round to the storage
 // type, accumulate per-channel statistics in registers across tiles and store the tile.
+// Fused reductions (stats != nullptr), selected by the side inputs:
+//   none                : sum v, sum v^2                      (BatchNorm statistics of a forward convolution)
+//   bn_y                : v gated by a > 0; sum v, sum v * a   (a = saved activation of the NEXT op in backward order: this
+//                         dgrad's output is d(relu(bn(.)))  ->  dbeta, dgamma in the activation domain)
+//   bn_y + pool_cnt     : sum v * cnt, sum v * p   (this dgrad's output is d(pool(relu(bn(.)))): p = the saved pooled output,
+//                         cnt = its open-gate code from tag_bn_relu_pool_fwd = 4 x the window's gradient weight; the same
+//                         two sums for the pooled layer, without a pass over its full-resolution input)
 //   decode(tile, n_tile, b, h0, w0): tile -> output-channel tile, image, tile origin (b == B marks a padding tile)
 //   arrive_empty(acc): hand accumulator `acc` back to the MMA issuer (a local or a remote mbarrier arrive)
 #pragma once
@@ -14,7 +21,8 @@ constexpr int TILE_H = 16, TILE_W = 8;
 template <int BLOCK_N, typename TO, typename Decode, typename ArriveEmpty>
 __device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_full, float* t_buf,
                                               TO* __restrict__ y, double* __restrict__ stats, int B, int H, int W,
-                                              int Cout, const bf16* __restrict__ bn_y, int dbg, int first_tile,
+                                              int Cout, const bf16* __restrict__ bn_y,
+                                              const uint8_t* __restrict__ pool_cnt, int dbg, int first_tile,
                                               int tile_stride, int total_tiles, Decode decode,
                                               ArriveEmpty arrive_empty) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,7 +94,14 @@ __device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_
             for (int j = 0; j < 4; ++j) ynext[j] = make_uint4(0u, 0u, 0u, 0u);
             if (valid && cc_ < CPW) { ld32(p, ynext[0], ynext[1]); ld32(p + 16, ynext[2], ynext[3]); }
         };
+        const uint8_t* cnt_row = pool_cnt != nullptr ? pool_cnt + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N : nullptr;
+        uint4 cnext[2];
+        auto fetch_c = [&](int cc_) {
+            cnext[0] = cnext[1] = make_uint4(0u, 0u, 0u, 0u);
+            if (valid && cc_ < CPW) ld32(cnt_row + (chalf * CPW + cc_) * 32, cnext[0], cnext[1]);
+        };
         if (bn_y != nullptr) fetch_y(0);
+        if (pool_cnt != nullptr) fetch_c(0);
         mbar_wait(tmem_full + 8 * acc, acc_phase);
         tc_fence_after();
 #pragma unroll
@@ -108,6 +123,9 @@ __device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_
             float v[32];                             // the values as stored (rounded to TO, gated)
             float q[32];                             // second statistic's factor: v (plain) or the activation (fused BN bwd)
             const bool fused = bn_y != nullptr;
+            const bool pooled = pool_cnt != nullptr;
+            uint4 craw[2];
+            if (pooled) { craw[0] = cnext[0]; craw[1] = cnext[1]; fetch_c(cc + 1); }
             if (fused) {
                 // fused "ReLU + BatchNorm backward, reduce pass": this kernel is the dgrad producing d(relu(bn(.))).
                 // bn_y is the SAVED ACTIVATION a = relu(gamma * xhat + beta) of that layer: the ReLU gate is a > 0 and the
@@ -125,7 +143,7 @@ __device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int j = j4 * 4 + e;
-                        r[j] = yv[e] > 0.f ? r[j] : 0u;
+                        if (!pooled) r[j] = yv[e] > 0.f ? r[j] : 0u;
                         q[j] = yv[e];
                     }
                 }
@@ -148,21 +166,24 @@ __device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_
                 for (int j = 0; j < 32; ++j) { pw[j] = r[j]; v[j] = __uint_as_float(r[j]); }
             }
             if (stats != nullptr) {
+                // the two terms per element: (v, v * v) | (v, v * a) | (v * cnt, v * p)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) q[j] = v[j] * (fused ? q[j] : v[j]);
+                if (pooled) {
+                    const uint32_t* cw = reinterpret_cast<const uint32_t*>(craw);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= (float)((cw[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+                }
                 if (STAGES == 0) {
                     if (valid) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            run_s[cc][j] += v[j];
-                            run_q[cc][j] = fmaf(v[j], fused ? q[j] : v[j], run_q[cc][j]);
-                        }
+                        for (int j = 0; j < 32; ++j) { run_s[cc][j] += v[j]; run_q[cc][j] += q[j]; }
                     }
                 } else {
                     if (edge_tile) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] : 0.f;
+                        for (int j = 0; j < 32; ++j) { v[j] = valid ? v[j] : 0.f; q[j] = valid ? q[j] : 0.f; }
                     }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) q[j] = v[j] * (fused ? q[j] : v[j]);
                     warp_transpose_head<STAGES>(v, lane);
                     warp_transpose_head<STAGES>(q, lane);
 #pragma unroll

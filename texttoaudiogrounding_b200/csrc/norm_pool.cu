@@ -110,8 +110,12 @@ __global__ void scale_shift_act_kernel(const TI* __restrict__ x, TO* __restrict_
 }
 
 // ------------------------------------------------------------------ BN + ReLU + avg+max pool + dropout
-template <typename T, int PH, int PW>
-__global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ y, T* __restrict__ out,
+// cnt (optional, uint8 per output element): 4 * (n / (PH PW) + [n > 0]) with n the number of window elements whose ReLU
+// gate is open (an integer: n + 4 [n > 0] for 2x2, 2 n + 4 [n > 0] for 1x2), or 0 when the output element was dropped —
+// all the backward reduce pass needs besides the output itself: with g the gradient routed back through pool + ReLU,
+//     sum_window g * a = dout * out      and      sum_window g = dout * keep_scale * cnt / 4.
+template <typename T, int PH, int PW, bool CNT>
+__global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ y, T* __restrict__ out, uint8_t* __restrict__ cnt,
                                         const float* __restrict__ scale, const float* __restrict__ shift,
                                         int B, int H, int W, int C, uint64_t seed, const uint64_t* __restrict__ seed_dev, uint32_t thresh,
                                         float keep_scale) {
@@ -129,8 +133,9 @@ __global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ y, T* __restrict__
         load8<float>(scale + cv * 8, sc);
         load8<float>(shift + cv * 8, sh);
         float sum[8], mx[8];
+        uint32_t nopen[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { sum[k] = 0.f; mx[k] = -INFINITY; }
+        for (int k = 0; k < 8; ++k) { sum[k] = 0.f; mx[k] = -INFINITY; nopen[k] = 0u; }
 #pragma unroll
         for (int dh = 0; dh < PH; ++dh)
 #pragma unroll
@@ -142,6 +147,7 @@ __global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ y, T* __restrict__
                     float a = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
                     sum[k] += a;
                     mx[k] = fmaxf(mx[k], a);
+                    if (CNT) nopen[k] += a > 0.f ? 1u : 0u;
                 }
             }
         float o[8];
@@ -154,10 +160,18 @@ __global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ y, T* __restrict__
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             float v = sum[k] * (1.0f / (PH * PW)) + mx[k];
-            if (thresh != 0u) v *= ds[k];
+            if (thresh != 0u) { v *= ds[k]; if (CNT && ds[k] == 0.f) nopen[k] = 0u; }
             o[k] = v;
         }
         store8<T>(out + obase, o);
+        if (CNT) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) nopen[k] = nopen[k] != 0u ? nopen[k] * (4u / (PH * PW)) + 4u : 0u;
+            uint2 c;
+            c.x = nopen[0] | (nopen[1] << 8) | (nopen[2] << 16) | (nopen[3] << 24);
+            c.y = nopen[4] | (nopen[5] << 8) | (nopen[6] << 16) | (nopen[7] << 24);
+            *reinterpret_cast<uint2*>(cnt + obase) = c;
+        }
     }
 }
 
@@ -337,29 +351,37 @@ extern "C" int tag_scale_shift_act(const void* x, int x_dtype, void* y, int y_dt
 }
 
 template <typename T>
-static int pool_fwd_dispatch(const void* y, void* out, const float* scale, const float* shift, int B,
+static int pool_fwd_dispatch(const void* y, void* out, uint8_t* cnt, const float* scale, const float* shift, int B,
                              int H, int W, int C, int ph, int pw, uint64_t seed, const uint64_t* __restrict__ seed_dev, uint32_t thresh,
                              float ks, cudaStream_t stream) {
     const long n = (long)B * (H / ph) * (W / pw) * (C / 8);
     const int blocks = grid_for(n, 256);
-    if (ph == 2 && pw == 2)
-        bn_relu_pool_fwd_kernel<T, 2, 2><<<blocks, 256, 0, stream>>>((const T*)y, (T*)out, scale, shift, B, H, W, C, seed, seed_dev, thresh, ks);
-    else if (ph == 1 && pw == 2)
-        bn_relu_pool_fwd_kernel<T, 1, 2><<<blocks, 256, 0, stream>>>((const T*)y, (T*)out, scale, shift, B, H, W, C, seed, seed_dev, thresh, ks);
+#define TAG_POOL_FWD(PH_, PW_)                                                                                              \
+    do {                                                                                                                    \
+        if (cnt != nullptr)                                                                                                 \
+            bn_relu_pool_fwd_kernel<T, PH_, PW_, true><<<blocks, 256, 0, stream>>>((const T*)y, (T*)out, cnt, scale, shift, B, \
+                                                                                   H, W, C, seed, seed_dev, thresh, ks);     \
+        else                                                                                                                \
+            bn_relu_pool_fwd_kernel<T, PH_, PW_, false><<<blocks, 256, 0, stream>>>((const T*)y, (T*)out, cnt, scale, shift, \
+                                                                                    B, H, W, C, seed, seed_dev, thresh, ks);  \
+    } while (0)
+    if (ph == 2 && pw == 2) TAG_POOL_FWD(2, 2);
+    else if (ph == 1 && pw == 2) TAG_POOL_FWD(1, 2);
+#undef TAG_POOL_FWD
     else
         return TAG_ERR_UNSUPPORTED;
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }
 
-extern "C" int tag_bn_relu_pool_fwd(const void* y, void* out, int dtype, const float* scale,
+extern "C" int tag_bn_relu_pool_fwd(const void* y, void* out, void* cnt, int dtype, const float* scale,
                                     const float* shift, int B, int H, int W, int C, int ph, int pw,
                                     float dropout_p, uint64_t seed, const uint64_t* seed_dev, cudaStream_t stream) {
     if (C % 8 != 0) return TAG_ERR_BAD_ARG;
     uint32_t thresh; float ks;
     dropout_params(dropout_p, &thresh, &ks);
-    if (dtype == TAG_DTYPE_F32) return pool_fwd_dispatch<float>(y, out, scale, shift, B, H, W, C, ph, pw, seed, seed_dev, thresh, ks, stream);
-    return pool_fwd_dispatch<bf16>(y, out, scale, shift, B, H, W, C, ph, pw, seed, seed_dev, thresh, ks, stream);
+    if (dtype == TAG_DTYPE_F32) return pool_fwd_dispatch<float>(y, out, (uint8_t*)cnt, scale, shift, B, H, W, C, ph, pw, seed, seed_dev, thresh, ks, stream);
+    return pool_fwd_dispatch<bf16>(y, out, (uint8_t*)cnt, scale, shift, B, H, W, C, ph, pw, seed, seed_dev, thresh, ks, stream);
 }
 
 

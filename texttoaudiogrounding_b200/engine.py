@@ -83,6 +83,7 @@ class EncoderCtx:
     out: torch.Tensor = None
     gates: torch.Tensor = None
     c1_fused: bool = False                          # block 1: y[0] is None, a[0] = relu(bn1(conv1)) in one pass
+    pcnt: list = field(default_factory=list)        # per block: open-gate counts of the pooling windows (uint8) or None
 
 
 def _seed_for(seed: int, layer: int) -> int:
@@ -181,6 +182,8 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
     c1_fused = ops.USE_C1_FUSE and (not save or (dtype == torch.bfloat16 and ops.USE_TC and ops.USE_HALO))
     if save:
         ctx.c1_fused = c1_fused
+    # the bn2 backward reductions of blocks 1-3 ride in the epilogue of the next block's conv1 dgrad (halo kernel)
+    pool_fused = dtype == torch.bfloat16 and ops.USE_TC and ops.USE_HALO and ops.USE_POOL_FUSE
     for blk, ((cin, cout), (ph, pw)) in enumerate(zip(CHANNELS, POOLS)):
         count = B * H * W
         # conv1
@@ -215,7 +218,9 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
         # bn2 + relu + pool + dropout
         Ho, Wo = H // ph, W // pw
         p = torch.empty(B, Ho, Wo, cout, **act)
-        call("tag_bn_relu_pool_fwd", y2, p, ops.dt(p), aux2[0], aux2[1], B, H, W, cout, ph, pw,
+        # open-gate counts of the pooling windows: with p itself all the backward reductions of bn2 need (engine backward)
+        pcnt = torch.empty(B, Ho, Wo, cout, device=dev, dtype=torch.uint8) if (save and pool_fused) else None
+        call("tag_bn_relu_pool_fwd", y2, p, pcnt, ops.dt(p), aux2[0], aux2[1], B, H, W, cout, ph, pw,
              P_BLOCK if use_dropout else 0.0, _seed_for(seed, blk), seed_dev)
         if stages is not None:
             stages[f"conv_block{blk + 1}"] = p
@@ -223,6 +228,7 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
             ctx.y += [y1, y2]
             ctx.a.append(a1)
             ctx.p.append(p)
+            ctx.pcnt.append(pcnt)
             ctx.bn_aux += [aux1, aux2]
             ctx.dims.append((H, W))
         x = p
@@ -331,6 +337,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
 
     # ---- conv blocks, last to first
     bn_tr = int(ctx.bn_training)
+    red_next = None
     for blk in range(3, -1, -1):
         cin, cout = CHANNELS[blk]
         ph, pw = POOLS[blk]
@@ -340,10 +347,16 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         aux1, aux2 = ctx.bn_aux[1 + 2 * blk], ctx.bn_aux[2 + 2 * blk]
         P = B * H * W
         # bn2 + relu + pool + dropout
-        red = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
         seed = _seed_for(ctx.seed, blk)
-        call("tag_bn_relu_pool_bwd", 0, y2, dp, None, ops.dt(y2), aux2[0], aux2[1], aux2[2], aux2[3], red,
-             bn_tr, B, H, W, cout, ph, pw, p_blk, seed, ctx.seed_dev)
+        if red_next is not None:
+            # the two reductions came with dp (epilogue of the previous iteration's conv1 dgrad), in the activation domain
+            red, red_next = red_next, None
+            call("tag_bn_red_act_to_xhat", red, Wt.bn[2 + 2 * blk][0], Wt.bn[2 + 2 * blk][1], cout,
+                 0.25 / (1.0 - p_blk) if p_blk > 0.0 else 0.25)        # the codes carry 4 x the weight; dropout keep scale
+        else:
+            red = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
+            call("tag_bn_relu_pool_bwd", 0, y2, dp, None, ops.dt(y2), aux2[0], aux2[1], aux2[2], aux2[3], red,
+                 bn_tr, B, H, W, cout, ph, pw, p_blk, seed, ctx.seed_dev)
         dg, dbt = G.bn[2 + 2 * blk]
         call("tag_bn_param_grads", red, cout, dg, dbt)
         dy2 = torch.empty_like(y2)
@@ -358,7 +371,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         if cin == 1 and ctx.c1_fused:
             # the BN input y1 was never stored; the fused reduce works on the saved activation a1 anyway
             ops.conv_fwd(dy2, w2t, da1, None, False, red1, B, H, W, cout, cout, 9, bn_fuse=a1)
-            call("tag_bn_red_act_to_xhat", red1, Wt.bn[1][0], Wt.bn[1][1], cout)
+            call("tag_bn_red_act_to_xhat", red1, Wt.bn[1][0], Wt.bn[1][1], cout, 1.0)
             del dy2
             dg, dbt = G.bn[1]
             call("tag_bn_param_grads", red1, cout, dg, dbt)
@@ -378,7 +391,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         if ops.can_fuse_bn_bwd(w2t, a1):
             # dgrad with the ReLU gate and the BN-backward reductions of bn1 fused into its epilogue (activation domain)
             ops.conv_fwd(dy2, w2t, da1, None, False, red1, B, H, W, cout, cout, 9, bn_fuse=a1)
-            call("tag_bn_red_act_to_xhat", red1, Wt.bn[1 + 2 * blk][0], Wt.bn[1 + 2 * blk][1], cout)
+            call("tag_bn_red_act_to_xhat", red1, Wt.bn[1 + 2 * blk][0], Wt.bn[1 + 2 * blk][1], cout, 1.0)
         else:
             ops.conv_fwd(dy2, w2t, da1, None, False, None, B, H, W, cout, cout, 9)
             call("tag_bn_relu_pool_bwd", 0, y1, da1, None, ops.dt(y1), aux1[0], aux1[1], aux1[2], aux1[3], red1,
@@ -406,7 +419,13 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
                                             ops.wgrad_splits(P, cin, cout, 9)), dy1, x_in)
             w1t = _operand(Wt, ("t", 2 * blk), lambda: ops.prep_weight_t(Wt.conv[2 * blk], cout, cin, 9, dtype, W))
             dp = torch.empty_like(x_in)
-            ops.conv_fwd(dy1, w1t, dp, None, False, None, B, H, W, cout, cin, 9)
+            pc = ctx.pcnt[blk - 1]
+            if pc is not None and ops.can_fuse_bn_bwd(w1t, x_in):
+                # x_in is the pooled output of block blk - 1: its bn2 backward reductions ride in this dgrad's epilogue
+                red_next = torch.zeros(2 * cin, device=dev, dtype=torch.float64)
+                ops.conv_fwd(dy1, w1t, dp, None, False, red_next, B, H, W, cout, cin, 9, bn_fuse=(x_in, pc))
+            else:
+                ops.conv_fwd(dy1, w1t, dp, None, False, None, B, H, W, cout, cin, 9)
         del dy1
         if on_block_done is not None:
             if blk == 2:

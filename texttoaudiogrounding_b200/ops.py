@@ -47,6 +47,7 @@ def call(name: str, *args) -> None:
 USE_TC = os.environ.get("TAG_B200_NO_TC", "0") != "1"
 USE_HALO = os.environ.get("TAG_B200_NO_HALO", "0") != "1"
 USE_C1_FUSE = os.environ.get("TAG_B200_NO_C1_FUSE", "0") != "1"      # conv_block1.conv1 + bn1 + relu in one pass
+USE_POOL_FUSE = os.environ.get("TAG_B200_NO_POOL_FUSE", "0") != "1"  # bn2 backward reductions in the next dgrad's epilogue
 
 
 def tc_eligible(W: int, Cin: int, Cout: int) -> bool:
@@ -56,7 +57,8 @@ def tc_eligible(W: int, Cin: int, Cout: int) -> bool:
 def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps, bn_fuse=None):
     """Dispatch on the weight dtype: bf16 weights -> tcgen05 kernel, fp32 weights -> SIMT kernel.
     ``bn_fuse`` = the saved activation relu(bn(.)) of the layer this dgrad differentiates through: output gated by
-    a > 0, ``stats`` = (sum g | sum g * a) — the fused ReLU + BN-backward reduce of the halo kernel."""
+    a > 0, ``stats`` = (sum g | sum g * a) — the fused ReLU + BN-backward reduce of the halo kernel; or the triple
+    pair (pooled output, open-gate codes) when the dgrad's output is the gradient of a pooled block output."""
     if getattr(w, "_tag_x3", False):
         # fp32 activations x split-bf16 weights: fp32-accurate product on the bf16 tensor cores (csrc/split.cu)
         if x.dtype != torch.float32 or y.dtype != torch.float32 or stats is not None or bn_fuse is not None:
@@ -65,7 +67,7 @@ def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps, bn_fuse=None)
         call("tag_split_bf16x3", x, xs, B * H * W, Cin, 0, 0)
         annotate(f"fwd M={B * H * W} N={Cout} K={taps * 3 * Cin}", 2.0 * B * H * W * Cout * taps * 3 * Cin)
         if taps == 9:
-            call("tag_conv_tc_fwd_halo", xs, w, y, dt(y), None, B, H, W, 3 * Cin, Cout, None)
+            call("tag_conv_tc_fwd_halo", xs, w, y, dt(y), None, B, H, W, 3 * Cin, Cout, None, None)
         else:
             call("tag_conv_tc_fwd", xs, w, y, dt(y), bias, int(relu), None, B, H, W, 3 * Cin, Cout, taps)
         return
@@ -76,7 +78,8 @@ def conv_fwd(x, w, y, bias, relu, stats, B, H, W, Cin, Cout, taps, bn_fuse=None)
         if getattr(w, "_tag_tapmajor", False):
             if taps != 9 or bias is not None or relu or W % 8 != 0:
                 raise _lib.TagError("tap-major weights are only valid for the 3x3 halo kernel")
-            call("tag_conv_tc_fwd_halo", x, w, y, dt(y), stats, B, H, W, Cin, Cout, bn_fuse)
+            act, cnt = bn_fuse if isinstance(bn_fuse, tuple) else (bn_fuse, None)
+            call("tag_conv_tc_fwd_halo", x, w, y, dt(y), stats, B, H, W, Cin, Cout, act, cnt)
             return
         if bn_fuse is not None:
             raise _lib.TagError("bn_fuse needs the halo kernel")
