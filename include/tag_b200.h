@@ -83,7 +83,7 @@ int tag_c1_stats_from_moments(const double* mom, const float* w, double* stats, 
 int tag_conv_c1_fwd_act(const void* x, const float* w, const float* scale, const float* shift, void* y, int dtype,
                         int B, int H, int W, cudaStream_t stream);
 int tag_bn_red_act_to_xhat(double* red, const float* gamma, const float* beta, int C, float sum_scale,
-                           cudaStream_t stream);
+                           float* dgamma, float* dbeta, cudaStream_t stream);   /* dgamma / dbeta (optional): += */
 int tag_conv_c1_bwd_bn(const void* g, const void* x, const float* w, const float* scale, const float* mean,
                        const float* invstd, const double* red, int bn_training, float* dw, float* dx, int B,
                        int H, int W, cudaStream_t stream);

@@ -228,10 +228,10 @@ def test_c1_one_pass_layer_statistics_forward_and_backward(B, H):
         assert rel_err(dx.cpu().reshape(B, 1, H, W), xr.grad) < 6e-3, training
     # ---- activation-domain reductions -> dgamma: (sum g a - beta sum g) / gamma
     red = torch.tensor([3.0, -2.0, 5.0, 7.0], dtype=torch.float64).cuda()        # C = 2: [sum g | sum g * a]
-    ops.call("tag_bn_red_act_to_xhat", red, torch.tensor([2.0, 0.0]).cuda(), torch.tensor([0.5, 1.0]).cuda(), 2, 1.0)
+    ops.call("tag_bn_red_act_to_xhat", red, torch.tensor([2.0, 0.0]).cuda(), torch.tensor([0.5, 1.0]).cuda(), 2, 1.0, None, None)
     assert red.cpu().tolist() == [3.0, -2.0, (5.0 - 0.5 * 3.0) / 2.0, 0.0]
     red = torch.tensor([3.0, -2.0, 5.0, 7.0], dtype=torch.float64).cuda()        # with a dropout keep scale on sum g
-    ops.call("tag_bn_red_act_to_xhat", red, torch.tensor([2.0, 4.0]).cuda(), torch.tensor([0.5, 1.0]).cuda(), 2, 1.25)
+    ops.call("tag_bn_red_act_to_xhat", red, torch.tensor([2.0, 4.0]).cuda(), torch.tensor([0.5, 1.0]).cuda(), 2, 1.25, None, None)
     assert red.cpu().tolist() == [3.75, -2.5, (5.0 - 0.5 * 3.75) / 2.0, (7.0 + 2.5) / 4.0]
 
 

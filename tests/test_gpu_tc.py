@@ -205,7 +205,7 @@ def test_halo_dgrad_with_fused_bn_relu_backward_reduce(B, H, W, C, halo_mode):
     g_f = torch.empty_like(da)
     red = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
     ops.conv_fwd(dy, wt, g_f, None, False, red, B, H, W, C, C, 9, bn_fuse=a1)
-    ops.call("tag_bn_red_act_to_xhat", red, gamma, beta, C, 1.0)
+    ops.call("tag_bn_red_act_to_xhat", red, gamma, beta, C, 1.0, None, None)
     torch.cuda.synchronize()
     mask = a1.float() > 0
     assert torch.equal(g_f.float(), torch.where(mask, da.float(), torch.zeros_like(da.float())))
@@ -245,7 +245,7 @@ def test_halo_dgrad_with_fused_pooled_bn_backward_reduce(B, H, W, Cin, Cout, ph,
     dp = torch.empty(B, H, W, Cin, device="cuda", dtype=torch.bfloat16)
     red = torch.zeros(2 * Cin, device="cuda", dtype=torch.float64)
     ops.conv_fwd(dy, wt, dp, None, False, red, B, H, W, Cout, Cin, 9, bn_fuse=(p, cnt))
-    ops.call("tag_bn_red_act_to_xhat", red, gamma, beta, Cin, 0.25 / (1.0 - pdrop) if pdrop > 0 else 0.25)
+    ops.call("tag_bn_red_act_to_xhat", red, gamma, beta, Cin, 0.25 / (1.0 - pdrop) if pdrop > 0 else 0.25, None, None)
     dp_plain = torch.empty_like(dp)
     ops.conv_fwd(dy, wt, dp_plain, None, False, None, B, H, W, Cout, Cin, 9)
     assert torch.equal(dp, dp_plain)                            # no gating in this mode

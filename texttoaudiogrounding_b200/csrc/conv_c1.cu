@@ -756,14 +756,19 @@ __global__ void c1_stats_from_moments_kernel(const double* __restrict__ mom, con
 //     sum g * xhat = (sum g * a - beta * sum g) / gamma        (the dgamma of the layer; red[c] is already its dbeta).
 // gamma == 0 leaves no trace of xhat in a: the term is set to 0.
 // sum_scale: the pooled form of the reduce delivers sum g / keep_scale of the dropout (a constant), applied here first.
+// dgamma / dbeta (optional): the parameter gradients are accumulated in the same launch (tag_bn_param_grads).
 __global__ void bn_red_act_to_xhat_kernel(double* __restrict__ red, const float* __restrict__ gamma,
-                                          const float* __restrict__ beta, int C, float sum_scale) {
+                                          const float* __restrict__ beta, int C, float sum_scale,
+                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double gm = (double)gamma[c];
     const double sg = red[c] * (double)sum_scale;
+    const double sx = gm != 0.0 ? (red[C + c] - (double)beta[c] * sg) / gm : 0.0;
     red[c] = sg;
-    red[C + c] = gm != 0.0 ? (red[C + c] - (double)beta[c] * sg) / gm : 0.0;
+    red[C + c] = sx;
+    if (dbeta != nullptr) dbeta[c] += (float)sg;
+    if (dgamma != nullptr) dgamma[c] += (float)sx;
 }
 
 }  // namespace
@@ -789,9 +794,9 @@ extern "C" int tag_c1_stats_from_moments(const double* mom, const float* w, doub
 }
 
 extern "C" int tag_bn_red_act_to_xhat(double* red, const float* gamma, const float* beta, int C, float sum_scale,
-                                      cudaStream_t stream) {
+                                      float* dgamma, float* dbeta, cudaStream_t stream) {
     if (C <= 0) return TAG_ERR_BAD_ARG;
-    bn_red_act_to_xhat_kernel<<<(C + 127) / 128, 128, 0, stream>>>(red, gamma, beta, C, sum_scale);
+    bn_red_act_to_xhat_kernel<<<(C + 127) / 128, 128, 0, stream>>>(red, gamma, beta, C, sum_scale, dgamma, dbeta);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }

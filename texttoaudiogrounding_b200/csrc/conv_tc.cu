@@ -158,17 +158,40 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * BLOCK_N + c * 32, r);
                 tmem_ld_wait();
                 float v[32], q[32];
+                float bv[32];
+                if (bias != nullptr) {
+                    // 8 x 16-byte loads (the same addresses in every lane: one L1 transaction each) instead of 32 scalar ones
+                    const float4* bp = reinterpret_cast<const float4*>(bias + n_tile * BLOCK_N + c * 32);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 t4 = __ldg(bp + j4);
+                        bv[4 * j4] = t4.x; bv[4 * j4 + 1] = t4.y; bv[4 * j4 + 2] = t4.z; bv[4 * j4 + 3] = t4.w;
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float f = __uint_as_float(r[j]);
-                    if (bias != nullptr) f += __ldg(bias + n_tile * BLOCK_N + c * 32 + j);
+                    if (bias != nullptr) f += bv[j];
                     if (relu) f = fmaxf(f, 0.f);
                     f = round_to<TO>(f);
                     v[j] = valid ? f : 0.f;
                 }
                 if (valid) {
+                    // 256-bit stores: whole 32-byte sectors per lane and instruction
+                    if (sizeof(TO) == 2) {
+                        uint4 pk[4];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) store8<TO>(yrow + c * 32 + j, &v[j]);
+                        for (int j = 0; j < 4; ++j) { pack4<TO>(pk[j], 0, &v[8 * j]); pack4<TO>(pk[j], 1, &v[8 * j + 4]); }
+                        st32(yrow + c * 32, pk[0], pk[1]);
+                        st32(yrow + c * 32 + 16, pk[2], pk[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 a4, b4;
+                            pack4<TO>(a4, 0, &v[j]); pack4<TO>(b4, 0, &v[j + 4]);
+                            st32(yrow + c * 32 + j, a4, b4);
+                        }
+                    }
                 }
                 if (stats != nullptr) {
 #pragma unroll

@@ -351,14 +351,16 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         if red_next is not None:
             # the two reductions came with dp (epilogue of the previous iteration's conv1 dgrad), in the activation domain
             red, red_next = red_next, None
+            dg, dbt = G.bn[2 + 2 * blk]
             call("tag_bn_red_act_to_xhat", red, Wt.bn[2 + 2 * blk][0], Wt.bn[2 + 2 * blk][1], cout,
-                 0.25 / (1.0 - p_blk) if p_blk > 0.0 else 0.25)        # the codes carry 4 x the weight; dropout keep scale
+                 0.25 / (1.0 - p_blk) if p_blk > 0.0 else 0.25,        # the codes carry 4 x the weight; dropout keep scale
+                 dg, dbt)
         else:
             red = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
             call("tag_bn_relu_pool_bwd", 0, y2, dp, None, ops.dt(y2), aux2[0], aux2[1], aux2[2], aux2[3], red,
                  bn_tr, B, H, W, cout, ph, pw, p_blk, seed, ctx.seed_dev)
-        dg, dbt = G.bn[2 + 2 * blk]
-        call("tag_bn_param_grads", red, cout, dg, dbt)
+            dg, dbt = G.bn[2 + 2 * blk]
+            call("tag_bn_param_grads", red, cout, dg, dbt)
         dy2 = torch.empty_like(y2)
         call("tag_bn_relu_pool_bwd", 1, y2, dp, dy2, ops.dt(y2), aux2[0], aux2[1], aux2[2], aux2[3], red,
              bn_tr, B, H, W, cout, ph, pw, p_blk, seed, ctx.seed_dev)
@@ -371,10 +373,9 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         if cin == 1 and ctx.c1_fused:
             # the BN input y1 was never stored; the fused reduce works on the saved activation a1 anyway
             ops.conv_fwd(dy2, w2t, da1, None, False, red1, B, H, W, cout, cout, 9, bn_fuse=a1)
-            call("tag_bn_red_act_to_xhat", red1, Wt.bn[1][0], Wt.bn[1][1], cout, 1.0)
-            del dy2
             dg, dbt = G.bn[1]
-            call("tag_bn_param_grads", red1, cout, dg, dbt)
+            call("tag_bn_red_act_to_xhat", red1, Wt.bn[1][0], Wt.bn[1][1], cout, 1.0, dg, dbt)
+            del dy2
             # conv1 backward with the BatchNorm backward applied on the fly (y1 recomputed from x0)
             dx0 = torch.empty(B, H, W, **f32)
             call("tag_conv_c1_bwd_bn", da1, ctx.x0, Wt.conv[0], aux1[0], aux1[2], aux1[3], red1, bn_tr, G.conv[0], dx0,
@@ -391,15 +392,16 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         if ops.can_fuse_bn_bwd(w2t, a1):
             # dgrad with the ReLU gate and the BN-backward reductions of bn1 fused into its epilogue (activation domain)
             ops.conv_fwd(dy2, w2t, da1, None, False, red1, B, H, W, cout, cout, 9, bn_fuse=a1)
-            call("tag_bn_red_act_to_xhat", red1, Wt.bn[1 + 2 * blk][0], Wt.bn[1 + 2 * blk][1], cout, 1.0)
+            dg, dbt = G.bn[1 + 2 * blk]
+            call("tag_bn_red_act_to_xhat", red1, Wt.bn[1 + 2 * blk][0], Wt.bn[1 + 2 * blk][1], cout, 1.0, dg, dbt)
         else:
             ops.conv_fwd(dy2, w2t, da1, None, False, None, B, H, W, cout, cout, 9)
             call("tag_bn_relu_pool_bwd", 0, y1, da1, None, ops.dt(y1), aux1[0], aux1[1], aux1[2], aux1[3], red1,
                  bn_tr, B, H, W, cout, 0, 0, 0.0, 0, None)
+            dg, dbt = G.bn[1 + 2 * blk]
+            call("tag_bn_param_grads", red1, cout, dg, dbt)
         del dy2
         # bn1 + relu
-        dg, dbt = G.bn[1 + 2 * blk]
-        call("tag_bn_param_grads", red1, cout, dg, dbt)
         dy1 = torch.empty_like(y1)
         call("tag_bn_relu_pool_bwd", 1, y1, da1, dy1, ops.dt(y1), aux1[0], aux1[1], aux1[2], aux1[3], red1,
              bn_tr, B, H, W, cout, 0, 0, 0.0, 0, None)
