@@ -21,6 +21,7 @@
 // x N = BLOCK_N output channels of dy, contracted over pixels.  Both operands are MN-major
 // (channels contiguous, pixels strided), which is exactly how NHWC boxes land in shared memory.
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -392,6 +393,166 @@ int launch_tc_fwd(const CUtensorMap& tx, const CUtensorMap& tw, void* y, const f
     return TAG_OK;
 }
 
+// CTA-pair variant (cta_group::2, M = 256): the two CTAs of a cluster take two adjacent 128-row M blocks — (tap, ci 0..127)
+// and (tap, ci 128..255) for Cin >= 256, two taps for Cin = 128 (an odd count pads the last pair) — against the SAME dy tile, of
+// which each CTA loads half the channels: the dy stream L2 -> shared memory, its shared-memory reads per MMA and the MMA
+// instruction count halve.  Barriers as in conv_tc_halo2.cu (loads of both CTAs complete on the leader, multicast commits).
+template <int BLOCK_N, int STAGES, int PIX>
+struct Wg2Smem {
+    static constexpr int BOX_BYTES = PIX * 128;
+    static constexpr int A_BYTES = 2 * BOX_BYTES;
+    static constexpr int B_BYTES = (BLOCK_N / 128) * BOX_BYTES;      // this CTA's half of the dy tile
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+    static_assert(BLOCK_N % 128 == 0, "the pair splits the dy tile in whole 64-channel boxes");
+};
+
+template <int BLOCK_N, int STAGES, int PIX>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                      float* __restrict__ dw, int B, int H, int W, int Cin, int Cout, int taps,
+                      int m_blocks, int n_blocks, int k_tiles_per_split) {
+    using L = Wg2Smem<BLOCK_N, STAGES, PIX>;
+    constexpr int WG_BOX_BYTES = L::BOX_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - raw);
+    const uint32_t full_bar = base + L::BAR_OFFSET;
+    const uint32_t empty_bar = full_bar + 8 * STAGES;
+    const uint32_t tmem_full = empty_bar + 8 * STAGES;
+    const uint32_t tmem_slot = tmem_full + 8;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L::BAR_OFFSET + 16 * STAGES + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int THK = PIX / W > 0 ? PIX / W : 1;
+    const int tiles_h = (H + THK - 1) / THK;
+    const int k_tiles = B * tiles_h;
+    const int m_pairs = (m_blocks + 1) / 2;
+
+    int wi = blockIdx.x >> 1;
+    const int m_pair = wi % m_pairs; wi /= m_pairs;
+    const int n_blk = wi % n_blocks; wi /= n_blocks;
+    const int split = wi;
+    const int kt_begin = split * k_tiles_per_split;
+    const int kt_end = min(k_tiles, kt_begin + k_tiles_per_split);      // >= kt_begin + 1 (host: splits re-derived from kps)
+
+    const int m_blk_raw = 2 * m_pair + (int)rank;
+    const bool blk_live = m_blk_raw < m_blocks;                         // the padding member of an odd count
+    const int m_blk = blk_live ? m_blk_raw : m_blocks - 1;
+    const int per_tap = Cin / 128;
+    const int tap = m_blk / per_tap;
+    const int ci0 = (m_blk % per_tap) * 128;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_dy); }
+    if (warp == 5) tmem_alloc_2sm(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        if (elect_one_sync()) {
+            const uint32_t lead_full = mapa_u32(full_bar, 0);
+            int stage = 0; uint32_t phase = 0;
+            const int dh = taps == 9 ? tap / 3 - 1 : 0;
+            const int dwv = taps == 9 ? tap % 3 - 1 : 0;
+            for (int kt = kt_begin; kt < kt_end; ++kt) {
+                const int b = kt / tiles_h, h0 = (kt - b * tiles_h) * THK;
+                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                if (rank == 0) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * L::STAGE_BYTES);
+                const uint32_t sa = base + stage * L::STAGE_BYTES;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh)
+                    tma_load_4d_2sm(sa + hh * WG_BOX_BYTES, &tmap_x, lead_full + 8 * stage, ci0 + 64 * hh, dwv, h0 + dh, b);
+#pragma unroll
+                for (int j = 0; j < BLOCK_N / 128; ++j)
+                    tma_load_4d_2sm(sa + L::A_BYTES + j * WG_BOX_BYTES, &tmap_dy, lead_full + 8 * stage,
+                                    n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2) + j * 64, 0, h0, b);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 5 && rank == 0) {
+        constexpr uint32_t idesc = make_idesc(256, BLOCK_N, 1, 1);
+        int stage = 0; uint32_t phase = 0;
+        for (int kt = kt_begin; kt < kt_end; ++kt) {
+            mbar_wait(full_bar + 8 * stage, phase);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint32_t sa = base + stage * L::STAGE_BYTES;
+                const uint64_t adesc = make_smem_desc(sa, WG_BOX_BYTES, 1024);
+                const uint64_t bdesc = make_smem_desc(sa + L::A_BYTES, WG_BOX_BYTES, 1024);
+#pragma unroll
+                for (int k = 0; k < PIX / 16; ++k)
+                    umma_bf16_2sm(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc,
+                                  (kt > kt_begin || k > 0) ? 1u : 0u);
+                umma_commit_2sm(empty_bar + 8 * stage, 3);
+                if (kt == kt_end - 1) umma_commit_2sm(tmem_full, 3);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp < 4) {
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int row = warp * 32 + lane;
+        const int ci = ci0 + row;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, r);
+            tmem_ld_wait();
+            if (blk_live) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int co = n_blk * BLOCK_N + c * 32 + j;
+                    atomicAdd(dw + ((long)co * taps + tap) * Cin + ci, __uint_as_float(r[j]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    if (warp == 5) tmem_dealloc_2sm(tmem_base, 256);
+}
+
+template <int BLOCK_N, int PIX>
+int launch_tc_wgrad2(const CUtensorMap& tx, const CUtensorMap& tdy, float* dw, int B, int H, int W, int Cin,
+                     int Cout, int taps, int splits, cudaStream_t stream) {
+    constexpr int STAGE_BYTES = (2 + BLOCK_N / 128) * PIX * 128;
+    constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    using L = Wg2Smem<BLOCK_N, STAGES, PIX>;
+    auto kern = conv_tc_wgrad2_kernel<BLOCK_N, STAGES, PIX>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int THK = PIX / W > 0 ? PIX / W : 1;
+    const int k_tiles = B * ((H + THK - 1) / THK);
+    const int m_blocks = taps * (Cin / 128);
+    const int m_pairs = (m_blocks + 1) / 2;
+    const int n_blocks = Cout / BLOCK_N;
+    if (splits > k_tiles) splits = k_tiles;
+    const int kps = (k_tiles + splits - 1) / splits;
+    splits = (k_tiles + kps - 1) / kps;
+    const long grid = 2l * m_pairs * n_blocks * splits;
+    kern<<<(unsigned)grid, 192, L::TOTAL, stream>>>(tx, tdy, dw, B, H, W, Cin, Cout, taps, m_blocks, n_blocks, kps);
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
 template <int BLOCK_N, int PIX>
 int launch_tc_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, float* dw, int B, int H, int W, int Cin,
                     int Cout, int taps, int splits, cudaStream_t stream) {
@@ -471,6 +632,16 @@ extern "C" int tag_conv_tc_wgrad(const void* dy, const void* x, float* dw, int B
     if (rc != TAG_OK) return rc;
     rc = make_act_tmap(&tdy, dy, B, H, W, Cout, box_w, THK);
     if (rc != TAG_OK) return rc;
+    static const bool pair_ok = getenv("TAG_B200_NO_WGRAD_PAIR") == nullptr;
+    // measured (scripts/bench_conv.py wgrad): pairs win where two M blocks share a tap (Cin >= 256: 1 446 -> 1 620, 1 432 ->
+    // 1 637, 1 544 -> 1 685 TFLOP/s); with Cin = 128 a pair spans two taps and the odd tap count pads a tenth of the grid
+    // (1 134 -> 970), and the one-tap GEMMs of the GRU are launch-bound either way
+    if (pair_ok && taps == 9 && Cin >= 256 && block_n >= 128) {
+#define TAG_WG2(BN_, PIX_) launch_tc_wgrad2<BN_, PIX_>(tx, tdy, dw, B, H, W, Cin, Cout, taps, splits, stream)
+        if (block_n == 256) return TAG_WG2(256, 64);
+        return pix == 128 ? TAG_WG2(128, 128) : TAG_WG2(128, 64);
+#undef TAG_WG2
+    }
 #define TAG_WG(BN_, PIX_) launch_tc_wgrad<BN_, PIX_>(tx, tdy, dw, B, H, W, Cin, Cout, taps, splits, stream)
     if (block_n == 256) return TAG_WG(256, 64);
     if (block_n == 128) return pix == 128 ? TAG_WG(128, 128) : TAG_WG(128, 64);
