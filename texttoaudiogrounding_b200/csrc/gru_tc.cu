@@ -98,7 +98,7 @@ __device__ long long g_gru_timing[64 * 8];
 
 struct FwdSmemA {
     bf16 h[2][BS][HPAD];              // receive buffers: hidden state of all 256 units, [slot][b][k]
-    float part[8][BS][100];           // per-warp partial gate pre-activations
+    float part[2][8][BS][100];        // per-warp partial gate pre-activations, alternating by step (see below)
     bf16 stage[BS][JS];               // this CTA's 32 new units per sequence (64 B rows), source of the st.async pieces
     unsigned long long bar[2];
 };
@@ -106,7 +106,8 @@ struct FwdSmemA {
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(256, 1)
 gru_fwd_tc_async_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                         float* __restrict__ out, float* __restrict__ gates, int B, int T) {
-    __shared__ __align__(16) FwdSmemA s;
+    extern __shared__ __align__(16) uint8_t gru_fwd_smem[];       // 59 KB: above the static limit
+    FwdSmemA& s = *reinterpret_cast<FwdSmemA*>(gru_fwd_smem);
     cg::cluster_group cluster = cg::this_cluster();
     const int cta = (int)cluster.block_rank();
     const int slice = blockIdx.y, dir = blockIdx.z;
@@ -189,20 +190,24 @@ gru_fwd_tc_async_kernel(const float* __restrict__ gi, const float* __restrict__ 
             mma_bf16_16816(d, afrag[mt][0], bfrag[0][0], bfrag[0][1]);
             mma_bf16_16816(d, afrag[mt][1], bfrag[1][0], bfrag[1][1]);
             const int r0 = mt * 16 + (lane >> 2), c0 = (lane & 3) * 2;
-            s.part[warp][c0][r0] = d[0];
-            s.part[warp][c0 + 1][r0] = d[1];
-            s.part[warp][c0][r0 + 8] = d[2];
-            s.part[warp][c0 + 1][r0 + 8] = d[3];
+            s.part[cur][warp][c0][r0] = d[0];
+            s.part[cur][warp][c0 + 1][r0] = d[1];
+            s.part[cur][warp][c0][r0 + 8] = d[2];
+            s.part[cur][warp][c0 + 1][r0 + 8] = d[3];
         }
         GRU_T(2);
+        // The partials alternate between two buffers: a warp that is already through the next step's mbarrier wait writes
+        // the OTHER buffer while a slower warp still sums this one, and the buffer is re-used two steps later, behind the
+        // next step's __syncthreads.  (With one buffer the ordering held only through the mbarrier: the wait needs every
+        // warp's st.async, issued after its reads — correct, but invisible to compute-sanitizer racecheck.)
         __syncthreads();
         GRU_T(3);
         float gh_r = bias_r, gh_z = bias_z, gh_n = bias_n;
 #pragma unroll
         for (int wv = 0; wv < 8; ++wv) {
-            gh_r += s.part[wv][bl][lane];
-            gh_z += s.part[wv][bl][JS + lane];
-            gh_n += s.part[wv][bl][2 * JS + lane];
+            gh_r += s.part[cur][wv][bl][lane];
+            gh_z += s.part[cur][wv][bl][JS + lane];
+            gh_n += s.part[cur][wv][bl][2 * JS + lane];
         }
         GRU_T(4);
         const float r = hw_sigmoid(gi_r + gh_r);
@@ -242,7 +247,9 @@ gru_fwd_tc_async_kernel(const float* __restrict__ gi, const float* __restrict__ 
 constexpr int GPL = 112;              // local gate-gradient row stride (96 rows + pad: 224 B, sequences skew by 24 banks)
 constexpr int SPL = 40;               // staging row stride (80 B: conflict-free 2-byte scatter, 16-byte aligned pieces)
 struct BwdSmemP {
-    bf16 dgl[BS][GPL];                // this CTA's gate gradients of the current step, [b][g * 32 + j]: the B operand
+    bf16 dgl[2][BS][GPL];             // this CTA's gate gradients, [step parity][b][g * 32 + j]: the B operand.  Two buffers:
+                                      // this CTA's mbarrier completes on ONE warp of every CTA, so a fast warp may write the
+                                      // next step's rows while a slow one still multiplies this step's
     bf16 recv[2][NCTA][BS][JS];       // partial dh_prev blocks, [slot][source CTA][b][k local]
     bf16 stage[8][BS][SPL];           // per warp: its outgoing 8 x 32 block
     unsigned long long bar[2];
@@ -283,7 +290,7 @@ gru_bwd_tc_prod_kernel(const float* __restrict__ d_out, const float* __restrict_
             }
         }
     }
-    for (int i = tid; i < BS * GPL; i += 256) (&s.dgl[0][0])[i] = __float2bfloat16_rn(0.f);
+    for (int i = tid; i < 2 * BS * GPL; i += 256) (&s.dgl[0][0][0])[i] = __float2bfloat16_rn(0.f);
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s.bar[0]);
     if (tid == 0) {
         g_mbar_init(bar0, 1); g_mbar_init(bar0 + 8, 1);
@@ -341,7 +348,7 @@ gru_bwd_tc_prod_kernel(const float* __restrict__ d_out, const float* __restrict_
         }
         const bf16 v_r = __float2bfloat16_rn(g_r), v_z = __float2bfloat16_rn(g_z), v_n = __float2bfloat16_rn(g_n);
         const bool exchange = step + 1 < T;       // the last step's dh_prev has no consumer
-        if (exchange) { s.dgl[bl][lane] = v_r; s.dgl[bl][JS + lane] = v_z; s.dgl[bl][2 * JS + lane] = v_n; }
+        if (exchange) { s.dgl[cur][bl][lane] = v_r; s.dgl[cur][bl][JS + lane] = v_z; s.dgl[cur][bl][2 * JS + lane] = v_n; }
         if (b_ok) {
             const long off = (long)step * t_stride;
             bf16* gi_o = dgi_p + off * (2 * G3);
@@ -353,7 +360,7 @@ gru_bwd_tc_prod_kernel(const float* __restrict__ d_out, const float* __restrict_
         if (!exchange) return;
         __syncthreads();                           // all 96 x 8 gate gradients of this CTA are in dgl
         float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-        const bf16* brow = &s.dgl[rho][4 * c];
+        const bf16* brow = &s.dgl[cur][rho][4 * c];
 #pragma unroll
         for (int kt = 0; kt < 6; ++kt) {
             const uint2 b = *reinterpret_cast<const uint2*>(brow + kt * 16);
@@ -399,7 +406,14 @@ extern "C" int tag_gru_fwd_bf16(const float* gi, const float* w_hh, const float*
                                 float* gates, int B, int T, cudaStream_t stream) {
     if (B <= 0 || T <= 0) return TAG_ERR_BAD_ARG;
     dim3 grid(NCTA, (B + BS - 1) / BS, 2);
-    gru_fwd_tc_async_kernel<<<grid, 256, 0, stream>>>(gi, w_hh, b_hh, out, gates, B, T);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gru_fwd_tc_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(FwdSmemA));
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    gru_fwd_tc_async_kernel<<<grid, 256, sizeof(FwdSmemA), stream>>>(gi, w_hh, b_hh, out, gates, B, T);
     TAG_RETURN_IF_LAUNCH_FAILED();
     return TAG_OK;
 }
