@@ -53,15 +53,15 @@ def _worker(rank, world, port, ret):
         assert all(torch.equal(gathered[0], g) for g in gathered)
         # one all-reduce(sum) over the whole bucket; the mean's 1/world is applied by the Adam kernel
         ts.flat_g.copy_(torch.arange(n, dtype=torch.float32) % 7 + rank)
-        overlap, ts._overlap_ar = ts._overlap_ar, False
+        assert ts._ar_in_graph and not ts._overlap_ar   # default: the step issues the one all-reduce itself (last graph node)
+        ts._ar_in_graph = False
         ts._allreduce()
-        ts._overlap_ar = overlap
+        ts._ar_in_graph = True
         expect = (torch.arange(n, dtype=torch.float32) % 7) * world + sum(range(world))
         assert torch.equal(ts.flat_g, expect)
         assert torch.equal(model.audio_encoder.fc1.bias.grad, expect[ts._views[27][0]:ts._views[27][0] + 512])
-        # the same collective as two calls (what runs under the backward pass on GPUs): the tail of the bucket — from
+        # the same collective as two calls (TAG_B200_AR_OVERLAP=1: under the backward pass on GPUs): the tail of the bucket — from
         # conv_block3.conv1.weight on, final once block 3 has run its backward — and then the head
-        assert ts._overlap_ar
         w31 = model.audio_encoder.conv_block3.conv1.weight
         assert ts.flat_g.data_ptr() + 4 * ts._ar_split == w31.grad.data_ptr()
         assert ts._ar_split == 262592 and ts._ar_split < 0.05 * n      # >= 95 % of the bytes travel early (97 % with the full vocabulary)
@@ -72,7 +72,6 @@ def _worker(rank, world, port, ret):
                 assert torch.equal(ts.flat_g, torch.arange(n, dtype=torch.float32) % 5 + 2 * rank)
         ts._finish_allreduce()
         assert torch.equal(ts.flat_g, (torch.arange(n, dtype=torch.float32) % 5) * world + 2 * sum(range(world)))
-        ts._overlap_ar = False                              # (restores the one-call path checked above)
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()

@@ -114,13 +114,17 @@ class FusedTrainStep:
         model.register_state_dict_pre_hook(lambda *a, **k: self.flush_counters())
         # weight-gradient GEMMs on a second stream (TAG_B200_OVERLAP=1)
         self.side_stream = torch.cuda.Stream(self.device) if os.environ.get("TAG_B200_OVERLAP", "0") == "1" else None
-        # Data parallel: the ONE logical all-reduce of the flat gradient bucket is issued as two calls so that 97 % of its
-        # bytes travel under the backward pass.  The bucket is ordered [BN affine | conv1_1 .. conv2_2 | conv3_1 .. rnn |
-        # embedding]: everything from conv_block3.conv1.weight on (8.5 M of 8.8 M floats) is final once block 3 has run its
-        # backward, ~2 ms before block 1 finishes; that tail is reduced on a communication stream forked INSIDE the captured
-        # region (NCCL collectives are graph-capturable), the 1 MB head on the main stream after the last kernel.
+        # Data parallel: ONE all-reduce of the flat gradient bucket per step, captured as the last node of the forward +
+        # backward graph (NCCL collectives are graph-capturable; no host round trip between the two graphs).
+        # TAG_B200_AR_OVERLAP=1 issues it as two calls instead — the bucket is ordered [BN affine | conv1_1 .. conv2_2 |
+        # conv3_1 .. rnn | embedding], everything from conv_block3.conv1.weight on (97 % of the bytes) is final once block 3
+        # has run its backward, and that tail is reduced on a communication stream forked inside the captured region while
+        # blocks 2 and 1 run.  Measured: 9.05 -> 8.98 ms/step on 2 GPUs, but 8.45 -> 8.76 ms on 8 — the compute kernels are
+        # persistent with one CTA per SM (all registers, ~220 KB of shared memory), so NCCL's CTAs cannot co-reside: they
+        # take whole SMs and every convolution launched meanwhile waits for them.  Hence off by default.
         self._ar_split = self._views[18 + 4][0]
-        self._overlap_ar = self.world > 1 and os.environ.get("TAG_B200_NO_AR_OVERLAP", "0") != "1"
+        self._overlap_ar = self.world > 1 and os.environ.get("TAG_B200_AR_OVERLAP", "0") == "1"
+        self._ar_in_graph = True
         self._comm_stream = None
         self._ar_done = None
 
@@ -321,6 +325,8 @@ class FusedTrainStep:
                                 on_block_done=self._early_allreduce if overlap else None)
         if overlap:
             self._finish_allreduce()
+        elif self._ar_in_graph and self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.pg)
         self.sim = sim
 
     def _early_allreduce(self, blk: int) -> None:
@@ -356,8 +362,8 @@ class FusedTrainStep:
              float(self.betas[0]), float(self.betas[1]), float(self.eps), self.norm_out)
 
     def _allreduce(self):
-        """The whole bucket in one call — only when the step did not already reduce it under its backward pass."""
-        if self.world > 1 and not self._overlap_ar:
+        """The whole bucket in one call between the graphs — for the steps whose backward does not issue it itself."""
+        if self.world > 1 and not (self._overlap_ar or self._ar_in_graph):
             torch.distributed.all_reduce(self.flat_g, group=self.pg)
 
     def _eager(self, s):
@@ -532,7 +538,7 @@ class WeakFusedTrainStep(FusedTrainStep):
         if model.pooling not in POOL_MODES:
             raise Exception(f"Unsupported pooling {model.pooling}")
         super().__init__(model, **kw)
-        self._overlap_ar = False          # this step's backward issues the bucket's all-reduce in one piece (_allreduce)
+        self._overlap_ar = self._ar_in_graph = False       # this step reduces the bucket between its two graphs (_allreduce)
         self.pool_mode = POOL_MODES[model.pooling]
         self.frame_weight = frame_weight
         self.loss_clip = torch.zeros((), device=self.device, dtype=torch.float32)
@@ -647,7 +653,7 @@ class AlignFusedTrainStep(FusedTrainStep):
         from .models.align import AUDIO_POOL, TEXT_POOL
         from .models.audio_text_model import AudioTextAlignByWord
         super().__init__(model, **kw)
-        self._overlap_ar = False          # this step's backward issues the bucket's all-reduce in one piece (_allreduce)
+        self._overlap_ar = self._ar_in_graph = False       # this step reduces the bucket between its two graphs (_allreduce)
         self.word_level = isinstance(model, AudioTextAlignByWord)
         self.a_mode = AUDIO_POOL[model.sim_pooling.audio_pool]
         self.t_mode = TEXT_POOL[model.sim_pooling.text_pool]
