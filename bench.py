@@ -314,19 +314,20 @@ class TrainWorkload:
     def e2e(self, steps):
         """two pinned host batches alternate; the copy of step i+1's inputs is started (prefetch) right after step i
         is queued, so it overlaps step i's kernels; every step uploads its own inputs and its own loss is copied to
-        the host and read there one step late, so the host never stalls the queue (software pipelining of the
-        reference's synchronous loss.item())"""
+        the host and read there two steps late, so the host never stalls the queue (software pipelining of the
+        reference's synchronous loss.item(); with one step of slack a 50 ms clock-sampler wake-up or any other host
+        hiccup drains the queue)"""
         ts, hosts = self.ts, self.hosts
         ts.prefetch(hosts[0])
-        pending = None
+        pending = []
         for i in range(steps):
-            handle = ts.step_async(hosts[i % 2])
+            pending.append(ts.step_async(hosts[i % 2]))
             if i + 1 < steps:
                 ts.prefetch(hosts[(i + 1) % 2])
-            if pending is not None:
-                self.last = pending.result()
-            pending = handle
-        self.last = pending.result()
+            if len(pending) > 2:                  # two steps stay queued behind the one whose loss is being read
+                self.last = pending.pop(0).result()
+        for h in pending:
+            self.last = h.result()
 
     def result(self):
         return float(self.ts.loss_out.item())
