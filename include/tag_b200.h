@@ -145,9 +145,12 @@ int tag_bn_relu_pool_bwd(int mode, const void* y, const void* dout, void* dy, in
 /* torch.mean(x, dim=3) + transpose + dropout(0.5) — models/audio_encoder.py:212-215 */
 int tag_freq_mean_fwd(const void* x, void* out, int dtype, long rows, int Wf, int C, float dropout_p,
                       uint64_t seed, const uint64_t* seed_dev, cudaStream_t stream);
+/* pool_out / pool_cnt / red (optional, bf16 dx): dx is the gradient of a pooled block output; accumulate its BatchNorm-backward
+ * sums in the activation domain on the way (red[c] += sum dx * cnt, red[C + c] += sum dx * pool_out), as the pooled form of
+ * tag_conv_tc_fwd_halo does for the blocks whose gradient comes from a convolution. */
 int tag_freq_mean_bwd(const void* dm, int dm_dtype, void* dx, int dx_dtype, long rows, int Wf, int C,
-                      float dropout_p, uint64_t seed, const uint64_t* seed_dev,
-                         cudaStream_t stream);
+                      float dropout_p, uint64_t seed, const uint64_t* seed_dev, const void* pool_out,
+                      const void* pool_cnt, double* red, cudaStream_t stream);
 int tag_dropout_mask(float* mask, long n, float dropout_p, uint64_t seed, const uint64_t* seed_dev,
                          cudaStream_t stream);
 int tag_colsum(const void* x, int dtype, long rows, int C, float* out, cudaStream_t stream);

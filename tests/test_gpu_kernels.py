@@ -235,6 +235,39 @@ def test_c1_one_pass_layer_statistics_forward_and_backward(B, H):
     assert red.cpu().tolist() == [3.75, -2.5, (5.0 - 0.5 * 3.75) / 2.0, (7.0 + 2.5) / 4.0]
 
 
+@pytest.mark.parametrize("pdrop", [0.0, 0.2])
+def test_freq_mean_bwd_with_fused_pooled_bn_backward_sums(pdrop):
+    """Block 4: the gradient of the pooled output comes from the frequency mean; its bn2 backward sums ride along in the
+    activation domain (sum dx * cnt, sum dx * p) and must equal the stand-alone reduce pass over the BatchNorm input."""
+    ops = _ops()
+    B, T, Wp, C = 3, 11, 8, 512                       # pooled [B, T, 4, C] from [B, T, 8, C] with (1, 2) pooling
+    bf = torch.bfloat16
+    y2 = torch.randn(B, T, Wp, C, generator=g(61)).cuda().to(bf)
+    gamma = (torch.rand(C, generator=g(62)) + 0.5).cuda()
+    gamma[5] = -gamma[5]
+    beta = (torch.randn(C, generator=g(63)) * 0.3).cuda()
+    mean, invstd = (torch.randn(C, generator=g(64)) * 0.1).cuda(), (torch.rand(C, generator=g(65)) + 0.5).cuda()
+    scale, shift = gamma * invstd, beta - mean * gamma * invstd
+    p = torch.empty(B, T, Wp // 2, C, device="cuda", dtype=bf)
+    cnt = torch.empty(B, T, Wp // 2, C, device="cuda", dtype=torch.uint8)
+    ops.call("tag_bn_relu_pool_fwd", y2, p, cnt, 1, scale, shift, B, T, Wp, C, 1, 2, pdrop, 77, None)
+    rows = B * T
+    dm = torch.randn(rows, C, generator=g(66)).cuda().to(bf)
+    dp = torch.empty_like(p)
+    red = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    ops.call("tag_freq_mean_bwd", dm, 1, dp, 1, rows, Wp // 2, C, 0.5, 99, None, p, cnt, red)
+    dp_plain = torch.empty_like(p)
+    ops.call("tag_freq_mean_bwd", dm, 1, dp_plain, 1, rows, Wp // 2, C, 0.5, 99, None, None, None, None)
+    assert torch.equal(dp, dp_plain)
+    ops.call("tag_bn_red_act_to_xhat", red, gamma, beta, C, 0.25 / (1.0 - pdrop) if pdrop > 0 else 0.25, None, None)
+    red_ref = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    ops.call("tag_bn_relu_pool_bwd", 0, y2, dp, None, 1, scale, shift, mean, invstd, red_ref, 1, B, T, Wp, C, 1, 2, pdrop,
+             77, None)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(red[:C].cpu().numpy(), red_ref[:C].cpu().numpy(), rtol=2e-3, atol=2e-2)
+    np.testing.assert_allclose(red[C:].cpu().numpy(), red_ref[C:].cpu().numpy(), rtol=1e-2, atol=0.5)
+
+
 @pytest.mark.parametrize("ph,pw,H", [(2, 2, 9), (1, 2, 6), (2, 2, 8)])
 def test_bn_relu_pool_fwd_bwd_matches_torch_autograd(ph, pw, H):
     ops = _ops()

@@ -203,12 +203,19 @@ __global__ void freq_mean_fwd_kernel(const T* __restrict__ x, T* __restrict__ ou
     }
 }
 
-template <typename TI, typename TO>
+// POOLRED: dx is the gradient of block 4's pooled output; with that output p and its open-gate codes cnt (see
+// bn_relu_pool_fwd_kernel) the two BatchNorm-backward sums of the block are accumulated on the way:
+// red[c] += sum dx * cnt, red[C + c] += sum dx * p  (activation domain, converted by tag_bn_red_act_to_xhat) — no pass
+// over the block's full-resolution BatchNorm input.  A thread keeps its 4 channels for the whole grid-stride loop.
+template <typename TI, typename TO, bool POOLRED>
 __global__ void freq_mean_bwd_kernel(const TI* __restrict__ dm, TO* __restrict__ dx, long rows, int Wf,
-                                     int C, uint64_t seed, const uint64_t* __restrict__ seed_dev, uint32_t thresh, float keep_scale) {
+                                     int C, uint64_t seed, const uint64_t* __restrict__ seed_dev, uint32_t thresh, float keep_scale,
+                                     const TO* __restrict__ pool_out, const uint8_t* __restrict__ pool_cnt,
+                                     double* __restrict__ red) {
     if (seed_dev != nullptr) seed += *seed_dev;
     const int CV = C / 4;
     const long n = rows * CV;
+    float rs[4] = {0.f, 0.f, 0.f, 0.f}, rq[4] = {0.f, 0.f, 0.f, 0.f};
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const int cv = (int)(i % CV);
         const long r = i / CV;
@@ -219,7 +226,34 @@ __global__ void freq_mean_bwd_kernel(const TI* __restrict__ dm, TO* __restrict__
             if (thresh != 0u) g[k] *= tag_dropout_scale(seed, (uint64_t)(i * 4 + k), thresh, keep_scale);
             g[k] *= 1.0f / Wf;
         }
-        for (int w = 0; w < Wf; ++w) Vec4<TO>::store(dx + (r * Wf + w) * C + cv * 4, g);
+        for (int w = 0; w < Wf; ++w) {
+            const long o = (r * Wf + w) * C + cv * 4;
+            Vec4<TO>::store(dx + o, g);
+            if (POOLRED) {
+                float p[4];
+                Vec4<TO>::load(pool_out + o, p);
+                const uint32_t cw = *reinterpret_cast<const uint32_t*>(pool_cnt + o);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float v = round_to<TO>(g[k]);                 // the value as stored
+                    rs[k] = fmaf(v, (float)((cw >> (8 * k)) & 0xFFu), rs[k]);
+                    rq[k] = fmaf(v, p[k], rq[k]);
+                }
+            }
+        }
+    }
+    if (POOLRED) {
+        extern __shared__ float s_fr[];                                 // [2][C]
+        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) s_fr[c] = 0.f;
+        __syncthreads();
+        const int cv = (int)((blockIdx.x * (long)blockDim.x + threadIdx.x) % CV);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            atomicAdd(&s_fr[cv * 4 + k], rs[k]);
+            atomicAdd(&s_fr[C + cv * 4 + k], rq[k]);
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) atomicAdd(red + c, (double)s_fr[c]);
     }
 }
 
@@ -400,17 +434,37 @@ extern "C" int tag_freq_mean_fwd(const void* x, void* out, int dtype, long rows,
 }
 
 extern "C" int tag_freq_mean_bwd(const void* dm, int dm_dtype, void* dx, int dx_dtype, long rows, int Wf,
-                                 int C, float dropout_p, uint64_t seed, const uint64_t* seed_dev, cudaStream_t stream) {
+                                 int C, float dropout_p, uint64_t seed, const uint64_t* seed_dev, const void* pool_out,
+                                 const void* pool_cnt, double* red, cudaStream_t stream) {
     if (C % 4 != 0) return TAG_ERR_BAD_ARG;
     uint32_t thresh; float ks;
     dropout_params(dropout_p, &thresh, &ks);
-    const int blocks = grid_for(rows * (C / 4), 256);
+    const int CV = C / 4;
+    if (pool_cnt != nullptr) {
+        // fused BatchNorm-backward sums of the pooled block: bf16 gradient, channels fixed per thread (stride % CV == 0)
+        if (dx_dtype != TAG_DTYPE_BF16 || pool_out == nullptr || red == nullptr || 256 % CV != 0) return TAG_ERR_BAD_ARG;
+        const int blocks = grid_for(rows * CV, 256, 148 * 4);
+        const size_t smem = (size_t)2 * C * sizeof(float);
+        if (dm_dtype == TAG_DTYPE_F32)
+            freq_mean_bwd_kernel<float, bf16, true><<<blocks, 256, smem, stream>>>(
+                (const float*)dm, (bf16*)dx, rows, Wf, C, seed, seed_dev, thresh, ks, (const bf16*)pool_out,
+                (const uint8_t*)pool_cnt, red);
+        else if (dm_dtype == TAG_DTYPE_BF16)
+            freq_mean_bwd_kernel<bf16, bf16, true><<<blocks, 256, smem, stream>>>(
+                (const bf16*)dm, (bf16*)dx, rows, Wf, C, seed, seed_dev, thresh, ks, (const bf16*)pool_out,
+                (const uint8_t*)pool_cnt, red);
+        else
+            return TAG_ERR_BAD_ARG;
+        TAG_RETURN_IF_LAUNCH_FAILED();
+        return TAG_OK;
+    }
+    const int blocks = grid_for(rows * CV, 256);
     if (dm_dtype == TAG_DTYPE_F32 && dx_dtype == TAG_DTYPE_F32)
-        freq_mean_bwd_kernel<float, float><<<blocks, 256, 0, stream>>>((const float*)dm, (float*)dx, rows, Wf, C, seed, seed_dev, thresh, ks);
+        freq_mean_bwd_kernel<float, float, false><<<blocks, 256, 0, stream>>>((const float*)dm, (float*)dx, rows, Wf, C, seed, seed_dev, thresh, ks, nullptr, nullptr, nullptr);
     else if (dm_dtype == TAG_DTYPE_F32 && dx_dtype == TAG_DTYPE_BF16)
-        freq_mean_bwd_kernel<float, bf16><<<blocks, 256, 0, stream>>>((const float*)dm, (bf16*)dx, rows, Wf, C, seed, seed_dev, thresh, ks);
+        freq_mean_bwd_kernel<float, bf16, false><<<blocks, 256, 0, stream>>>((const float*)dm, (bf16*)dx, rows, Wf, C, seed, seed_dev, thresh, ks, nullptr, nullptr, nullptr);
     else if (dm_dtype == TAG_DTYPE_BF16 && dx_dtype == TAG_DTYPE_BF16)
-        freq_mean_bwd_kernel<bf16, bf16><<<blocks, 256, 0, stream>>>((const bf16*)dm, (bf16*)dx, rows, Wf, C, seed, seed_dev, thresh, ks);
+        freq_mean_bwd_kernel<bf16, bf16, false><<<blocks, 256, 0, stream>>>((const bf16*)dm, (bf16*)dx, rows, Wf, C, seed, seed_dev, thresh, ks, nullptr, nullptr, nullptr);
     else
         return TAG_ERR_BAD_ARG;
     TAG_RETURN_IF_LAUNCH_FAILED();

@@ -332,12 +332,18 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
     # ---- frequency mean (+dropout)
     Wf = ctx.p[3].shape[2]
     dp = torch.empty_like(ctx.p[3])
-    call("tag_freq_mean_bwd", dm, ops.dt(dm), dp, ops.dt(dp), rows, Wf, 512, p_fc,
-         _seed_for(ctx.seed, 4), ctx.seed_dev)
+    red_next = None
+    if ctx.pcnt[3] is not None and dp.dtype == torch.bfloat16:
+        # block 4's bn2 backward sums ride along (activation domain), as blocks 1-3 get theirs from the next conv1 dgrad
+        red_next = torch.zeros(2 * CHANNELS[3][1], device=dev, dtype=torch.float64)
+        call("tag_freq_mean_bwd", dm, ops.dt(dm), dp, ops.dt(dp), rows, Wf, 512, p_fc,
+             _seed_for(ctx.seed, 4), ctx.seed_dev, ctx.p[3], ctx.pcnt[3], red_next)
+    else:
+        call("tag_freq_mean_bwd", dm, ops.dt(dm), dp, ops.dt(dp), rows, Wf, 512, p_fc,
+             _seed_for(ctx.seed, 4), ctx.seed_dev, None, None, None)
 
     # ---- conv blocks, last to first
     bn_tr = int(ctx.bn_training)
-    red_next = None
     for blk in range(3, -1, -1):
         cin, cout = CHANNELS[blk]
         ph, pw = POOLS[blk]
