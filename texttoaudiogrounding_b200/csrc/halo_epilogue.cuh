@@ -71,6 +71,48 @@ __device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
     };
+    // Side inputs of the fused reductions (saved activation / pooled output, open-gate codes) are prefetched into registers
+    // one chunk ahead ACROSS tiles: the first chunk of the next tile is requested before this tile's accumulator is even
+    // waited for.  With the request issued at the start of its own tile, a narrow tile (one chunk per warp) paid the whole
+    // global-load latency per tile on top of its arithmetic and held the layer at 39 % tensor-pipe-active.
+    constexpr bool CAN_FUSE = sizeof(TO) == 2;        // the fused reductions exist for bf16 gradients only
+    if (!CAN_FUSE) { bn_y = nullptr; pool_cnt = nullptr; }
+    uint4 ynext[4], cnext[2];
+    const bf16* f_yrow = nullptr;
+    const uint8_t* f_crow = nullptr;
+    bool f_valid = false;
+    const int e_lq = warp & 3, e_chalf = warp >> 2;
+    auto setup_fetch = [&](int tile_) {               // row pointers of this thread in tile `tile_`
+        int nt_, b_, h0_, w0_;
+        decode(tile_, nt_, b_, h0_, w0_);
+        const int row_ = e_lq * 32 + lane;
+        const int h_ = h0_ + (row_ >> 3), w_ = w0_ + (row_ & 7);
+        f_valid = h_ < H && b_ < B;
+        const long off = (((long)b_ * H + h_) * W + w_) * Cout + nt_ * BLOCK_N;
+        f_yrow = bn_y != nullptr ? bn_y + off : nullptr;
+        f_crow = pool_cnt != nullptr ? pool_cnt + off : nullptr;
+    };
+    auto fetch_side = [&](int cc_) {
+        if (bn_y != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ynext[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (f_valid) {
+                const bf16* p = f_yrow + (e_chalf * CPW + cc_) * 32;
+                ld32(p, ynext[0], ynext[1]);
+                ld32(p + 16, ynext[2], ynext[3]);
+            }
+        }
+        if (pool_cnt != nullptr) {
+            cnext[0] = cnext[1] = make_uint4(0u, 0u, 0u, 0u);
+            if (f_valid) ld32(f_crow + (e_chalf * CPW + cc_) * 32, cnext[0], cnext[1]);
+        }
+    };
+    // after the call the registers hold chunk (cc_ + 1) of this tile, or chunk 0 of the next tile of this CTA
+    auto fetch_following = [&](int tile_, int cc_) {
+        if (cc_ + 1 < CPW) { fetch_side(cc_ + 1); return; }
+        if (tile_ + tile_stride < total_tiles) { setup_fetch(tile_ + tile_stride); fetch_side(0); }
+    };
+    if (bn_y != nullptr && first_tile < total_tiles) { setup_fetch(first_tile); fetch_side(0); }
     for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
         int n_tile, b, h0, w0;
         decode(tile, n_tile, b, h0, w0);
@@ -84,24 +126,14 @@ __device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_
         const bool valid = h < H && b < B;
         const bool edge_tile = h0 + TILE_H > H || b >= B;   // tile-uniform: some rows fall off the image
         TO* yrow = y + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N;
-        // fused BN backward: the BN input of this row is prefetched one chunk ahead (the first chunk
-        // before waiting for the accumulator)
-        const bf16* yin_row = bn_y != nullptr ? bn_y + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N : nullptr;
-        uint4 ynext[4];
-        auto fetch_y = [&](int cc_) {
-            const bf16* p = yin_row + (chalf * CPW + cc_) * 32;
+        // chunk 0 of this tile is in ynext / cnext already; take it and request what follows BEFORE waiting for the MMAs
+        uint4 yraw[4], craw[2];
+        if (bn_y != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ynext[j] = make_uint4(0u, 0u, 0u, 0u);
-            if (valid && cc_ < CPW) { ld32(p, ynext[0], ynext[1]); ld32(p + 16, ynext[2], ynext[3]); }
-        };
-        const uint8_t* cnt_row = pool_cnt != nullptr ? pool_cnt + (((long)b * H + h) * W + w) * Cout + n_tile * BLOCK_N : nullptr;
-        uint4 cnext[2];
-        auto fetch_c = [&](int cc_) {
-            cnext[0] = cnext[1] = make_uint4(0u, 0u, 0u, 0u);
-            if (valid && cc_ < CPW) ld32(cnt_row + (chalf * CPW + cc_) * 32, cnext[0], cnext[1]);
-        };
-        if (bn_y != nullptr) fetch_y(0);
-        if (pool_cnt != nullptr) fetch_c(0);
+            for (int j = 0; j < 4; ++j) yraw[j] = ynext[j];
+            craw[0] = cnext[0]; craw[1] = cnext[1];
+            fetch_following(tile, 0);
+        }
         mbar_wait(tmem_full + 8 * acc, acc_phase);
         tc_fence_after();
 #pragma unroll
@@ -124,18 +156,18 @@ __device__ __forceinline__ void halo_epilogue(uint32_t tmem_base, uint32_t tmem_
             float q[32];                             // second statistic's factor: v (plain) or the activation (fused BN bwd)
             const bool fused = bn_y != nullptr;
             const bool pooled = pool_cnt != nullptr;
-            uint4 craw[2];
-            if (pooled) { craw[0] = cnext[0]; craw[1] = cnext[1]; fetch_c(cc + 1); }
+            if (fused && cc > 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) yraw[j] = ynext[j];
+                craw[0] = cnext[0]; craw[1] = cnext[1];
+                fetch_following(tile, cc);
+            }
             if (fused) {
                 // fused "ReLU + BatchNorm backward, reduce pass": this kernel is the dgrad producing d(relu(bn(.))).
                 // bn_y is the SAVED ACTIVATION a = relu(gamma * xhat + beta) of that layer: the ReLU gate is a > 0 and the
                 // two reductions are taken in the activation domain, sum g and sum g * a — no per-channel parameter is
                 // touched per element (32 LDS.128 per chunk paced the narrow layers); tag_bn_red_act_to_xhat turns them
                 // into dbeta = sum g, dgamma = sum g * xhat = (sum g * a - beta * sum g) / gamma afterwards.
-                uint4 yraw[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) yraw[j] = ynext[j];
-                fetch_y(cc + 1);
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                     float yv[4];
