@@ -121,6 +121,19 @@ int tag_conv_tc_fwd_halo(const void* x, const void* w, void* y, int y_dtype, dou
  * (Cin >= 128) run on CTA PAIRS — a 2-CTA cluster computes a 256-pixel tile with cta_group::2 tcgen05 MMAs, each CTA
  * loading half of every weight tile; 0 = one CTA per 128-pixel tile everywhere. */
 int tag_conv_halo_set_pair_mode(int mode);
+/* Scheduling knob of every persistent tensor-core kernel (conv forward/dgrad/wgrad): launch them on `sms` fewer SMs
+ * (0 .. 64, default 0) from now on.  The data-parallel train step sets it while the gradient all-reduce runs beside the
+ * last part of its backward pass (a collective's CTAs cannot share an SM with these kernels' CTAs) and resets it to 0.
+ * Same results either way.  No reference counterpart (torch DDP overlaps its buckets the same way, run_strong.py has
+ * no data-parallel path). */
+int tag_set_sm_reserve(int sms);
+/* Deterministic split-K for the tensor-core weight-gradient kernels (tag_conv_tc_wgrad, tag_conv_tc_wgrad64): with a
+ * workspace set (device memory, 16-byte aligned; 64 MB covers every layer of cnn8rnn at bs=64), each split stores its
+ * partial tile into its own slab and a second pass adds the slabs to dw in split order, so the weight gradients are
+ * bit-identical from run to run (torch.use_deterministic_algorithms for the reference's cudnn wgrad).  ws = NULL,
+ * bytes = 0 (default) restores fp32 atomics into dw.  A call whose slabs do not fit returns 10002.  The workspace is
+ * shared: issue weight gradients on ONE stream while it is set. */
+int tag_set_splitk_workspace(void* ws, long bytes);
 /* its weight operand: bf16 tap-major [9][Cout][Cin] (flip_transpose=0) or, for dgrad,
  * [9][Cin][Cout] of the 180-degree rotated kernel (flip_transpose=1), from the fp32 master. */
 int tag_weight_prep_tapmajor_bf16(const float* w, void* out, int Co, int Ci, int flip_transpose,

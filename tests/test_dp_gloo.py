@@ -33,9 +33,14 @@ def _worker(rank, world, port, ret):
         assert float(model.audio_encoder.bn0.running_mean.abs().max()) == 0.0
         n = ts.n_params
         assert n == sum(p.numel() for p in model.parameters())
-        # parameters and .grad are views of the flat buffers, in the fixed order
+        # parameters and .grad are views of the flat buffers, in the bucket order: what the backward pass writes last
+        # (bn0, conv block 1's BatchNorms and convolutions) first, then everything else in _param_list() order
+        enc_params = model.audio_encoder._param_list()
+        late = enc_params[0:6] + enc_params[18:20]
+        assert late[6] is model.audio_encoder.conv_block1.conv1.weight and late[5] is model.audio_encoder.conv_block1.bn2.bias
+        rest = [p for p in enc_params if not any(p is q for q in late)] + [model.text_encoder.embedding.core.weight]
         off = 0
-        for p in model.audio_encoder._param_list() + [model.text_encoder.embedding.core.weight]:
+        for p in late + rest:
             assert p.data_ptr() == ts.flat_p.data_ptr() + 4 * off
             assert p.grad.data_ptr() == ts.flat_g.data_ptr() + 4 * off
             off += p.numel()
@@ -59,16 +64,17 @@ def _worker(rank, world, port, ret):
         ts._ar_in_graph = True
         expect = (torch.arange(n, dtype=torch.float32) % 7) * world + sum(range(world))
         assert torch.equal(ts.flat_g, expect)
-        assert torch.equal(model.audio_encoder.fc1.bias.grad, expect[ts._views[27][0]:ts._views[27][0] + 512])
-        # the same collective as two calls (TAG_B200_AR_OVERLAP=1: under the backward pass on GPUs): the tail of the bucket — from
-        # conv_block3.conv1.weight on, final once block 3 has run its backward — and then the head
-        w31 = model.audio_encoder.conv_block3.conv1.weight
-        assert ts.flat_g.data_ptr() + 4 * ts._ar_split == w31.grad.data_ptr()
-        assert ts._ar_split == 262592 and ts._ar_split < 0.05 * n      # >= 95 % of the bytes travel early (97 % with the full vocabulary)
+        fcb = [id(p) for p in ts._params].index(id(model.audio_encoder.fc1.bias))
+        assert torch.equal(model.audio_encoder.fc1.bias.grad, expect[ts._views[fcb][0]:ts._views[fcb][0] + 512])
+        # the same collective as two calls (TAG_B200_AR_OVERLAP=1: under the backward pass on GPUs): the tail of the bucket —
+        # everything but bn0 and conv block 1, final once block 2 has run its backward — and then the head
+        first_early = model.audio_encoder.conv_block2.bn1.weight
+        assert ts.flat_g.data_ptr() + 4 * ts._ar_split == first_early.grad.data_ptr()
+        assert ts._ar_split == 3 * 2 * 64 + 64 * 9 + 64 * 64 * 9 and ts._ar_split < 0.01 * n      # > 99 % of the bytes travel early
         ts.flat_g.copy_(torch.arange(n, dtype=torch.float32) % 5 + 2 * rank)
         for blk in (3, 2, 1, 0):
             ts._early_allreduce(blk)
-            if blk == 3:                                    # nothing is reduced before block 3 is done
+            if blk == 2:                                    # nothing is reduced before block 2 is done
                 assert torch.equal(ts.flat_g, torch.arange(n, dtype=torch.float32) % 5 + 2 * rank)
         ts._finish_allreduce()
         assert torch.equal(ts.flat_g, (torch.arange(n, dtype=torch.float32) % 5) * world + 2 * sum(range(world)))

@@ -111,6 +111,54 @@ def test_tc_linear_fwd_and_wgrad(M, K, N):
     assert rel_err(dw, ref_dw) < 2e-3, rel_err(dw, ref_dw)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps", [
+    (8, 250, 64, 64, 64, 9),       # wgrad64 (conv_block1.conv2), ~100 splits
+    (8, 125, 32, 64, 128, 9),      # wgrad64, Cout 128
+    (8, 125, 32, 128, 128, 9),     # one-CTA wgrad
+    (8, 62, 16, 256, 256, 9),      # CTA-pair wgrad
+    (1, 4000, 1, 512, 1536, 1),    # linear (GRU input projection)
+])
+def test_deterministic_splitk_wgrad_is_bit_reproducible(B, H, W, Cin, Cout, taps):
+    """tag_set_splitk_workspace: slabs + ordered reduce give the same bits on every run and agree with the atomic path;
+    the result is ADDED to dw like the atomic path's."""
+    from texttoaudiogrounding_b200 import ops
+    x = _bf(torch.randn(B, H, W, Cin, generator=g(31))).cuda().bfloat16()
+    dy = _bf(torch.randn(B, H, W, Cout, generator=g(32))).cuda().bfloat16()
+    P = B * H * W
+    splits = ops.wgrad_splits(P, Cin, Cout, taps)
+    shape = (Cout, 3, 3, Cin) if taps == 9 else (Cout, Cin)
+    atomic = torch.zeros(shape, device="cuda")
+    ops.conv_wgrad(dy, x, atomic, B, H, W, Cin, Cout, taps, splits)
+    ops.set_deterministic_wgrad(True)
+    try:
+        runs = []
+        for _ in range(3):
+            dw = torch.full(shape, 0.5, device="cuda")
+            ops.conv_wgrad(dy, x, dw, B, H, W, Cin, Cout, taps, splits)
+            runs.append(dw)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_deterministic_wgrad(False)
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    assert rel_err(runs[0] - 0.5, atomic) < 1e-4, rel_err(runs[0] - 0.5, atomic)
+    again = torch.zeros(shape, device="cuda")
+    ops.conv_wgrad(dy, x, again, B, H, W, Cin, Cout, taps, splits)      # the switch back to atomics works
+    assert rel_err(again, atomic) < 1e-5
+
+
+def test_deterministic_splitk_workspace_too_small_is_an_error():
+    from texttoaudiogrounding_b200 import _lib, ops
+    x = torch.zeros(8, 62, 16, 256, device="cuda", dtype=torch.bfloat16)
+    dy = torch.zeros(8, 62, 16, 256, device="cuda", dtype=torch.bfloat16)
+    dw = torch.zeros(256, 3, 3, 256, device="cuda")
+    ops.set_deterministic_wgrad(True, megabytes=1)
+    try:
+        with pytest.raises(_lib.TagError):
+            ops.conv_wgrad(dy, x, dw, 8, 62, 16, 256, 256, 9, 8)
+    finally:
+        ops.set_deterministic_wgrad(False)
+
+
 def test_tc_matches_simt_on_model_shapes_end_to_end():
     """Same bf16 train step with the tensor-core kernels and with the SIMT kernels."""
     from oracle import tag_oracle as O

@@ -234,7 +234,7 @@ template <int BLOCK_N, int STAGES, int PIX>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                      float* __restrict__ dw, int B, int H, int W, int Cin, int Cout, int taps,
-                     int m_blocks, int n_blocks, int k_tiles_per_split) {
+                     int m_blocks, int n_blocks, int k_tiles_per_split, long slab_stride) {
     using L = WgSmem<BLOCK_N, STAGES, PIX>;
     constexpr int WG_BOX_BYTES = L::BOX_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -336,6 +336,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const int tap = tap_h[half];
         const int ci = ci_h[half] + (row & 63);
         const bool live = half == 0 || half1_live;
+        const bool slab = slab_stride != 0;
+        float* dwp = dw + (long)split * slab_stride;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
             uint32_t r[32];
@@ -345,7 +347,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int co = n_blk * BLOCK_N + c * 32 + j;
-                    atomicAdd(dw + ((long)co * taps + tap) * Cin + ci, __uint_as_float(r[j]));
+                    wg_put(dwp + ((long)co * taps + tap) * Cin + ci, __uint_as_float(r[j]), slab);
                 }
             }
         }
@@ -412,7 +414,7 @@ template <int BLOCK_N, int STAGES, int PIX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                       float* __restrict__ dw, int B, int H, int W, int Cin, int Cout, int taps,
-                      int m_blocks, int n_blocks, int k_tiles_per_split) {
+                      int m_blocks, int n_blocks, int k_tiles_per_split, long slab_stride) {
     using L = Wg2Smem<BLOCK_N, STAGES, PIX>;
     constexpr int WG_BOX_BYTES = L::BOX_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -505,6 +507,8 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         tc_fence_after();
         const int row = warp * 32 + lane;
         const int ci = ci0 + row;
+        const bool slab = slab_stride != 0;
+        float* dwp = dw + (long)split * slab_stride;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
             uint32_t r[32];
@@ -514,7 +518,7 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int co = n_blk * BLOCK_N + c * 32 + j;
-                    atomicAdd(dw + ((long)co * taps + tap) * Cin + ci, __uint_as_float(r[j]));
+                    wg_put(dwp + ((long)co * taps + tap) * Cin + ci, __uint_as_float(r[j]), slab);
                 }
             }
         }
@@ -548,9 +552,13 @@ int launch_tc_wgrad2(const CUtensorMap& tx, const CUtensorMap& tdy, float* dw, i
     const int kps = (k_tiles + splits - 1) / splits;
     splits = (k_tiles + kps - 1) / kps;
     const long grid = 2l * m_pairs * n_blocks * splits;
-    kern<<<(unsigned)grid, 192, L::TOTAL, stream>>>(tx, tdy, dw, B, H, W, Cin, Cout, taps, m_blocks, n_blocks, kps);
+    const long n = (long)Cout * taps * Cin;
+    float* target; long slab;
+    int rc = splitk_target(dw, splits, n, stream, &target, &slab);
+    if (rc != TAG_OK) return rc;
+    kern<<<(unsigned)grid, 192, L::TOTAL, stream>>>(tx, tdy, target, B, H, W, Cin, Cout, taps, m_blocks, n_blocks, kps, slab);
     TAG_RETURN_IF_LAUNCH_FAILED();
-    return TAG_OK;
+    return slab ? tag_splitk_reduce(target, splits, n, dw, stream) : TAG_OK;
 }
 
 template <int BLOCK_N, int PIX>
@@ -574,9 +582,13 @@ int launch_tc_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, float* dw, in
     const int kps = (k_tiles + splits - 1) / splits;
     splits = (k_tiles + kps - 1) / kps;
     const long grid = (long)m_blocks * n_blocks * splits;
-    kern<<<(unsigned)grid, 192, L::TOTAL, stream>>>(tx, tdy, dw, B, H, W, Cin, Cout, taps, m_blocks, n_blocks, kps);
+    const long n = (long)Cout * taps * Cin;
+    float* target; long slab;
+    int rc = splitk_target(dw, splits, n, stream, &target, &slab);
+    if (rc != TAG_OK) return rc;
+    kern<<<(unsigned)grid, 192, L::TOTAL, stream>>>(tx, tdy, target, B, H, W, Cin, Cout, taps, m_blocks, n_blocks, kps, slab);
     TAG_RETURN_IF_LAUNCH_FAILED();
-    return TAG_OK;
+    return slab ? tag_splitk_reduce(target, splits, n, dw, stream) : TAG_OK;
 }
 
 bool width_ok(int W) { return W == 1 || W == 2 || W == 4 || W == 8 || W == 16 || W == 32 || W == 64; }

@@ -22,7 +22,8 @@ __device__ __forceinline__ uint32_t tap_addr(int tp) { return (uint32_t)((tp / 3
 
 __global__ void __launch_bounds__(192, 1)
 conv_tc_wgrad64_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
-                       float* __restrict__ dw, int B, int H, int W, int Cout, int n_blocks, int tiles_per_split) {
+                       float* __restrict__ dw, int B, int H, int W, int Cout, int n_blocks, int tiles_per_split,
+                       long slab_stride) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -101,6 +102,8 @@ conv_tc_wgrad64_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         tc_fence_after();
         const int row = warp * 32 + lane;
         const int ci = row & 63;
+        const bool slab = slab_stride != 0;
+        float* dwp = dw + (long)split * slab_stride;
 #pragma unroll 1
         for (int m = 0; m < 5; ++m) {
             const int tp = 2 * m + (row >> 6);          // tap' = dwi*3 + dhi
@@ -114,7 +117,7 @@ conv_tc_wgrad64_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int co = n_blk * 64 + c * 32 + j;
-                        atomicAdd(dw + ((long)co * 9 + tap) * 64 + ci, __uint_as_float(r[j]));
+                        wg_put(dwp + ((long)co * 9 + tap) * 64 + ci, __uint_as_float(r[j]), slab);
                     }
                 }
             }
@@ -149,7 +152,11 @@ extern "C" int tag_conv_tc_wgrad64(const void* dy, const void* x, float* dw, int
     if (splits > k_tiles) splits = k_tiles;
     const int tps = (k_tiles + splits - 1) / splits;
     splits = (k_tiles + tps - 1) / tps;
-    conv_tc_wgrad64_kernel<<<n_blocks * splits, 192, SMEM_TOTAL, stream>>>(tx, tdy, dw, B, H, W, Cout, n_blocks, tps);
+    const long n = (long)Cout * 9 * 64;
+    float* target; long slab;
+    rc = splitk_target(dw, splits, n, stream, &target, &slab);
+    if (rc != TAG_OK) return rc;
+    conv_tc_wgrad64_kernel<<<n_blocks * splits, 192, SMEM_TOTAL, stream>>>(tx, tdy, target, B, H, W, Cout, n_blocks, tps, slab);
     TAG_RETURN_IF_LAUNCH_FAILED();
-    return TAG_OK;
+    return slab ? tag_splitk_reduce(target, splits, n, dw, stream) : TAG_OK;
 }

@@ -97,6 +97,53 @@ extern "C" int tag_cast_f32_to_bf16(const float* x, void* y, long n, cudaStream_
 
 extern "C" int tag_version(void) { return 100; }
 
+// SMs the persistent tensor-core kernels leave free (tc_common.cuh sm_count()): the data-parallel step sets this while
+// an all-reduce runs beside the last part of its backward pass, and back to 0 afterwards.  Read at launch time.
+int g_tag_sm_reserve = 0;
+extern "C" int tag_set_sm_reserve(int sms) {
+    if (sms < 0 || sms > 64) return TAG_ERR_BAD_ARG;
+    g_tag_sm_reserve = sms;
+    return TAG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic split-K: with a workspace set, the tensor-core weight-gradient kernels store every split's partial tile
+// into that split's slab (plain stores) and this reduce adds the slabs to dw in split order — bit-identical results from
+// run to run, at the price of the slab traffic (default: fp32 atomics straight into dw, order not fixed).
+float* g_tag_det_ws = nullptr;
+long g_tag_det_ws_bytes = 0;
+
+namespace {
+__global__ void splitk_reduce_kernel(const float4* __restrict__ ws, int splits, long n4, float4* __restrict__ dw) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 a = ws[i];
+    for (int s = 1; s < splits; ++s) {
+        const float4 b = ws[(long)s * n4 + i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float4 d = dw[i];
+    d.x += a.x; d.y += a.y; d.z += a.z; d.w += a.w;
+    dw[i] = d;
+}
+}  // namespace
+
+int tag_splitk_reduce(const float* ws, int splits, long n, float* dw, cudaStream_t stream) {
+    if (n % 4 != 0 || (reinterpret_cast<uintptr_t>(dw) & 15) != 0) return TAG_ERR_UNSUPPORTED;
+    const long n4 = n / 4;
+    splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(ws), splits, n4,
+                                                                          reinterpret_cast<float4*>(dw));
+    TAG_RETURN_IF_LAUNCH_FAILED();
+    return TAG_OK;
+}
+
+extern "C" int tag_set_splitk_workspace(void* ws, long bytes) {
+    if ((ws == nullptr) != (bytes == 0) || bytes < 0 || (reinterpret_cast<uintptr_t>(ws) & 15) != 0) return TAG_ERR_BAD_ARG;
+    g_tag_det_ws = static_cast<float*>(ws);
+    g_tag_det_ws_bytes = bytes;
+    return TAG_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Batched weight preparation: every bf16 GEMM operand of a step (plain casts, tap-major conv
 // operands, flipped+transposed dgrad operands) from the fp32 master weights in ONE launch.
@@ -109,29 +156,55 @@ extern "C" int tag_version(void) { return 100; }
 namespace {
 constexpr int PREP_ELEMS_PER_BLOCK = 2048;
 
-__global__ void weight_prep_batch_kernel(const long long* __restrict__ table, int n_entries) {
+__global__ void __launch_bounds__(256) weight_prep_batch_kernel(const long long* __restrict__ table, int n_entries) {
+    __shared__ float tile[64][33];
     int e = 0;
     while (e + 1 < n_entries && (long long)blockIdx.x >= table[(e + 1) * 5 + 4]) ++e;
     const float* src = reinterpret_cast<const float*>(table[e * 5 + 0]);
     bf16* dst = reinterpret_cast<bf16*>(table[e * 5 + 1]);
     const int Co = (int)(table[e * 5 + 2] >> 32), Ci = (int)(table[e * 5 + 2] & 0xFFFFFFFF);
     const int taps = (int)(table[e * 5 + 3] >> 32), mode = (int)(table[e * 5 + 3] & 0xFFFFFFFF);
-    const long n = (long)Co * Ci * taps;
-    const long base = ((long)blockIdx.x - table[e * 5 + 4]) * PREP_ELEMS_PER_BLOCK;
-    for (long i = base + threadIdx.x; i < base + PREP_ELEMS_PER_BLOCK && i < n; i += blockDim.x) {
+    const unsigned n = (unsigned)Co * Ci * taps;             // < 2^31 for every operand of this model
+    const unsigned blk = (unsigned)((long long)blockIdx.x - table[e * 5 + 4]);
+    const int t = threadIdx.x;
+    if (mode >= 2 && Ci % 32 == 0 && Co % 64 == 0) {
+        // transposing modes through a 64(co) x 32(ci) shared-memory tile: 128-byte runs on both sides
+        // (2048 elements per block, like the linear modes, so the host's block count holds)
+        const unsigned tiles_ci = Ci / 32, tiles_co = Co / 64;
+        const unsigned tco = blk % tiles_co, r1 = blk / tiles_co;
+        const unsigned tci = r1 % tiles_ci, tp = r1 / tiles_ci;
+        const int stap = (mode == 2) ? 8 - ((tp % 3) * 3 + tp / 3) : 0;
+        const long row = (long)taps * Ci;                    // floats between consecutive co in src
+        const float* s0 = src + (long)(tco * 64) * row + (long)stap * Ci + tci * 32;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int co = r * 8 + (t >> 5), ci = t & 31;
+            tile[co][ci] = s0[(long)co * row + ci];
+        }
+        __syncthreads();
+        bf16* d0 = dst + ((long)tp * Ci + tci * 32) * Co + tco * 64;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int ci = r * 4 + (t >> 6), co = t & 63;
+            d0[(long)ci * Co + co] = __float2bfloat16_rn(tile[co][ci]);
+        }
+        return;
+    }
+    const unsigned base = blk * PREP_ELEMS_PER_BLOCK;
+    for (unsigned i = base + t; i < base + PREP_ELEMS_PER_BLOCK && i < n; i += 256) {
         float v;
         if (mode == 0) {
             v = src[i];
         } else if (mode == 1) {            // i -> [tp][co][ci]
-            const int ci = (int)(i % Ci); const long r = i / Ci;
-            const int co = (int)(r % Co); const int tp = (int)(r / Co);
+            const unsigned ci = i % Ci, r = i / Ci;
+            const unsigned co = r % Co, tp = r / Co;
             v = src[((long)co * 9 + ((tp % 3) * 3 + tp / 3)) * Ci + ci];
         } else if (mode == 2) {            // i -> [tp][ci][co]
-            const int co = (int)(i % Co); const long r = i / Co;
-            const int ci = (int)(r % Ci); const int tp = (int)(r / Ci);
+            const unsigned co = i % Co, r = i / Co;
+            const unsigned ci = r % Ci, tp = r / Ci;
             v = src[((long)co * 9 + (8 - ((tp % 3) * 3 + tp / 3))) * Ci + ci];
         } else {                           // i -> [ci][co]
-            const int co = (int)(i % Co); const int ci = (int)(i / Co);
+            const unsigned co = i % Co, ci = i / Co;
             v = src[(long)co * Ci + ci];
         }
         dst[i] = __float2bfloat16_rn(v);

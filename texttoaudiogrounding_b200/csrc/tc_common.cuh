@@ -3,6 +3,11 @@
 #include "common.cuh"
 #include <cuda.h>
 
+extern int g_tag_sm_reserve;      // optim.cu; tag_set_sm_reserve()
+extern float* g_tag_det_ws;       // optim.cu; tag_set_splitk_workspace(): non-null = deterministic split-K
+extern long g_tag_det_ws_bytes;
+int tag_splitk_reduce(const float* ws, int splits, long n, float* dw, cudaStream_t stream);   // optim.cu
+
 namespace {
 
 constexpr uint32_t WAIT_SPIN_LIMIT = 1u << 24;
@@ -264,6 +269,27 @@ int make_w_tmap(CUtensorMap* map, const void* ptr, int Cout, int K, int block_n)
     return r == CUDA_SUCCESS ? TAG_OK : 20000 + (int)r;
 }
 
+// split-K partial of a weight gradient: accumulated with atomics into dw (default), or — deterministic mode — stored
+// into this split's own slab of the workspace, summed in split order by tag_splitk_reduce afterwards
+__device__ __forceinline__ void wg_put(float* p, float v, bool slab) {
+    if (slab) *p = v;
+    else atomicAdd(p, v);
+}
+
+// Host side of the deterministic mode: `need` floats per split.  Returns the pointer the kernel accumulates into and
+// the slab stride (0 = atomics straight into dw).
+inline int splitk_target(float* dw, int splits, long n, cudaStream_t stream, float** out, long* stride) {
+    if (g_tag_det_ws == nullptr) { *out = dw; *stride = 0; return TAG_OK; }
+    const long need = (long)splits * n * (long)sizeof(float);
+    if (need > g_tag_det_ws_bytes) return TAG_ERR_UNSUPPORTED;
+    cudaError_t e = cudaMemsetAsync(g_tag_det_ws, 0, (size_t)need, stream);      // tiles a split does not own stay zero
+    if (e != cudaSuccess) return (int)e;
+    *out = g_tag_det_ws; *stride = n;
+    return TAG_OK;
+}
+
+// SMs the persistent kernels may fill: all of them, minus what tag_set_sm_reserve() set aside for a collective
+// that runs beside them (an NCCL CTA cannot share an SM with a CTA that holds ~200 KB of shared memory).
 int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -272,7 +298,8 @@ int sm_count() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
-    return n;
+    const int left = n - g_tag_sm_reserve;
+    return left < 2 ? 2 : left;
 }
 
 }  // namespace

@@ -86,6 +86,22 @@ class EncoderCtx:
     pcnt: list = field(default_factory=list)        # per block: open-gate counts of the pooling windows (uint8) or None
 
 
+class _ZeroArena:
+    """The float64 reduction targets of one pass (BatchNorm statistics, BN-backward sums) are slices of one arena
+    zeroed by a single fill, instead of one fill kernel per target (20 per train step)."""
+
+    def __init__(self, dev, doubles: int):
+        self.buf = torch.zeros(doubles, device=dev, dtype=torch.float64)
+        self.off = 0
+
+    def __call__(self, n: int) -> torch.Tensor:
+        if self.off + n > self.buf.numel():
+            return torch.zeros(n, device=self.buf.device, dtype=torch.float64)
+        out = self.buf[self.off:self.off + n]
+        self.off += n
+        return out
+
+
 def _seed_for(seed: int, layer: int) -> int:
     return (seed * 1000003 + layer * 7919 + 12345) & 0xFFFFFFFFFFFFFFFF
 
@@ -133,6 +149,8 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
                      dropout=dropout and training) if save else None
     use_dropout = dropout and training
 
+    zeros64 = _ZeroArena(dev, 4096 if bn_training else 0)
+
     def bn_aux(C):
         return tuple(torch.empty(C, **f32) for _ in range(4))
 
@@ -143,7 +161,7 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
 
     # ---- log-mel + bn0
     db = torch.empty(B, T0, N_MELS, **f32)
-    st = torch.zeros(2 * N_MELS, device=dev, dtype=torch.float64) if bn_training else None
+    st = zeros64(2 * N_MELS) if bn_training else None
     ops.annotate(f"logmel B={B} L={L}", 0.0, wav.numel() * wav.element_size() + db.numel() * 4.0)
     if 0 < Wt.mel_nnz <= LOGMEL_FB_CAP:
         # compact (triangular) filterbank: warp-per-frame-pair kernel; fp32 or fp16 waveform (the reference stores
@@ -187,7 +205,7 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
     for blk, ((cin, cout), (ph, pw)) in enumerate(zip(CHANNELS, POOLS)):
         count = B * H * W
         # conv1
-        st1 = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if bn_training else None
+        st1 = zeros64(2 * cout) if bn_training else None
         aux1 = bn_aux(cout)
         if cin == 1 and c1_fused:
             # Cin = 1: the batch statistics of conv1's output follow from 54 moments of its 16 MB input, so the layer
@@ -211,7 +229,7 @@ def encoder_forward(Wt: EncoderWeights, wav: torch.Tensor, *, training: bool, bn
             ops.scale_shift_act(y1, a1, aux1[0], aux1[1], cout, relu=True)
         # conv2
         y2 = torch.empty(B, H, W, cout, **act)
-        st2 = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if bn_training else None
+        st2 = zeros64(2 * cout) if bn_training else None
         ops.conv_fwd(a1, _operand(Wt, ("f", 2 * blk + 1), lambda: fwd_operand(Wt.conv[2 * blk + 1], W)), y2, None, False, st2, B, H, W, cout, cout, 9)
         aux2 = bn_aux(cout)
         finalize(st2, count, cout, 2 + 2 * blk, aux2)
@@ -301,6 +319,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
     d_emb = d_emb.contiguous()
     p_blk = P_BLOCK if ctx.dropout else 0.0
     p_fc = P_FC if ctx.dropout else 0.0
+    zeros64 = _ZeroArena(dev, 8192)
 
     # ---- GRU
     tc = dtype == torch.bfloat16 and ops.USE_TC
@@ -335,7 +354,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
     red_next = None
     if ctx.pcnt[3] is not None and dp.dtype == torch.bfloat16:
         # block 4's bn2 backward sums ride along (activation domain), as blocks 1-3 get theirs from the next conv1 dgrad
-        red_next = torch.zeros(2 * CHANNELS[3][1], device=dev, dtype=torch.float64)
+        red_next = zeros64(2 * CHANNELS[3][1])
         call("tag_freq_mean_bwd", dm, ops.dt(dm), dp, ops.dt(dp), rows, Wf, 512, p_fc,
              _seed_for(ctx.seed, 4), ctx.seed_dev, ctx.p[3], ctx.pcnt[3], red_next)
     else:
@@ -362,7 +381,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
                  0.25 / (1.0 - p_blk) if p_blk > 0.0 else 0.25,        # the codes carry 4 x the weight; dropout keep scale
                  dg, dbt)
         else:
-            red = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
+            red = zeros64(2 * cout)
             call("tag_bn_relu_pool_bwd", 0, y2, dp, None, ops.dt(y2), aux2[0], aux2[1], aux2[2], aux2[3], red,
                  bn_tr, B, H, W, cout, ph, pw, p_blk, seed, ctx.seed_dev)
             dg, dbt = G.bn[2 + 2 * blk]
@@ -375,7 +394,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
                                         ops.wgrad_splits(P, cout, cout, 9)), dy2, a1)
         w2t = _operand(Wt, ("t", 2 * blk + 1), lambda: ops.prep_weight_t(Wt.conv[2 * blk + 1], cout, cout, 9, dtype, W))
         da1 = torch.empty_like(a1)
-        red1 = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
+        red1 = zeros64(2 * cout)
         if cin == 1 and ctx.c1_fused:
             # the BN input y1 was never stored; the fused reduce works on the saved activation a1 anyway
             ops.conv_fwd(dy2, w2t, da1, None, False, red1, B, H, W, cout, cout, 9, bn_fuse=a1)
@@ -387,7 +406,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
             call("tag_conv_c1_bwd_bn", da1, ctx.x0, Wt.conv[0], aux1[0], aux1[2], aux1[3], red1, bn_tr, G.conv[0], dx0,
                  B, H, W)
             del da1
-            red0 = torch.zeros(2 * N_MELS, device=dev, dtype=torch.float64)
+            red0 = zeros64(2 * N_MELS)
             aux0 = ctx.bn_aux[0]
             call("tag_bn_bwd_reduce_f32", dx0, ctx.db, aux0[2], aux0[3], B * H, N_MELS, red0)
             dg, dbt = G.bn[0]
@@ -416,7 +435,7 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
         if cin == 1:
             dx0 = torch.empty(B, H, W, **f32)
             call("tag_conv_c1_bwd", dy1, ctx.x0, Wt.conv[0], ops.dt(dy1), G.conv[0], dx0, B, H, W)
-            red0 = torch.zeros(2 * N_MELS, device=dev, dtype=torch.float64)
+            red0 = zeros64(2 * N_MELS)
             aux0 = ctx.bn_aux[0]
             call("tag_bn_bwd_reduce_f32", dx0, ctx.db, aux0[2], aux0[3], B * H, N_MELS, red0)
             dg, dbt = G.bn[0]
@@ -430,13 +449,12 @@ def encoder_backward(Wt: EncoderWeights, ctx: EncoderCtx, d_emb: torch.Tensor, G
             pc = ctx.pcnt[blk - 1]
             if pc is not None and ops.can_fuse_bn_bwd(w1t, x_in):
                 # x_in is the pooled output of block blk - 1: its bn2 backward reductions ride in this dgrad's epilogue
-                red_next = torch.zeros(2 * cin, device=dev, dtype=torch.float64)
+                red_next = zeros64(2 * cin)
                 ops.conv_fwd(dy1, w1t, dp, None, False, red_next, B, H, W, cout, cin, 9, bn_fuse=(x_in, pc))
             else:
                 ops.conv_fwd(dy1, w1t, dp, None, False, None, B, H, W, cout, cin, 9)
         del dy1
         if on_block_done is not None:
-            if blk == 2:
-                side.join()          # the hook may read the weight gradients queued on the side stream so far
+            side.join()              # the hook may read the weight gradients queued on the side stream so far
             on_block_done(blk)
     side.join()

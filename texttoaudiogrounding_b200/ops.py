@@ -44,6 +44,26 @@ def call(name: str, *args) -> None:
     LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
 
 
+def set_sm_reserve(sms: int) -> None:
+    """Persistent tensor-core kernels launched from now on leave ``sms`` SMs free (0 = use all); see tag_set_sm_reserve."""
+    _lib.check(_lib.lib().tag_set_sm_reserve(int(sms)), "tag_set_sm_reserve")
+
+
+_SPLITK_WS = None
+
+
+def set_deterministic_wgrad(on: bool, device=None, megabytes: int = 64) -> None:
+    """Deterministic (two-pass) split-K for the tensor-core weight gradients: every split writes its own slab of a
+    workspace, a reduce adds the slabs in split order (tag_set_splitk_workspace).  Off = fp32 atomics (default)."""
+    global _SPLITK_WS
+    if on:
+        _SPLITK_WS = torch.empty(megabytes << 20, device=device or "cuda", dtype=torch.uint8)
+        _lib.check(_lib.lib().tag_set_splitk_workspace(_SPLITK_WS.data_ptr(), _SPLITK_WS.numel()), "tag_set_splitk_workspace")
+    else:
+        _lib.check(_lib.lib().tag_set_splitk_workspace(None, 0), "tag_set_splitk_workspace")
+        _SPLITK_WS = None
+
+
 USE_TC = os.environ.get("TAG_B200_NO_TC", "0") != "1"
 USE_HALO = os.environ.get("TAG_B200_NO_HALO", "0") != "1"
 USE_C1_FUSE = os.environ.get("TAG_B200_NO_C1_FUSE", "0") != "1"      # conv_block1.conv1 + bn1 + relu in one pass

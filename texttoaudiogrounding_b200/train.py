@@ -114,16 +114,23 @@ class FusedTrainStep:
         model.register_state_dict_pre_hook(lambda *a, **k: self.flush_counters())
         # weight-gradient GEMMs on a second stream (TAG_B200_OVERLAP=1)
         self.side_stream = torch.cuda.Stream(self.device) if os.environ.get("TAG_B200_OVERLAP", "0") == "1" else None
-        # Data parallel: ONE all-reduce of the flat gradient bucket per step, captured as the last node of the forward +
+        # TAG_B200_DETERMINISTIC_WGRAD=1: two-pass split-K (slabs + ordered reduce) instead of fp32 atomics for the
+        # tensor-core weight gradients; the workspace is shared, so the weight gradients stay on the main stream
+        if os.environ.get("TAG_B200_DETERMINISTIC_WGRAD", "0") == "1" and self.device.type == "cuda":
+            ops.set_deterministic_wgrad(True, self.device)
+            self.side_stream = None
+        # Data parallel: ONE logical all-reduce of the flat gradient bucket per step, issued inside the captured forward +
         # backward graph (NCCL collectives are graph-capturable; no host round trip between the two graphs).
-        # TAG_B200_AR_OVERLAP=1 issues it as two calls instead — the bucket is ordered [BN affine | conv1_1 .. conv2_2 |
-        # conv3_1 .. rnn | embedding], everything from conv_block3.conv1.weight on (97 % of the bytes) is final once block 3
-        # has run its backward, and that tail is reduced on a communication stream forked inside the captured region while
-        # blocks 2 and 1 run.  Measured: 9.05 -> 8.98 ms/step on 2 GPUs, but 8.45 -> 8.76 ms on 8 — the compute kernels are
-        # persistent with one CTA per SM (all registers, ~220 KB of shared memory), so NCCL's CTAs cannot co-reside: they
-        # take whole SMs and every convolution launched meanwhile waits for them.  Hence off by default.
-        self._ar_split = self._views[18 + 4][0]
+        # Default: a single call as the last node.  TAG_B200_AR_OVERLAP=1 issues it as two calls: the bucket is ordered
+        # [bn0, block-1 BatchNorms and convolutions | everything else]; the tail (99.9 % of the bytes) is final once conv
+        # block 2 has run its backward and is reduced on a communication stream forked inside the captured region while
+        # block 1 (1.3 ms of kernels) runs.  The convolution kernels are persistent with one CTA per SM (all registers,
+        # ~200 KB of shared memory) and NCCL's CTAs cannot co-reside with them, so for that window the persistent kernels
+        # are launched on SM_RESERVE fewer SMs (tag_set_sm_reserve) and NCCL is expected to be capped to as many CTAs
+        # (NCCL_MAX_CTAS, set by bench.py before the process group is created).
+        self._ar_split = self._views[self._n_late][0]
         self._overlap_ar = self.world > 1 and os.environ.get("TAG_B200_AR_OVERLAP", "0") == "1"
+        self._sm_reserve = int(os.environ.get("TAG_B200_AR_SM_RESERVE", "8"))
         self._ar_in_graph = True
         self._comm_stream = None
         self._ar_done = None
@@ -227,6 +234,13 @@ class FusedTrainStep:
     # ------------------------------------------------------------------ flat buffers
     def _flatten(self):
         params = self.enc._param_list() + [self.txt.embedding.core.weight]
+        # bucket order: the parameters whose gradients are written last by the backward pass (bn0 and conv block 1: its
+        # two BatchNorms and two convolutions) sit at the head, everything else — final once block 2 has run its
+        # backward — forms one contiguous tail (see _early_allreduce)
+        late = params[0:6] + params[18:20]
+        late_ids = {id(p) for p in late}
+        params = late + [p for p in params if id(p) not in late_ids]
+        self._n_late = len(late)
         if not all(p.requires_grad for p in params):
             raise NotImplementedError("FusedTrainStep trains all parameters; use the autograd path "
                                       "(train_step) with frozen sub-modules")
@@ -330,8 +344,9 @@ class FusedTrainStep:
         self.sim = sim
 
     def _early_allreduce(self, blk: int) -> None:
-        """After conv block 3 (index 2): all-reduce flat_g[_ar_split:] on the communication stream."""
-        if blk != 2:
+        """After conv block 2 (index 1): all-reduce flat_g[_ar_split:] on the communication stream; block 1's persistent
+        kernels leave ``_sm_reserve`` SMs to NCCL."""
+        if blk != 1:
             return
         tail = self.flat_g[self._ar_split:]
         if self.device.type != "cuda":
@@ -346,9 +361,12 @@ class FusedTrainStep:
             torch.distributed.all_reduce(tail, group=self.pg)
             self._ar_done = torch.cuda.Event()
             self._ar_done.record()
+        ops.set_sm_reserve(self._sm_reserve)
 
     def _finish_allreduce(self) -> None:
-        """The head of the bucket (BN affine gradients, blocks 1-2) after the last backward kernel; joins the tail."""
+        """The head of the bucket (bn0 and block 1) after the last backward kernel; joins the tail."""
+        if self.device.type == "cuda":
+            ops.set_sm_reserve(0)
         torch.distributed.all_reduce(self.flat_g[:self._ar_split], group=self.pg)
         if self._ar_done is not None:
             torch.cuda.current_stream().wait_event(self._ar_done)
