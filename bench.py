@@ -504,6 +504,16 @@ def main():
     # sampler first, run untimed steps until the clocks have settled, and enter the timed regions (device-resident, then
     # end-to-end) straight from continuous load, so that both see the same clocks instead of one paying for the order.
     wl.e2e(2)      # warm-up of the end-to-end path too: staging buffers, copy stream, pinned loss slots are created here
+    # informational: the same K steps timed right after the warm-up, before the clocks have sunk (the state round 1's
+    # numbers were taken in); reported as details.value_before_settle, never as `value`
+    barrier()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for _ in range(args.steps):
+        wl.resident()
+    b1.record()
+    barrier()
+    ms_burst = b0.elapsed_time(b1)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -631,6 +641,7 @@ def main():
             "vs_baseline": None, "dtype": precision, "data": "synthetic",
             "config": config_dict(name, B, world),
             "details": {"cuda_graph": not args.no_graph, "dropout": kind == "train", "settle_s": args.settle,
+                        "value_before_settle": round(B * world * args.steps / (ms_burst * 1e-3), 1),
                         "e2e_events_ms": round(e2e_events_ms, 3), "e2e_wall_ms": round(e2e_wall_ms, 3),
                         "waveform_dtype": ("f16" if args.wav_fp16 else "f32") if kind == "train" else "f32",
                         "bench_config": name},

@@ -111,6 +111,28 @@ def test_tc_linear_fwd_and_wgrad(M, K, N):
     assert rel_err(dw, ref_dw) < 2e-3, rel_err(dw, ref_dw)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(40, 50, 8, 256, 512), (6, 100, 64, 64, 64), (3, 40, 16, 128, 64)])
+def test_sm_reserve_leaves_results_unchanged(B, H, W, Cin, Cout):
+    """tag_set_sm_reserve: the persistent conv kernels on 8 or 41 fewer SMs (odd: a CTA pair loses its partner's SM too)
+    compute the same tiles — bit-identical outputs; the knob resets."""
+    from texttoaudiogrounding_b200 import ops
+    x = _bf(torch.randn(B, H, W, Cin, generator=g(41))).cuda().bfloat16()
+    w = ops.prep_weight((torch.randn(Cout, 3, 3, Cin, generator=g(42)) * (1.0 / (3 * Cin ** 0.5))).cuda(), torch.bfloat16, W)
+    outs = []
+    try:
+        for reserve in (0, 8, 41):
+            ops.set_sm_reserve(reserve)
+            y = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+            ops.conv_fwd(x, w, y, None, False, None, B, H, W, Cin, Cout, 9)
+            outs.append(y)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_sm_reserve(0)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    with pytest.raises(Exception):
+        ops.set_sm_reserve(65)
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout,taps", [
     (8, 250, 64, 64, 64, 9),       # wgrad64 (conv_block1.conv2), ~100 splits
     (8, 125, 32, 64, 128, 9),      # wgrad64, Cout 128
