@@ -33,7 +33,7 @@ def main(path):
     out = {e: {"traffic_bytes_per_launch": sum(v) / len(v), "launches": len(v),
                "source": f"{path}: mean of dram__bytes_read.sum + dram__bytes_write.sum over the launches of the kernels "
                          "behind this entry point (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
-                         "dram__bytes_write.sum --clock-control none, bench.py --steps 2 --warmup 3 --no-graph --settle 0)"}
+                         "dram__bytes_write.sum --clock-control none, bench.py --steps 2 --warmup 1 --settle 0, scripts/final_1gpu.sh)"}
            for e, v in agg.items()}
     print(json.dumps(out, indent=1))
 
