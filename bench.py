@@ -7,7 +7,9 @@ Default workload (the BASELINE.json metric, configs[2]): one "step" = the cnn8rn
 backward + clip_grad_norm_ + Adam) over one batch of 64 synthetic 10 s @ 32 kHz clips with 8-token phrases PER GPU
 (weak scaling).  Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` runs the
 same step through the public API with pinned host buffers, the H2D copies and the loss / result D2H read inside the
-timed region.  `--impl reference` times the UNMODIFIED reference modules (staged under oracle/_ref by
+timed region.  Both timed regions are entered from sustained load (--settle seconds of untimed steps; the chip is
+power-capped during the step and the first steps after any pause run 3-4 % faster — that figure is reported as
+details.value_before_settle, not as `value`).  `--impl reference` times the UNMODIFIED reference modules (staged under oracle/_ref by
 oracle/build_ref.py; the oracle port when they are absent) on the host cores, every step a bounded sample of the
 workload.  `gpu_baseline` (N=1) times the same reference modules with stock torch.cuda eager on the same GPU.
 --config selects the other BASELINE.json configurations: fwd_fp32 = configs[1], attn_bf16 = configs[3],
