@@ -7,8 +7,9 @@
 //             per CTA and step), each CTA multiplies its 96 gate rows with the full state (K split over the 8 warps).
 //   backward: a CTA multiplies its OWN 96 gate-gradient rows with its rows of W_hh for all 256 units and ships the eight
 //             8 x 32 partial products to their owners (256 pieces per CTA and step instead of 768 gate-gradient pieces).
-// Measured (scripts/gru_timing.py, B = 64, T = 250): the hand-off costs ~2 ns per arriving piece, so the piece count sets
-// the step time: 1.50 -> 1.17 us / step forward, 2.0 -> 1.19 us / step backward against the cluster-barrier version.
+// Measured (scripts/gru_timing.py, B = 64, T = 250): 1.50 -> 1.17 us / step forward, 2.0 -> 1.19 us / step backward against
+// the cluster-barrier version.  The hand-off alone (scripts/micro/dsmem_handoff.cu) is ~0.35 us per step however the 4 KB
+// are cut (16-byte st.async pieces or bulk copies); the rest of a step is the dependent chain inside the CTA.
 //
 // (tcgen05 needs M >= 64 and pays a TMEM round trip per step; for a 96 x 8 x 256 product on the critical path of a
 // 250-step recurrence the register-resident mma.sync form has lower latency.)
