@@ -42,6 +42,8 @@ SHAPES = [
     (40, 50, 8, 256, 512),    # > 148 tiles: persistent loop + both TMEM stages
     (1, 16, 8, 256, 256),     # ONE tile: the second CTA of a pair computes a padding tile
     (3, 40, 16, 128, 64),     # block-2 conv1 dgrad shape (N = 64, weights stream), odd tile count
+    (3, 47, 16, 64, 64),      # weights-resident 64 -> 64 layer: several row tiles per column, the last one clipped
+    (5, 151, 64, 64, 64),     # the same with > 148 tiles: both accumulators, both MMA issuers, ring wrap-around
 ]
 
 
@@ -249,7 +251,7 @@ def test_bigru_bf16_tensor_core_variant_close_to_oracle(B, T):
 
 
 @pytest.mark.parametrize("halo_mode", [True, "single"], indirect=True)
-@pytest.mark.parametrize("B,H,W,C", [(2, 21, 16, 128), (3, 9, 64, 64), (2, 17, 8, 512), (1, 16, 8, 256)])
+@pytest.mark.parametrize("B,H,W,C", [(2, 21, 16, 128), (3, 9, 64, 64), (2, 17, 8, 512), (1, 16, 8, 256), (4, 77, 64, 64)])
 def test_halo_dgrad_with_fused_bn_relu_backward_reduce(B, H, W, C, halo_mode):
     """dgrad epilogue fusion: ReLU gate from the saved activation + (sum g, sum g * a) in the epilogue, converted by
     tag_bn_red_act_to_xhat  ==  the separate mode-0 pass over the BatchNorm input (dbeta, dgamma)."""
