@@ -38,10 +38,9 @@ conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __re
                    double* __restrict__ stats, int B, int H, int W, const float* __restrict__ bn_scale,
                    const float* __restrict__ bn_shift) {
     __shared__ float xs[TH + 2][XS_W];
-    __shared__ float s_sum[CO], s_sq[CO];
+    __shared__ float s_sum[8][CO], s_sq[8][CO];                   // per-warp totals, summed in warp order (no fp32 atomics)
     const int tiles_h = (H + TH - 1) / TH;
     const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;        // 8 channel groups x 32 pixels
-    if (threadIdx.x < CO) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
     float wr[8][9];
 #pragma unroll
     for (int c = 0; c < 8; ++c)
@@ -118,14 +117,17 @@ conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __re
             sv += __shfl_xor_sync(0xffffffffu, sv, 8);  qv += __shfl_xor_sync(0xffffffffu, qv, 8);
             sv += __shfl_xor_sync(0xffffffffu, sv, 16); qv += __shfl_xor_sync(0xffffffffu, qv, 16);
             if ((threadIdx.x & 31) < 8) {
-                atomicAdd(&s_sum[cg * 8 + c], sv);
-                atomicAdd(&s_sq[cg * 8 + c], qv);
+                s_sum[threadIdx.x >> 5][cg * 8 + c] = sv;
+                s_sq[threadIdx.x >> 5][cg * 8 + c] = qv;
             }
         }
         __syncthreads();
         if (threadIdx.x < CO) {
-            atomicAdd(stats + threadIdx.x, (double)s_sum[threadIdx.x]);
-            atomicAdd(stats + CO + threadIdx.x, (double)s_sq[threadIdx.x]);
+            double ts = 0.0, tq = 0.0;
+#pragma unroll
+            for (int wv = 0; wv < 8; ++wv) { ts += (double)s_sum[wv][threadIdx.x]; tq += (double)s_sq[wv][threadIdx.x]; }
+            atomicAdd(stats + threadIdx.x, ts);
+            atomicAdd(stats + CO + threadIdx.x, tq);
         }
     }
 }
@@ -675,9 +677,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 c1_moments_w64_kernel(const T* __restrict__ x, int B, int H, double* __restrict__ mom) {
     constexpr int W = 64;
-    __shared__ float s_m[N_MOM];
-    if (threadIdx.x < N_MOM) s_m[threadIdx.x] = 0.f;
-    __syncthreads();
+    __shared__ float s_m[8][64];               // per-warp totals, summed in warp order: no order-dependent fp32 atomics
     const int chunks = (H + 4 * MOM_ROWS - 1) / (4 * MOM_ROWS);
     const int b = blockIdx.x / chunks;
     const int h_begin = (blockIdx.x % chunks) * 4 * MOM_ROWS + (threadIdx.x >> 6) * MOM_ROWS;
@@ -724,10 +724,15 @@ c1_moments_w64_kernel(const T* __restrict__ x, int B, int H, double* __restrict_
     for (int i = 0; i < 32; ++i) { lo32[i] = m[i]; hi32[i] = 32 + i < N_MOM ? m[32 + i] : 0.f; }
     const int lane = threadIdx.x & 31;
     const float t0 = c1_transpose_sum(lo32, lane), t1 = c1_transpose_sum(hi32, lane);
-    atomicAdd(&s_m[lane], t0);
-    if (32 + lane < N_MOM) atomicAdd(&s_m[32 + lane], t1);
+    s_m[threadIdx.x >> 5][lane] = t0;
+    s_m[threadIdx.x >> 5][32 + lane] = t1;
     __syncthreads();
-    if (threadIdx.x < N_MOM) atomicAdd(mom + threadIdx.x, (double)s_m[threadIdx.x]);
+    if (threadIdx.x < N_MOM) {
+        double tot = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) tot += (double)s_m[wv][threadIdx.x];
+        atomicAdd(mom + threadIdx.x, tot);       // double: the order of the blocks matters only below fp32 resolution
+    }
 }
 
 // stats[co] = sum y, stats[64 + co] = sum y^2 (the layout tag_bn_finalize reads) from the moments, in double

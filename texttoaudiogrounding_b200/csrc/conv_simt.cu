@@ -30,7 +30,7 @@ conv_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, TO* __res
     constexpr int B_LOADS = (BN * BK / 4) / NTHREADS;   // float4 loads per thread for B
     __shared__ __align__(16) float As[BK][BM];
     __shared__ __align__(16) float Bs[BK][BN];
-    __shared__ float s_sum[BN], s_sq[BN];
+    __shared__ float s_sum[NTHREADS / 32][BN], s_sq[NTHREADS / 32][BN];     // per-warp totals (every warp covers all BN columns)
 
     const int tid = threadIdx.x;
     const long M = (long)B * H * W;
@@ -128,10 +128,6 @@ conv_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, TO* __res
     }
 
     // ---- epilogue: bias / relu / round / per-channel statistics / store
-    if (stats != nullptr) {
-        if (tid < BN) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
-        __syncthreads();
-    }
 #pragma unroll
     for (int jj = 0; jj < TN / 4; ++jj) {
         const int nl = jj * 64 + tn * 4;
@@ -160,9 +156,9 @@ conv_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, TO* __res
             for (int e = 0; e < 4; ++e) {
                 float sv = cs[e] + __shfl_xor_sync(0xffffffffu, cs[e], 16);
                 float qv = cq[e] + __shfl_xor_sync(0xffffffffu, cq[e], 16);
-                if ((tid & 31) < 16) {
-                    atomicAdd(&s_sum[nl + e], sv);
-                    atomicAdd(&s_sq[nl + e], qv);
+                if ((tid & 31) < 16) {                 // written, not accumulated: summed in warp order below
+                    s_sum[tid >> 5][nl + e] = sv;
+                    s_sq[tid >> 5][nl + e] = qv;
                 }
             }
         }
@@ -170,8 +166,11 @@ conv_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, TO* __res
     if (stats != nullptr) {
         __syncthreads();
         if (tid < BN) {
-            atomicAdd(stats + n0 + tid, (double)s_sum[tid]);
-            atomicAdd(stats + Cout + n0 + tid, (double)s_sq[tid]);
+            double ts = 0.0, tq = 0.0;
+#pragma unroll
+            for (int wv = 0; wv < NTHREADS / 32; ++wv) { ts += (double)s_sum[wv][tid]; tq += (double)s_sq[wv][tid]; }
+            atomicAdd(stats + n0 + tid, ts);
+            atomicAdd(stats + Cout + n0 + tid, tq);
         }
     }
 }
